@@ -1,0 +1,55 @@
+/*
+ * panda_debug.h -- diagnostic entry points of libpanda-cuda (B200 implementation).  Not part of the reference's
+ * ABI; used by tests/ (to check the device field / curve arithmetic against the oracle one operation at a time)
+ * and by bench.py (per-stage timings, integer-pipe peak).  All pointers are DEVICE pointers unless noted.
+ */
+#ifndef PANDA_DEBUG_H
+#define PANDA_DEBUG_H
+
+#include "panda_interface.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* field ids: 0 BN254 Fq, 1 BN254 Fr, 2 BLS12-377 Fq, 3 BLS12-377 Fr (same numbering as oracle/panda_oracle.c) */
+enum panda_debug_field_opcode {
+    PANDA_FOP_MUL = 0, PANDA_FOP_ADD = 1, PANDA_FOP_SUB = 2, PANDA_FOP_SQR = 3, PANDA_FOP_FROM_MONT = 4,
+    PANDA_FOP_TO_MONT = 5, PANDA_FOP_INV = 6, PANDA_FOP_NEG = 7
+};
+/* out[i] = a[i] (op) b[i], canonical Montgomery limbs; b is ignored by unary ops */
+panda_error panda_debug_field_op(int field_id, int op, const void *a, const void *b, void *out, size_t count, panda_stream stream);
+
+/* curve ids: 0 BN254, 1 BLS12-377.  Points are Jacobian triples (x||y||z) except q of MADD (affine x||y). */
+enum panda_debug_curve_opcode {
+    PANDA_COP_MADD = 0,        /* out = p + q(affine), through the XYZZ mixed addition the MSM uses */
+    PANDA_COP_ADD = 1,         /* out = p + q, through the XYZZ addition */
+    PANDA_COP_DBL_XYZZ = 2,    /* out = 2p, XYZZ doubling */
+    PANDA_COP_DBL_JAC = 3,     /* out = 2p, Jacobian dbl-2009-l */
+    PANDA_COP_TO_HOMOGENEOUS = 4
+};
+panda_error panda_debug_curve_op(int curve_id, int op, const void *p, const void *q, void *out, size_t count, panda_stream stream);
+
+typedef struct panda_debug_msm_plan_info {
+    unsigned window_bits, windows, buckets_per_window, segment_len, segments_per_window, reduce_chunk;
+    size_t workspace_bytes;
+} panda_debug_msm_plan_info;
+/* the plan msm_execute would use for n points (c_override / seg_override = 0: automatic) */
+panda_error panda_debug_msm_plan(int curve_id, size_t n, unsigned c_override, unsigned seg_override, panda_debug_msm_plan_info *out);
+
+/* MSM with explicit window width / segment length and per-stage device times.
+ * stage_ms (HOST float[7], may be NULL): digits, scan, scatter, accumulate, bucket_reduce, window_reduce, final.
+ * Synchronises the stream when stage_ms != NULL. */
+panda_error panda_debug_msm_timed(int curve_id, const panda_msm_configuration cfg, size_t n, unsigned c_override, unsigned seg_override,
+                                  float *stage_ms);
+
+/* Integer-pipe microbenchmarks on the current device (synchronous).
+ * kind 0: independent IMAD (32-bit) chains, 1: independent IMAD.WIDE chains, 2: Montgomery products (BN254 Fq) in
+ * 4 independent chains per thread.  Fills *ms (device time of the timed launch) and *ops (instructions of that kind /
+ * modular products executed). */
+panda_error panda_debug_int_peak(int kind, unsigned iters, float *ms, unsigned long long *ops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANDA_DEBUG_H */

@@ -1,0 +1,162 @@
+/*
+ * panda_interface.h -- C ABI of libpanda-cuda (B200 / sm_100a implementation).
+ *
+ * Drop-in for the reference's src/cuda/core/panda_interface.cuh:10-110, i.e. exactly the symbols the Rust side
+ * binds in src/gpu_ffi/binding.rs:3-115 with the #[repr(C)] types of src/gpu_ffi/common.rs:40-208.
+ * Plain pointers and sizes only; every function returns panda_error: 0 on success, otherwise the raw
+ * cudaError_t value (reference convention, panda_interface.cu:11-191; Rust only tests `!= 0`).
+ *
+ * Device pointers are owned by the caller.  Inputs (bases, scalars, d_src when the result lands in d_dst)
+ * are never written: the reference converts scalars in place (msm_cuda.cuh:155, msm_host.cuh:293-296) and
+ * thereby corrupts cached scalars on their second use -- this implementation does not.
+ * MSM execution is asynchronous on cfg.stream (the Rust caller records + syncs an event on it afterwards,
+ * gpu_manager/unit.rs:60-62); temporaries are allocated stream-ordered from cfg.mem_pool.
+ * All calls act on the calling thread's current device (the reference hard-codes device 0,
+ * msm_cuda.cuh:554-555).
+ */
+#ifndef PANDA_INTERFACE_H
+#define PANDA_INTERFACE_H
+
+#include <stddef.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* panda_interface.cuh:10-16 */
+typedef enum panda_error {
+    panda_success = 0,
+    panda_error_invalid_value = 1,
+    panda_error_memory_allocation = 2,
+    panda_error_not_ready = 600
+} panda_error;
+
+/* panda_interface.cuh:18-31; gpu_ffi/common.rs:40-44, 89-93, 134-138 -- raw cudaStream_t / cudaEvent_t / cudaMemPool_t, by value */
+typedef struct panda_stream { void *handle; } panda_stream;
+typedef struct panda_event { void *handle; } panda_event;
+typedef struct panda_mem_pool { void *handle; } panda_mem_pool;
+
+/* panda_interface.cuh:33-37; gpu_ffi/common.rs:168-173 */
+typedef enum panda_msm_result_coordinate_type {
+    JACOBIAN = 0,   /* (X, Y, Z), x = X/Z^2, y = Y/Z^3 -- what arkworks' G1Projective::new expects (tests/test.rs:87-102) */
+    PROJECTIVE      /* homogeneous (X*Z, Y, Z^3), projective.cuh:66-77 */
+} panda_msm_result_coordinate_type;
+
+typedef void (*panda_host_fn)(void *user_data);
+
+/* ---- device / stream / event / memory plumbing: panda_interface.cuh:40-68, panda_interface.cu:11-150 ---- */
+panda_error panda_get_device_number(int *count);
+panda_error panda_get_device(int *device_id);
+panda_error panda_set_device(int device_id);
+panda_error panda_stream_create(panda_stream *stream, bool blocking_sync);
+panda_error panda_stream_wait_event(panda_stream stream, panda_event event);
+panda_error panda_stream_sync(panda_stream stream);          /* spelling defined by the reference C side (panda_interface.cu:36-39) */
+panda_error panda_stream_synchronize(panda_stream stream);   /* spelling the Rust side links against (binding.rs:14); undefined in the reference */
+panda_error panda_stream_query(panda_stream stream);         /* binding.rs:16; declared but undefined in the reference */
+panda_error panda_stream_destroy(panda_stream stream);
+panda_error panda_launch_host_fn(panda_stream stream, panda_host_fn fn, void *user_data);
+panda_error panda_event_create(panda_event *event, bool blocking_sync, bool disable_timing);
+panda_error panda_event_record(panda_event event, panda_stream stream);
+panda_error panda_event_sync(panda_event event);
+panda_error panda_event_query(panda_event event);
+panda_error panda_event_destroy(panda_event event);
+panda_error panda_mem_get_info(size_t *free, size_t *total);
+panda_error panda_malloc(void **ptr, size_t size);
+panda_error panda_malloc_host(void **ptr, size_t size);
+panda_error panda_free(void *ptr);
+panda_error panda_free_host(void *ptr);
+panda_error panda_host_register(void *ptr, size_t size);
+panda_error panda_host_unregister(void *ptr);
+panda_error panda_device_disable_peer_access(int device_id); /* binding.rs:54; undefined in the reference */
+panda_error panda_device_enable_peer_access(int device_id);  /* binding.rs:56; undefined in the reference */
+panda_error panda_memcpy(void *dst, const void *src, size_t count);
+panda_error panda_memcpy_async(void *dst, const void *src, size_t count, panda_stream stream);
+panda_error panda_memset(void *ptr, int value, size_t count);
+panda_error panda_memset_async(void *ptr, int value, size_t count, panda_stream stream);
+panda_error panda_mem_pool_create(panda_mem_pool *pool, int device_id);
+panda_error panda_mem_pool_destroy(panda_mem_pool pool);
+panda_error panda_malloc_from_pool_async(void **ptr, size_t size, panda_mem_pool pool, panda_stream stream);
+panda_error panda_free_async(void *ptr, panda_stream stream);
+
+/* ---- MSM: panda_interface.cuh:70-84; gpu_ffi/common.rs:175-185 (48 bytes, passed by value) ---- */
+typedef struct panda_msm_configuration {
+    panda_mem_pool mem_pool;        /* pool for the execution's temporaries (NULL handle: the device's default pool) */
+    panda_stream stream;            /* stream the execution is ordered on */
+    void *bases;                    /* device: 2^log_scalars_count affine points, x||y, Fq Montgomery LE; x == 0 <=> identity */
+    void *scalars;                  /* device: 2^log_scalars_count x 32 B, Fr Montgomery LE */
+    void *results;                  /* device: 3 Fq elements (96 B BN254, 144 B BLS12-377), Montgomery, canonical */
+    unsigned log_scalars_count;
+    panda_msm_result_coordinate_type msm_result_coordinate_type;
+} panda_msm_configuration;
+typedef panda_msm_configuration msm_configuration;
+
+panda_error panda_msm_setup_bn254(void);
+panda_error panda_msm_execute_bn254(const panda_msm_configuration exec_cfg);
+/* Reference: CPU debug path taking HOST pointers for bases / scalars / results (msm_host.cuh:267-370).
+ * Here the same contract (host pointers in, 96-byte Jacobian/projective result out, synchronous) is served by
+ * staging through the device; the host buffers are not modified. */
+panda_error panda_msm_execute_bn254_host(const panda_msm_configuration exec_cfg);
+panda_error panda_msm_tear_down(void);
+
+/* ---- NTT: panda_interface.cuh:86-110; gpu_ffi/common.rs:187-208 ---- */
+typedef struct panda_ntt_configuration {
+    panda_mem_pool mem_pool;
+    panda_stream stream;
+    void *d_src;                    /* device: 2^log_n Fr elements, Montgomery LE, natural order */
+    void *d_dst;                    /* device: scratch / output buffer of the same size */
+    unsigned log_n;
+    void *flag;                     /* HOST unsigned*: written before return; 0 -> result in d_src, 1 -> result in d_dst */
+} panda_ntt_configuration;
+typedef panda_ntt_configuration ntt_configuration;
+
+typedef struct panda_ntt_configuration_v1 {
+    panda_mem_pool mem_pool;
+    panda_stream stream;
+    void *d_src;
+    void *d_dst;
+    void *d_omega;                  /* HOST pointer to the 2^log_n-th root of unity (32 B, Montgomery) -- unit.rs:507-518 */
+    unsigned log_n;
+    void *flag;
+} panda_ntt_configuration_v1;
+typedef panda_ntt_configuration_v1 ntt_configuration_v1;
+
+/* input_omega: HOST pointer to omega for the transform size the caller is going to use (wrapper.rs:199-210). */
+panda_error panda_ntt_setup_bn254(void *input_omega);
+/* Forward DFT y[j] = sum_i x[i] * omega^(i*j), natural order in and out, no scaling (the function the reference's
+ * disabled radix_fft text describes, fft.cu:107-169).  *flag = ceil(log_n / 8) & 1 as in fft.cu:193-211. */
+panda_error panda_ntt_execute_bn254(panda_ntt_configuration exec_cfg);
+panda_error panda_ntt_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cfg);
+panda_error panda_ntt_tear_down(void);
+
+/* ---- additions the configs in BASELINE.json need; no reference precedent, same naming pattern ---- */
+
+/* BLS12-377 G1: bases 96 B (x||y, 12 x u32 each), scalars 32 B (Fr, 253 bit), result 144 B. */
+panda_error panda_msm_setup_bls12_377(void);
+panda_error panda_msm_execute_bls12_377(const panda_msm_configuration exec_cfg);
+
+/* MSM over an arbitrary point count (a shard of a larger MSM): like panda_msm_execute_* but n need not be a
+ * power of two; cfg.log_scalars_count is ignored. */
+panda_error panda_msm_execute_bn254_n(const panda_msm_configuration exec_cfg, size_t n);
+panda_error panda_msm_execute_bls12_377_n(const panda_msm_configuration exec_cfg, size_t n);
+
+/* Sum `count` Jacobian partial results (device, count x 96 B / 144 B; e.g. the all-gathered per-GPU results of an
+ * MSM sharded by point range) into `result` (device) in the requested coordinates.  Asynchronous on `stream`. */
+panda_error panda_msm_combine_bn254(const void *partials, unsigned count, void *result,
+                                    panda_msm_result_coordinate_type coord, panda_stream stream);
+panda_error panda_msm_combine_bls12_377(const void *partials, unsigned count, void *result,
+                                        panda_msm_result_coordinate_type coord, panda_stream stream);
+
+/* Inverse transform: x = (1/n) * DFT_{omega^-1}(y); omega is the FORWARD root (host pointer), same flag contract. */
+panda_error panda_intt_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cfg);
+
+/* Library identification: "panda-b200 <version> sm_100a". */
+const char *panda_version(void);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* PANDA_INTERFACE_H */

@@ -1,0 +1,316 @@
+// field.cuh -- Montgomery prime-field arithmetic on 32-bit limbs for sm_100a (IMAD pipe).
+//
+// Replaces the reference's Field<CONFIG> (src/cuda/core/field/field.cuh:139-257 montmul, :81-137 add/sub/reduce,
+// :566-619 to/from_montgomery, :925-972 inverse) and its parameter structs (curve/bn254/paramter.cuh,
+// curve/bls12_377/paramter.cuh).  Same wire format: N little-endian u32 limbs, Montgomery form with
+// R = 2^(32N).  Differences by design:
+//   * values live in the redundant range [0, 2p) between operations ("lazy reduction"): the Montgomery
+//     product of two values < 2p is again < 2p for every modulus here (4p < R), so mul has no final
+//     conditional subtraction; add/sub fold by 2p.  canon() gives the unique residue in [0,p) and is
+//     applied wherever bytes leave the device or values are compared.
+//   * the product and the reduction are interleaved row by row over two column accumulators whose 64-bit
+//     (lo,hi) pairs sit on even / odd limb boundaries, so that every 32x32->64 multiply-accumulate is one
+//     carry-chained IMAD.WIDE (2N^2 + N of them per product: 136 for N = 8, 300 for N = 12).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pb {
+
+#define PB_DEV __device__ __forceinline__
+
+namespace ptx {
+// carry-flag (CC.CF) arithmetic; one PTX instruction per statement, chained through the flag register.
+PB_DEV uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PB_DEV uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PB_DEV uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PB_DEV uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PB_DEV uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PB_DEV uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PB_DEV uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+PB_DEV uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// full 64-bit product as one IMAD.WIDE
+PB_DEV void mul_wide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+// d = a*b (lo / hi half) + c [+ CF]
+PB_DEV uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+PB_DEV uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+PB_DEV uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+PB_DEV uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+}  // namespace ptx
+
+// ---------------------------------------------------------------------------------------------------
+// Field parameters.  limb(i) is constexpr so that fully unrolled code sees immediates.
+// Values re-derived from the moduli (tests/test_constants.py) and equal to the reference's tables:
+//   bn254/paramter.cuh:18-25,96-123 (Fq), :134-141,212-239 (Fr); bls12_377/paramter.cuh:19-60,134-172.
+
+struct Bn254Fq {
+    static constexpr int N = 8;
+    static constexpr int BITS = 254;
+    static constexpr uint32_t NINV = 0xe4866389u;   // -p^-1 mod 2^32
+    PB_DEV static constexpr uint32_t mod(int i) {
+        constexpr uint32_t v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t one(int i) {   // R mod p
+        constexpr uint32_t v[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t r2(int i) {    // R^2 mod p
+        constexpr uint32_t v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return v[i];
+    }
+};
+
+struct Bn254Fr {
+    static constexpr int N = 8;
+    static constexpr int BITS = 254;
+    static constexpr uint32_t NINV = 0xefffffffu;
+    PB_DEV static constexpr uint32_t mod(int i) {
+        constexpr uint32_t v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t one(int i) {
+        constexpr uint32_t v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t r2(int i) {
+        constexpr uint32_t v[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return v[i];
+    }
+};
+
+struct Bls377Fq {
+    static constexpr int N = 12;
+    static constexpr int BITS = 377;
+    static constexpr uint32_t NINV = 0xffffffffu;
+    PB_DEV static constexpr uint32_t mod(int i) {
+        constexpr uint32_t v[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu,
+                                    0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t one(int i) {
+        constexpr uint32_t v[12] = {0xffffff68u, 0x02cdffffu, 0x7fffffb1u, 0x51409f83u, 0x8a7d3ff2u, 0x9f7db3a9u,
+                                    0x6e7c6305u, 0x7b4e97b7u, 0x803c84e8u, 0x4cf495bfu, 0xe2fdf49au, 0x008d6661u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t r2(int i) {
+        constexpr uint32_t v[12] = {0x9400cd22u, 0xb786686cu, 0xb00431b1u, 0x0329fcaau, 0x62d6b46du, 0x22a5f111u,
+                                    0x827dc3acu, 0xbfdf7d03u, 0x41790bf9u, 0x837e92f0u, 0x1e914b88u, 0x006dfccbu};
+        return v[i];
+    }
+};
+
+struct Bls377Fr {
+    static constexpr int N = 8;
+    static constexpr int BITS = 253;
+    static constexpr uint32_t NINV = 0xffffffffu;
+    PB_DEV static constexpr uint32_t mod(int i) {
+        constexpr uint32_t v[8] = {0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu, 0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t one(int i) {
+        constexpr uint32_t v[8] = {0xfffffff3u, 0x7d1c7fffu, 0x6ffffff2u, 0x7257f50fu, 0x512c0feeu, 0x16d81575u, 0x2bbb9a9du, 0x0d4bda32u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t r2(int i) {
+        constexpr uint32_t v[8] = {0xb861857bu, 0x25d577bau, 0x8860591fu, 0xcc2c27b5u, 0xe5dc8593u, 0xa7cc008fu, 0xeff1c939u, 0x011fdae7u};
+        return v[i];
+    }
+};
+
+// 2p limb i (p < 2^(32N-1) for every field here, so 2p fits N limbs)
+template <class P>
+PB_DEV constexpr uint32_t mod2(int i) {
+    return (P::mod(i) << 1) | (i ? (P::mod(i - 1) >> 31) : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+
+template <class P>
+struct Fe {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+
+    PB_DEV static Fe zero() { Fe r; _Pragma("unroll") for (int i = 0; i < N; i++) r.l[i] = 0; return r; }
+    PB_DEV static Fe one() { Fe r; _Pragma("unroll") for (int i = 0; i < N; i++) r.l[i] = P::one(i); return r; }
+    PB_DEV static Fe r2() { Fe r; _Pragma("unroll") for (int i = 0; i < N; i++) r.l[i] = P::r2(i); return r; }
+
+    // vectorised global access (16-byte aligned pointers; N is a multiple of 4)
+    PB_DEV static Fe load(const void *ptr) {
+        Fe r;
+        const uint4 *q = reinterpret_cast<const uint4 *>(ptr);
+        _Pragma("unroll") for (int i = 0; i < N / 4; i++) {
+            uint4 v = __ldg(q + i);
+            r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+        }
+        return r;
+    }
+    PB_DEV static Fe load_plain(const void *ptr) {   // for memory written earlier by the same grid / stream (no nc path)
+        Fe r;
+        const uint4 *q = reinterpret_cast<const uint4 *>(ptr);
+        _Pragma("unroll") for (int i = 0; i < N / 4; i++) {
+            uint4 v = q[i];
+            r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+        }
+        return r;
+    }
+    PB_DEV void store(void *ptr) const {
+        uint4 *q = reinterpret_cast<uint4 *>(ptr);
+        _Pragma("unroll") for (int i = 0; i < N / 4; i++) q[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+    }
+
+    PB_DEV bool is_zero_raw() const { uint32_t t = 0; _Pragma("unroll") for (int i = 0; i < N; i++) t |= l[i]; return t == 0; }
+    // value == 0 (mod p) for a lazily reduced element: raw 0 or raw p
+    PB_DEV bool is_zero() const {
+        uint32_t t0 = 0, t1 = 0;
+        _Pragma("unroll") for (int i = 0; i < N; i++) { t0 |= l[i]; t1 |= l[i] ^ P::mod(i); }
+        return t0 == 0 || t1 == 0;
+    }
+
+    // [0,2p) -> [0,p)
+    PB_DEV Fe canon() const {
+        Fe t;
+        t.l[0] = ptx::sub_cc(l[0], P::mod(0));
+        _Pragma("unroll") for (int i = 1; i < N; i++) t.l[i] = ptx::subc_cc(l[i], P::mod(i));
+        uint32_t borrow = ptx::subc(0, 0);   // 0 or 0xffffffff
+        Fe r;
+        _Pragma("unroll") for (int i = 0; i < N; i++) r.l[i] = borrow ? l[i] : t.l[i];
+        return r;
+    }
+
+    // a + b, folded to [0,2p)
+    PB_DEV friend Fe operator+(const Fe &a, const Fe &b) {
+        Fe s, t;
+        s.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+        _Pragma("unroll") for (int i = 1; i < N - 1; i++) s.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+        s.l[N - 1] = ptx::addc(a.l[N - 1], b.l[N - 1]);
+        t.l[0] = ptx::sub_cc(s.l[0], mod2<P>(0));
+        _Pragma("unroll") for (int i = 1; i < N; i++) t.l[i] = ptx::subc_cc(s.l[i], mod2<P>(i));
+        uint32_t borrow = ptx::subc(0, 0);
+        Fe r;
+        _Pragma("unroll") for (int i = 0; i < N; i++) r.l[i] = borrow ? s.l[i] : t.l[i];
+        return r;
+    }
+    // a - b, folded to [0,2p)
+    PB_DEV friend Fe operator-(const Fe &a, const Fe &b) {
+        Fe d;
+        d.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+        _Pragma("unroll") for (int i = 1; i < N; i++) d.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+        uint32_t borrow = ptx::subc(0, 0);
+        Fe r;
+        r.l[0] = ptx::add_cc(d.l[0], borrow & mod2<P>(0));
+        _Pragma("unroll") for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(d.l[i], borrow & mod2<P>(i));
+        r.l[N - 1] = ptx::addc(d.l[N - 1], borrow & mod2<P>(N - 1));
+        return r;
+    }
+    PB_DEV Fe dbl() const { return *this + *this; }
+    // -a in [0,2p):  2p - a  (a == 0 gives 2p ... folded back to 0 by the compare below)
+    PB_DEV Fe neg() const { return zero() - *this; }
+
+    // Montgomery product, inputs < 2p, output < 2p.
+    PB_DEV friend Fe operator*(const Fe &a, const Fe &b) {
+        // Two accumulators.  In the frame of the current row, A holds limb positions 0..N-1 as pairs
+        // (0,1),(2,3),..  and B holds positions 1..N as pairs (1,2),(3,4),..   After the reduction step
+        // A[0] == 0; dividing by 2^32 turns B into the even-aligned accumulator and A (shifted by two
+        // limbs) into the odd-aligned one, so the two arrays swap roles every row.
+        uint32_t A[N], B[N];
+        const uint32_t *al = a.l;
+        {   // row 0: plain products
+            const uint32_t bi = b.l[0];
+            _Pragma("unroll") for (int j = 0; j < N; j += 2) {
+                ptx::mul_wide(A[j], A[j + 1], al[j], bi);
+                ptx::mul_wide(B[j], B[j + 1], al[j + 1], bi);
+            }
+            reduce_row(A, B);
+        }
+        _Pragma("unroll") for (int i = 1; i < N; i++) {
+            const uint32_t bi = b.l[i];
+            if (i & 1) { mul_row(B, A, al, bi); reduce_row(B, A); }
+            else       { mul_row(A, B, al, bi); reduce_row(A, B); }
+        }
+        // The last row (i = N-1, odd) left B even-aligned with B[0] == 0 and A odd-aligned:
+        // result = (B + (A << 32)) >> 32 = A + (B >> 32)
+        Fe r;
+        r.l[0] = ptx::add_cc(A[0], B[1]);
+        _Pragma("unroll") for (int k = 1; k < N - 1; k++) r.l[k] = ptx::addc_cc(A[k], B[k + 1]);
+        r.l[N - 1] = ptx::addc(A[N - 1], 0);
+        return r;
+    }
+    PB_DEV Fe sqr() const { return *this * *this; }
+
+    // Montgomery -> canonical integer (multiply by 1): reduction rows only.  Output canonical.
+    PB_DEV Fe from_mont() const {
+        Fe o = zero(); o.l[0] = 1;
+        return (*this * o).canon();
+    }
+    PB_DEV Fe to_mont() const { return *this * r2(); }
+
+private:
+    // E: even-aligned accumulator (positions 0..N-1), O: odd-aligned (positions 1..N).
+    // Adds m*p with m chosen so that E[0] becomes 0.
+    PB_DEV static void reduce_row(uint32_t *E, uint32_t *O) {
+        const uint32_t m = ptx::mul_lo(E[0], P::NINV);
+        O[0] = ptx::mad_lo_cc(P::mod(1), m, O[0]);
+        O[1] = ptx::madc_hi_cc(P::mod(1), m, O[1]);
+        _Pragma("unroll") for (int j = 2; j < N; j += 2) {
+            O[j] = ptx::madc_lo_cc(P::mod(j + 1), m, O[j]);
+            O[j + 1] = ptx::madc_hi_cc(P::mod(j + 1), m, O[j + 1]);
+        }
+        E[0] = ptx::mad_lo_cc(P::mod(0), m, E[0]);
+        E[1] = ptx::madc_hi_cc(P::mod(0), m, E[1]);
+        _Pragma("unroll") for (int j = 2; j < N; j += 2) {
+            E[j] = ptx::madc_lo_cc(P::mod(j), m, E[j]);
+            E[j + 1] = ptx::madc_hi_cc(P::mod(j), m, E[j + 1]);
+        }
+        O[N - 1] = ptx::addc(O[N - 1], 0);
+    }
+    // Entering a new row: Y was odd-aligned, Z was even-aligned with Z[0] == 0.  Divide by 2^32:
+    // Y becomes the even accumulator, Z (dropping two limbs) the odd one; Z[1] folds into Y[0].
+    // Then add a * bi.
+    PB_DEV static void mul_row(uint32_t *Y, uint32_t *Z, const uint32_t *a, uint32_t bi) {
+        Y[0] = ptx::add_cc(Y[0], Z[1]);
+        _Pragma("unroll") for (int j = 0; j < N - 2; j += 2) {
+            Z[j] = ptx::madc_lo_cc(a[j + 1], bi, Z[j + 2]);
+            Z[j + 1] = ptx::madc_hi_cc(a[j + 1], bi, Z[j + 3]);
+        }
+        Z[N - 2] = ptx::madc_lo_cc(a[N - 1], bi, 0);
+        Z[N - 1] = ptx::madc_hi(a[N - 1], bi, 0);
+        Y[0] = ptx::mad_lo_cc(a[0], bi, Y[0]);
+        Y[1] = ptx::madc_hi_cc(a[0], bi, Y[1]);
+        _Pragma("unroll") for (int j = 2; j < N; j += 2) {
+            Y[j] = ptx::madc_lo_cc(a[j], bi, Y[j]);
+            Y[j + 1] = ptx::madc_hi_cc(a[j], bi, Y[j + 1]);
+        }
+        Z[N - 1] = ptx::addc(Z[N - 1], 0);
+    }
+};
+
+// a == b (mod p) for lazily reduced operands
+template <class P>
+PB_DEV bool fe_equal(const Fe<P> &a, const Fe<P> &b) { return (a - b).is_zero(); }
+
+// a^-1 by Fermat (a^(p-2)); Montgomery in / out.  Only used once per result (affine normalisation in tests
+// and utilities), never in a hot loop -- the reference's binary GCD (field.cuh:925-972) is not needed.
+template <class P>
+PB_DEV Fe<P> fe_inverse(const Fe<P> &a) {
+    Fe<P> acc = Fe<P>::one(), base = a;
+    // exponent p - 2, bit by bit (p odd, p - 2 only changes limb 0 unless mod(0) < 2, which never happens)
+    #pragma unroll 1
+    for (int i = 0; i < P::BITS; i++) {
+        uint32_t limb = 0;
+        #pragma unroll
+        for (int k = 0; k < P::N; k++) if (k == (i >> 5)) limb = P::mod(k) - (k == 0 ? 2u : 0u);
+        if ((limb >> (i & 31)) & 1) acc = acc * base;
+        base = base.sqr();
+    }
+    return acc;
+}
+
+using FqBn254 = Fe<Bn254Fq>;
+using FrBn254 = Fe<Bn254Fr>;
+using FqBls377 = Fe<Bls377Fq>;
+using FrBls377 = Fe<Bls377Fr>;
+
+}  // namespace pb

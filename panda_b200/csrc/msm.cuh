@@ -1,0 +1,46 @@
+// msm.cuh -- Pippenger multi-scalar multiplication pipeline for sm_100a (internal interface).
+//
+// Replaces the reference's msm_execute_cuda and its kernels (src/cuda/core/unit/msm/msm_cuda.cuh:552-769,
+// kernels :148-282, :373-497; host Horner :59-77).  See DESIGN.md for the data layout and the per-kernel
+// rooflines.  Everything runs on the caller's stream, temporaries come from the caller's memory pool
+// (stream-ordered), inputs are never written (the reference converts scalars in place, msm_cuda.cuh:155).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pb {
+
+enum CurveId { CURVE_BN254 = 0, CURVE_BLS12_377 = 1 };
+enum CoordType { COORD_JACOBIAN = 0, COORD_PROJECTIVE = 1 };   // curve.cuh:23-27
+
+struct MsmPlan {
+    uint32_t n;            // points
+    uint32_t c;            // window width in bits (signed digits), 1 <= c <= 16
+    uint32_t windows;      // W
+    uint32_t nb;           // buckets per window = 2^(c-1)
+    uint32_t seg_len;      // L: sorted entries handled by one accumulation thread
+    uint32_t segs_pw;      // ceil(n / L) segments per window
+    uint32_t chunk;        // m: buckets folded serially by one reduction thread
+    uint32_t chunks_pw;    // nb / m
+    // workspace layout (byte offsets into one arena)
+    size_t off_counts, off_offsets, off_cursor, off_digits, off_sorted, off_slots, off_chunks, off_wsums, bytes;
+};
+
+// window width / segment length selection; c_override = 0 -> cost model
+MsmPlan msm_make_plan(CurveId curve, uint32_t n, uint32_t c_override, uint32_t seg_override);
+
+// Per-stage device timings (ms) filled when msm_run is called with timings != nullptr (adds event syncs;
+// the benchmark harness uses it to attribute time to kernels -- never set on the product path).
+struct MsmStageTimes { float digits, scan, scatter, accumulate, bucket_reduce, window_reduce, final; };
+
+// bases: n affine points (x||y Montgomery), scalars: n x 32 B (Montgomery), result: 3 field elements.
+// pool may be nullptr (default pool).  Asynchronous on `stream`.
+cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result,
+                    CoordType coord, cudaMemPool_t pool, cudaStream_t stream,
+                    uint32_t c_override = 0, uint32_t seg_override = 0, MsmStageTimes *timings = nullptr);
+
+// result = sum of `count` Jacobian partials (the per-GPU results of a sharded MSM), then coordinate conversion.
+cudaError_t msm_combine(CurveId curve, const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream);
+
+}  // namespace pb

@@ -1,0 +1,422 @@
+// msm_impl.cuh -- kernels and templated driver of the Pippenger MSM (see msm.cu for the overview).
+// Instantiated once per curve in msm_bn254.cu / msm_bls12_377.cu so the two compile in parallel.
+#pragma once
+#include "msm.cuh"
+#include "ec.cuh"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace pb {
+
+struct Bn254 {
+    using Fq = Fe<Bn254Fq>;
+    using Fr = Fe<Bn254Fr>;
+    static constexpr int SCALAR_BITS = 254;
+};
+struct Bls377 {
+    using Fq = Fe<Bls377Fq>;
+    using Fr = Fe<Bls377Fr>;
+    static constexpr int SCALAR_BITS = 253;
+};
+
+static constexpr uint32_t DIGIT_SKIP = 0xFFFFu;     // digit 0: contributes nothing
+static constexpr int ACC_THREADS = 128;
+static constexpr int RED_THREADS = 128;
+static constexpr int WIN_THREADS = 256;
+
+// ----------------------------------------------------------------------------------------------------
+// K1: scalars -> signed window digits (window-major, 16 bit) + per-(window,bucket) counts.
+// HBM-bound: 32 B read + 2W B written per scalar, W reductions into an L2-resident histogram.
+
+template <class C>
+__global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb,
+                                                uint16_t *__restrict__ digits, uint32_t *__restrict__ counts) {
+    using Fr = typename C::Fr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; input untouched
+        uint32_t carry = 0;
+        const uint32_t mask = (1u << c) - 1;
+        for (uint32_t w = 0; w < W; w++) {
+            uint32_t v = (s.l[0] & mask) + carry;
+#pragma unroll
+            for (int k = 0; k < Fr::N - 1; k++) s.l[k] = __funnelshift_r(s.l[k], s.l[k + 1], c);
+            s.l[Fr::N - 1] >>= c;
+            uint32_t mag = v, neg = 0;
+            carry = 0;
+            if (w + 1 < W && v > nb) { mag = (1u << c) - v; neg = 1; carry = 1; }
+            uint32_t code = mag ? ((mag - 1) | (neg << 15)) : DIGIT_SKIP;
+            digits[(size_t)w * n + i] = (uint16_t)code;
+            if (mag) atomicAdd(&counts[(size_t)w * nb + (mag - 1)], 1u);
+        }
+    }
+}
+
+// K2: per-window exclusive scan of the bucket counts -> offsets[w][0..nb], cursor[w][0..nb-1].
+static __global__ void __launch_bounds__(1024) k_scan(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t *__restrict__ offsets,
+                                               uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t *cw = counts + (size_t)w * nb;
+    uint32_t *ow = offsets + (size_t)w * (nb + 1);
+    uint32_t *kw = cursor + (size_t)w * nb;
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t idx = base + tid;
+        const uint32_t v = idx < nb ? cw[idx] : 0;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t t = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, t, o); if ((int)lane >= o) t += u; }
+            warp_tot[lane] = t;
+        }
+        __syncthreads();
+        const uint32_t excl = running + (warp ? warp_tot[warp - 1] : 0) + incl - v;
+        if (idx < nb) { ow[idx] = excl; kw[idx] = excl; }
+        running += warp_tot[31];
+        __syncthreads();
+    }
+    if (tid == 0) ow[nb] = running;
+}
+
+// K3: scatter point indices (with the digit's sign in bit 31) into their bucket's range.  blockIdx.y = window, so
+// one window's 4n-byte output range is being filled at a time and stays in L2 while it is written.
+static __global__ void __launch_bounds__(256) k_scatter(const uint16_t *__restrict__ digits, uint32_t n, uint32_t nb,
+                                                 uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+    const uint32_t w = blockIdx.y;
+    const uint16_t *dw = digits + (size_t)w * n;
+    uint32_t *kw = cursor + (size_t)w * nb;
+    uint32_t *sw = sorted + (size_t)w * n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t code = dw[i];
+        if (code == DIGIT_SKIP) continue;
+        const uint32_t pos = atomicAdd(&kw[code & 0x7FFFu], 1u);
+        sw[pos] = i | ((code >> 15) << 31);
+    }
+}
+
+// K4: bucket accumulation.  Thread (w, s) owns sorted entries [s*L, (s+1)*L) of window w -- a fixed amount
+// of work whatever the bucket sizes are -- and emits one partial sum per bucket it touches into slot
+// (s + bucket), which is unique and makes a bucket's partials contiguous.
+// IMAD-bound: 10 modmul = 1370 IMAD per entry; 4 B index + 64 B (96 B) gathered point read per entry.
+template <class C>
+__global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                                                           const uint32_t *__restrict__ offsets, uint32_t n, uint32_t nb, uint32_t L,
+                                                           uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
+    using Fq = typename C::Fq;
+    using Pt = Xyzz<Fq>;
+    using Af = Affine<Fq>;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (uint64_t)W * segs_pw) return;
+    const uint32_t w = (uint32_t)(gid / segs_pw), s = (uint32_t)(gid % segs_pw);
+    const uint32_t *ow = offsets + (size_t)w * (nb + 1);
+    const uint32_t cnt = __ldg(ow + nb);
+    const uint32_t start = s * L;
+    if (start >= cnt) return;
+    const uint32_t end = min(start + L, cnt);
+    const uint32_t *sw = sorted + (size_t)w * n;
+    uint8_t *slot_w = slots + ((size_t)w * ((size_t)segs_pw + nb) + s) * Pt::BYTES;
+
+    uint32_t lo = 0, hi = nb;          // largest b with offsets[b] <= start
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(ow + mid) <= start) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo;
+    uint32_t next_bd = __ldg(ow + b + 1);
+
+    Pt acc = Pt::identity();
+    uint32_t e_next = __ldg(sw + start);
+    Af p_next = Af::load(bases + (size_t)(e_next & 0x7FFFFFFFu) * Af::BYTES);
+#pragma unroll 1
+    for (uint32_t pos = start; pos < end; pos++) {
+        const uint32_t e = e_next;
+        Af p = p_next;
+        if (pos + 1 < end) {           // prefetch the next point while this one is being added
+            e_next = __ldg(sw + pos + 1);
+            p_next = Af::load(bases + (size_t)(e_next & 0x7FFFFFFFu) * Af::BYTES);
+        }
+        if (pos >= next_bd) {          // bucket boundary: emit the finished partial, skip empty buckets
+            acc.store(slot_w + (size_t)b * Pt::BYTES);
+            acc = Pt::identity();
+            do { b++; next_bd = __ldg(ow + b + 1); } while (pos >= next_bd);
+        }
+        if (p.is_identity()) continue; // affine identity <=> x == 0 (affine.cuh:72-75)
+        if (e >> 31) p.y = p.y.neg();
+        acc.madd(p.x, p.y);
+    }
+    acc.store(slot_w + (size_t)b * Pt::BYTES);
+}
+
+// K5: bucket combine + first level of the running-sum reduction.  Thread (w, t) folds buckets
+// [t*m, (t+1)*m) of window w from the top: B_j = sum of its partial slots, run += B_j, tri += run.
+// Emits Lc = sum_i (i+1) * B_{t*m+i} and Rc = sum_i B_{t*m+i}.
+template <class C>
+__global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ offsets,
+                                                              uint32_t nb, uint32_t L, uint32_t segs_pw, uint32_t W, uint32_t m,
+                                                              uint32_t chunks_pw, uint8_t *__restrict__ chunks) {
+    using Fq = typename C::Fq;
+    using Pt = Xyzz<Fq>;
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= W * chunks_pw) return;
+    const uint32_t w = gid / chunks_pw, t = gid % chunks_pw;
+    const uint32_t *ow = offsets + (size_t)w * (nb + 1);
+    const uint8_t *slot_w = slots + (size_t)w * ((size_t)segs_pw + nb) * Pt::BYTES;
+    Pt run = Pt::identity(), tri = Pt::identity();
+#pragma unroll 1
+    for (uint32_t i = m; i-- > 0;) {
+        const uint32_t j = t * m + i;
+        const uint32_t o0 = __ldg(ow + j), o1 = __ldg(ow + j + 1);
+        if (o1 > o0) {
+            const uint32_t s0 = o0 / L, s1 = (o1 - 1) / L;
+#pragma unroll 1
+            for (uint32_t s = s0; s <= s1; s++) {
+                Pt part = Pt::load(slot_w + ((size_t)s + j) * Pt::BYTES);
+                run.add(part);
+            }
+        }
+        tri.add(run);
+    }
+    uint8_t *out = chunks + (size_t)gid * 2 * Pt::BYTES;
+    tri.store(out);
+    run.store(out + Pt::BYTES);
+}
+
+// ---- cold-path wrappers: the stitching kernels below are latency-bound one-offs; keeping the group law out of
+// line there keeps code size (and compile time) down without touching the hot accumulate / bucket kernels.
+template <class F>
+__device__ __noinline__ void add_cold(Xyzz<F> &a, const Xyzz<F> &b) { a.add(b); }
+template <class F>
+__device__ __noinline__ void dbl_cold(Xyzz<F> &a) { a = a.dbl(); }
+
+// ---- warp-shuffle helpers -------------------------------------------------------------------------
+
+template <class F>
+PB_DEV Xyzz<F> shfl_down_pt(const Xyzz<F> &p, int delta) {
+    Xyzz<F> r;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, p.x.l[i], delta);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, p.y.l[i], delta);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, p.zz.l[i], delta);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, p.zzz.l[i], delta);
+    }
+    return r;
+}
+
+template <class F>
+PB_DEV Xyzz<F> mul_pow2(Xyzz<F> p, uint32_t log2k) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < log2k; i++) dbl_cold(p);
+    return p;
+}
+
+// Over the 32 lanes of a warp, with lane l holding (P_l, R_l):
+//   lane 0 returns  sumP = sum_l P_l,  sumR = sum_l R_l,  wR = sum_l l * R_l
+// (suffix running sums by shuffle: sum_l l*R_l = sum_{l>=1} sum_{j>=l} R_j).
+template <class F>
+PB_DEV void warp_running_sums(Xyzz<F> &P, Xyzz<F> &R, Xyzz<F> &wR, uint32_t lane) {
+#pragma unroll 1
+    for (int o = 1; o < 32; o <<= 1) {                 // inclusive suffix scan of R
+        Xyzz<F> t = shfl_down_pt(R, o);
+        if (lane + o < 32) add_cold(R, t);
+    }
+    wR = lane ? R : Xyzz<F>::identity();
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {                 // tree sums
+        Xyzz<F> t = shfl_down_pt(wR, o);
+        if (lane + o < 32) add_cold(wR, t);
+        Xyzz<F> u = shfl_down_pt(P, o);
+        if (lane + o < 32) add_cold(P, u);
+    }
+}
+
+// K6: one CTA per window stitches the chunk sums:  S_w = sum_t Lc_t + m * sum_t t * Rc_t.
+template <class C>
+__global__ void __launch_bounds__(WIN_THREADS) k_window_reduce(const uint8_t *__restrict__ chunks, uint32_t chunks_pw, uint32_t log2m,
+                                                              uint8_t *__restrict__ wsums) {
+    using Fq = typename C::Fq;
+    using Pt = Xyzz<Fq>;
+    __shared__ uint4 sh_raw[(WIN_THREADS / 32) * 2 * Pt::BYTES / 16];
+    uint8_t *sh = reinterpret_cast<uint8_t *>(sh_raw);
+    const uint32_t w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t q = chunks_pw > WIN_THREADS ? chunks_pw / WIN_THREADS : 1;     // items per thread (power of two)
+    uint32_t log2q = 0; while ((1u << log2q) < q) log2q++;
+    const uint8_t *cw = chunks + (size_t)w * chunks_pw * 2 * Pt::BYTES;
+
+    // thread-serial part: P = sum Lc + m * sum_i i*Rc_i,  R = sum Rc   over this thread's q items
+    Pt A = Pt::identity(), run = Pt::identity(), tri = Pt::identity();
+#pragma unroll 1
+    for (uint32_t i = q; i-- > 0;) {
+        const uint32_t t = tid * q + i;
+        if (t < chunks_pw) {
+            Pt lc = Pt::load(cw + (size_t)t * 2 * Pt::BYTES);
+            Pt rc = Pt::load(cw + (size_t)t * 2 * Pt::BYTES + Pt::BYTES);
+            add_cold(A, lc);
+            add_cold(tri, run);
+            add_cold(run, rc);
+        }
+    }
+    Pt P = A;
+    if (q > 1) add_cold(P, mul_pow2(tri, log2m));
+    Pt R = run, wR;
+    // S_w = sum_j P_j + (m*q) * sum_j j * R_j        (j = thread index)
+    warp_running_sums(P, R, wR, lane);
+    if (lane == 0) {
+        // sum_j j*R_j over the block = sum_warp ( wR_warp + 32*warp*R_warp )
+        add_cold(P, mul_pow2(wR, log2m + log2q));
+        P.store(sh + (size_t)warp * 2 * Pt::BYTES);
+        R.store(sh + (size_t)warp * 2 * Pt::BYTES + Pt::BYTES);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        Pt P2 = Pt::identity(), R2 = Pt::identity();
+        if (lane < WIN_THREADS / 32) {
+            P2 = Pt::load(sh + (size_t)lane * 2 * Pt::BYTES);
+            R2 = Pt::load(sh + (size_t)lane * 2 * Pt::BYTES + Pt::BYTES);
+        }
+        Pt wR2;
+        warp_running_sums(P2, R2, wR2, lane);
+        if (lane == 0) {
+            add_cold(P2, mul_pow2(wR2, log2m + log2q + 5));
+            P2.store(wsums + (size_t)w * Pt::BYTES);
+        }
+    }
+}
+
+// K7: Horner over the windows, conversion to the reference's result coordinates, canonical store.
+template <class C>
+__global__ void k_final(const uint8_t *__restrict__ wsums, uint32_t W, uint32_t c, int coord, uint8_t *__restrict__ result) {
+    using Fq = typename C::Fq;
+    using Pt = Xyzz<Fq>;
+    if (threadIdx.x || blockIdx.x) return;
+    Pt acc = Pt::load(wsums + (size_t)(W - 1) * Pt::BYTES);
+#pragma unroll 1
+    for (uint32_t w = W - 1; w-- > 0;) {
+        acc = mul_pow2(acc, c);
+        Pt sw = Pt::load(wsums + (size_t)w * Pt::BYTES);
+        add_cold(acc, sw);
+    }
+    Jacobian<Fq> j = Jacobian<Fq>::from_xyzz(acc);
+    if (coord == COORD_PROJECTIVE) j = j.to_homogeneous();
+    j.store_canonical(result);
+}
+
+// sum of Jacobian partials (sharded MSM): one thread, a handful of additions
+template <class C>
+__global__ void k_combine(const uint8_t *__restrict__ partials, uint32_t count, int coord, uint8_t *__restrict__ result) {
+    using Fq = typename C::Fq;
+    using Pt = Xyzz<Fq>;
+    if (threadIdx.x || blockIdx.x) return;
+    Pt acc = Pt::identity();
+#pragma unroll 1
+    for (uint32_t i = 0; i < count; i++) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(partials + (size_t)i * Jacobian<Fq>::BYTES);
+        Jacobian<Fq> j;
+        j.x = Fq::load_plain(q); j.y = Fq::load_plain(q + Fq::N); j.z = Fq::load_plain(q + 2 * Fq::N);
+        add_cold(acc, j.to_xyzz());
+    }
+    Jacobian<Fq> j = Jacobian<Fq>::from_xyzz(acc);
+    if (coord == COORD_PROJECTIVE) j = j.to_homogeneous();
+    j.store_canonical(result);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host driver
+
+#define PB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[panda-b200] CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); return e_; } } while (0)
+
+struct StageTimer {
+    cudaEvent_t ev[8];
+    cudaStream_t stream;
+    int k = 0;
+    bool on;
+    StageTimer(bool enable, cudaStream_t s) : stream(s), on(enable) { if (on) for (auto &e : ev) cudaEventCreate(&e); }
+    ~StageTimer() { if (on) for (auto &e : ev) cudaEventDestroy(e); }
+    void mark() { if (on && k < 8) cudaEventRecord(ev[k++], stream); }
+    float ms(int i) { float t = 0; cudaEventElapsedTime(&t, ev[i], ev[i + 1]); return t; }
+};
+
+template <class C>
+cudaError_t msm_run_t(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
+                             cudaMemPool_t pool, cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings) {
+    using Pt = Xyzz<typename C::Fq>;
+    if (n == 0) {   // empty sum: the identity, all-zero like the reference (msm_cuda.cuh:395,405)
+        PB_CUDA(cudaMemsetAsync(result, 0, Jacobian<typename C::Fq>::BYTES, stream));
+        return cudaSuccess;
+    }
+    const MsmPlan p = msm_make_plan(curve, n, c_override, seg_override);
+    uint8_t *ws = nullptr;
+    if (pool) PB_CUDA(cudaMallocFromPoolAsync((void **)&ws, p.bytes, pool, stream));
+    else PB_CUDA(cudaMallocAsync((void **)&ws, p.bytes, stream));
+    uint32_t *counts = (uint32_t *)(ws + p.off_counts), *offsets = (uint32_t *)(ws + p.off_offsets), *cursor = (uint32_t *)(ws + p.off_cursor);
+    uint16_t *digits = (uint16_t *)(ws + p.off_digits);
+    uint32_t *sorted = (uint32_t *)(ws + p.off_sorted);
+    uint8_t *slots = ws + p.off_slots, *chunks = ws + p.off_chunks, *wsums = ws + p.off_wsums;
+
+    StageTimer tm(timings != nullptr, stream);
+    cudaError_t err = cudaSuccess;
+    do {
+        if ((err = cudaMemsetAsync(counts, 0, (size_t)p.windows * p.nb * 4, stream)) != cudaSuccess) break;
+        tm.mark();
+        {
+            const uint32_t blocks = std::min<uint32_t>((n + 255) / 256, 148 * 8);
+            k_digits<C><<<blocks, 256, 0, stream>>>((const uint32_t *)scalars, n, p.c, p.windows, p.nb, digits, counts);
+        }
+        tm.mark();
+        k_scan<<<p.windows, 1024, 0, stream>>>(counts, p.nb, offsets, cursor);
+        tm.mark();
+        {
+            dim3 grid(std::min<uint32_t>((n + 255) / 256, 148 * 8), p.windows);
+            k_scatter<<<grid, 256, 0, stream>>>(digits, n, p.nb, cursor, sorted);
+        }
+        tm.mark();
+        {
+            const uint64_t threads = (uint64_t)p.windows * p.segs_pw;
+            const uint32_t blocks = (uint32_t)((threads + ACC_THREADS - 1) / ACC_THREADS);
+            k_accumulate<C><<<blocks, ACC_THREADS, 0, stream>>>((const uint8_t *)bases, sorted, offsets, n, p.nb, p.seg_len, p.segs_pw, p.windows, slots);
+        }
+        tm.mark();
+        {
+            const uint32_t threads = p.windows * p.chunks_pw;
+            k_bucket_reduce<C><<<(threads + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, stream>>>(slots, offsets, p.nb, p.seg_len, p.segs_pw,
+                                                                                                   p.windows, p.chunk, p.chunks_pw, chunks);
+        }
+        tm.mark();
+        {
+            uint32_t log2m = 0; while ((1u << log2m) < p.chunk) log2m++;
+            k_window_reduce<C><<<p.windows, WIN_THREADS, 0, stream>>>(chunks, p.chunks_pw, log2m, wsums);
+        }
+        tm.mark();
+        k_final<C><<<1, 32, 0, stream>>>(wsums, p.windows, p.c, (int)coord, (uint8_t *)result);
+        tm.mark();
+        err = cudaGetLastError();
+    } while (0);
+    cudaError_t ferr = cudaFreeAsync(ws, stream);
+    if (err == cudaSuccess) err = ferr;
+    if (err != cudaSuccess) {
+        fprintf(stderr, "[panda-b200] msm_run failed: %s\n", cudaGetErrorString(err));
+        return err;
+    }
+    if (timings) {
+        PB_CUDA(cudaStreamSynchronize(stream));
+        timings->digits = tm.ms(0); timings->scan = tm.ms(1); timings->scatter = tm.ms(2); timings->accumulate = tm.ms(3);
+        timings->bucket_reduce = tm.ms(4); timings->window_reduce = tm.ms(5); timings->final = tm.ms(6);
+    }
+    (void)sizeof(Pt);
+    return cudaSuccess;
+}
+
+
+template <class C>
+cudaError_t msm_combine_t(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream) {
+    k_combine<C><<<1, 32, 0, stream>>>((const uint8_t *)partials, count, (int)coord, (uint8_t *)result);
+    return cudaGetLastError();
+}
+
+}  // namespace pb

@@ -1,0 +1,353 @@
+// ntt.cu -- multi-pass radix-2^r NTT (r <= 8 per pass) with shared-memory butterflies and precomputed twiddles.
+//
+// n = 2^k is split into P = ceil(k/8) digits N_1..N_P (balanced).  With i = (i_1,..,i_P) (i_1 most significant)
+// and j = j_1 + N_1 j_2 + N_1 N_2 j_3 + ..:
+//   pass p < P : for every (j_1..j_{p-1}) and every inner index i' (C adjacent ones per CTA, so global accesses
+//                are C*32-byte runs): N_p-point DFT over digit p, times omega_n^(i' * j_p * N_1..N_{p-1}),
+//                written back to the same positions of the other buffer;
+//   pass P     : N_P-point DFTs over contiguous runs (C runs per CTA, adjacent in j_1), written to the digit-
+//                reversed positions, which are C*32-byte runs again.
+// Each pass reads one buffer and writes the other, so the result lands in d_dst iff P is odd (fft.cu:193-211).
+#include "ntt.cuh"
+#include "field.cuh"
+
+#include <array>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace pb {
+
+static constexpr int NTT_THREADS = 256;
+static constexpr unsigned NTT_MAX_RADIX_LOG = 8;      // fft.cu:10 MAX_LOG2_RADIX
+
+struct NttShape {
+    unsigned log_n, passes;
+    unsigned r[4];
+};
+
+static NttShape ntt_shape(unsigned log_n) {
+    NttShape s{};
+    s.log_n = log_n;
+    s.passes = (log_n + NTT_MAX_RADIX_LOG - 1) / NTT_MAX_RADIX_LOG;
+    for (unsigned p = 0; p < s.passes; p++) s.r[p] = log_n / s.passes + (p < log_n % s.passes ? 1 : 0);
+    return s;
+}
+
+// ---- twiddle tables --------------------------------------------------------------------------------
+// words: [omega 8][scale 8][t_lo 8<<lo_bits][t_hi 8<<(k-lo_bits)][stage table of r_max][stage table of r_min]
+
+struct NttTableLayout {
+    unsigned lo_bits, hi_bits, r_a, r_b;
+    size_t off_omega, off_scale, off_lo, off_hi, off_sa, off_sb, words;
+};
+
+static NttTableLayout ntt_table_layout(const NttShape &s) {
+    NttTableLayout t{};
+    t.lo_bits = (s.log_n + 1) / 2;
+    t.hi_bits = s.log_n - t.lo_bits;
+    t.r_a = s.passes ? s.r[0] : 0;
+    t.r_b = s.passes ? s.r[s.passes - 1] : 0;
+    size_t off = 0;
+    t.off_omega = off; off += 8;
+    t.off_scale = off; off += 8;
+    t.off_lo = off; off += (size_t)8 << t.lo_bits;
+    t.off_hi = off; off += (size_t)8 << t.hi_bits;
+    t.off_sa = off; off += t.r_a ? (size_t)8 << (t.r_a - 1) : 8;
+    t.off_sb = off; off += t.r_b ? (size_t)8 << (t.r_b - 1) : 8;
+    t.words = off;
+    return t;
+}
+
+template <class F>
+PB_DEV F fe_pow_u32(const F &base, uint32_t e) {
+    F acc = F::one(), b = base;
+#pragma unroll 1
+    while (e) {
+        if (e & 1) acc = acc * b;
+        b = b.sqr();
+        e >>= 1;
+    }
+    return acc;
+}
+
+template <class P>
+__global__ void k_ntt_tables(uint32_t *tab, unsigned log_n, unsigned lo_bits, unsigned hi_bits, unsigned r_a, unsigned r_b,
+                             size_t off_lo, size_t off_hi, size_t off_sa, size_t off_sb, size_t off_scale, int inverse) {
+    using F = Fe<P>;
+    const uint32_t n_lo = 1u << lo_bits, n_hi = 1u << hi_bits;
+    const uint32_t n_sa = r_a ? 1u << (r_a - 1) : 1, n_sb = r_b ? 1u << (r_b - 1) : 1;
+    const uint32_t total = n_lo + n_hi + n_sa + n_sb + 1;
+    const uint32_t nmask = log_n >= 32 ? 0xffffffffu : ((1u << log_n) - 1);
+    const F omega = F::load_plain(tab);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t e;
+        uint32_t *out;
+        if (i < n_lo) { e = i; out = tab + off_lo + (size_t)i * 8; }
+        else if (i < n_lo + n_hi) { uint32_t t = i - n_lo; e = t << lo_bits; out = tab + off_hi + (size_t)t * 8; }
+        else if (i < n_lo + n_hi + n_sa) { uint32_t t = i - n_lo - n_hi; e = t << (log_n - r_a); out = tab + off_sa + (size_t)t * 8; }
+        else if (i < n_lo + n_hi + n_sa + n_sb) { uint32_t t = i - n_lo - n_hi - n_sa; e = t << (log_n - r_b); out = tab + off_sb + (size_t)t * 8; }
+        else {
+            // scale = 2^-log_n (Montgomery): halve ONE log_n times
+            F x = F::one().canon();
+            for (unsigned k = 0; k < log_n; k++) {
+                uint32_t odd = x.l[0] & 1, carry = 0;
+                if (odd) {   // x += p (may carry out of the top limb)
+                    x.l[0] = ptx::add_cc(x.l[0], P::mod(0));
+#pragma unroll
+                    for (int q = 1; q < F::N; q++) x.l[q] = ptx::addc_cc(x.l[q], P::mod(q));
+                    carry = ptx::addc(0, 0);
+                }
+#pragma unroll
+                for (int q = 0; q < F::N - 1; q++) x.l[q] = __funnelshift_r(x.l[q], x.l[q + 1], 1);
+                x.l[F::N - 1] = (x.l[F::N - 1] >> 1) | (carry << 31);
+            }
+            x.store(tab + off_scale);
+            continue;
+        }
+        if (inverse) e = (0u - e) & nmask;
+        fe_pow_u32(omega, e).canon().store(out);
+    }
+}
+
+// ---- shared-memory tile helpers --------------------------------------------------------------------
+// tile element (row, col) limb l lives at sm[l * LS + row * CP + col]
+
+template <class F>
+PB_DEV F sm_load(const uint32_t *sm, uint32_t LS, uint32_t idx) {
+    F x;
+#pragma unroll
+    for (int l = 0; l < F::N; l++) x.l[l] = sm[l * LS + idx];
+    return x;
+}
+template <class F>
+PB_DEV void sm_store(uint32_t *sm, uint32_t LS, uint32_t idx, const F &x) {
+#pragma unroll
+    for (int l = 0; l < F::N; l++) sm[l * LS + idx] = x.l[l];
+}
+
+// in-place radix-2 DIF over the N = 2^r rows of an N x C tile; output row pos holds X[bitrev_r(pos)]
+template <class F>
+PB_DEV void tile_dft(uint32_t *sm, uint32_t LS, uint32_t CP, unsigned r, unsigned logC, const uint32_t *__restrict__ stage_tw) {
+    const uint32_t C = 1u << logC;
+    const uint32_t bflies = (1u << (r - 1)) << logC;
+#pragma unroll 1
+    for (unsigned s = 0; s < r; s++) {
+        const uint32_t half = 1u << (r - 1 - s);
+#pragma unroll 1
+        for (uint32_t q = threadIdx.x; q < bflies; q += blockDim.x) {
+            const uint32_t col = q & (C - 1), bf = q >> logC;
+            const uint32_t j = bf & (half - 1), grp = bf >> (r - 1 - s);
+            const uint32_t i0 = ((grp << (r - s)) + j) * CP + col, i1 = i0 + half * CP;
+            F u = sm_load<F>(sm, LS, i0), v = sm_load<F>(sm, LS, i1);
+            F sum = u + v, diff = u - v;
+            if (s + 1 < r) {
+                F w = F::load(stage_tw + (size_t)(j << s) * F::N);
+                diff = diff * w;
+            }
+            sm_store(sm, LS, i0, sum);
+            sm_store(sm, LS, i1, diff);
+        }
+        __syncthreads();
+    }
+}
+
+struct NttPassArgs {
+    unsigned log_n, r, log_M, log_O, logC, lo_bits;
+    unsigned passes, rad[4];          // all radices (last pass: digit reversal)
+    const uint32_t *stage_tw, *t_lo, *t_hi, *scale;
+};
+
+// pass p < P
+template <class P>
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, NttPassArgs a) {
+    using F = Fe<P>;
+    extern __shared__ uint32_t sm[];
+    const uint32_t N = 1u << a.r, C = 1u << a.logC, CP = C > 1 ? C + 1 : 1, LS = N * CP;
+    const uint32_t blocks_per_o = 1u << (a.log_M - a.logC);
+    const uint32_t o = blockIdx.x / blocks_per_o, ib = blockIdx.x % blocks_per_o;
+    const uint32_t i0 = ib << a.logC;
+    const size_t base = ((size_t)o << (a.r + a.log_M)) + i0;
+    for (uint32_t e = threadIdx.x; e < N * C; e += blockDim.x) {
+        const uint32_t row = e >> a.logC, col = e & (C - 1);
+        F x = F::load(src + (base + ((size_t)row << a.log_M) + col) * F::N);
+        sm_store(sm, LS, row * CP + col, x);
+    }
+    __syncthreads();
+    tile_dft<F>(sm, LS, CP, a.r, a.logC, a.stage_tw);
+    const uint32_t lo_mask = (1u << a.lo_bits) - 1;
+    for (uint32_t e = threadIdx.x; e < N * C; e += blockDim.x) {
+        const uint32_t jp = e >> a.logC, col = e & (C - 1);
+        const uint32_t pos = __brev(jp) >> (32 - a.r);
+        F x = sm_load<F>(sm, LS, pos * CP + col);
+        const uint32_t ex = ((i0 + col) * jp) << a.log_O;       // < n
+        if (ex) {
+            F tw = F::load(a.t_hi + (size_t)(ex >> a.lo_bits) * F::N) * F::load(a.t_lo + (size_t)(ex & lo_mask) * F::N);
+            x = x * tw;
+        }
+        x.canon().store(dst + (base + ((size_t)jp << a.log_M) + col) * F::N);
+    }
+}
+
+// pass P (last): contiguous runs in, digit-reversed positions out
+template <class P>
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, NttPassArgs a) {
+    using F = Fe<P>;
+    extern __shared__ uint32_t sm[];
+    const uint32_t N = 1u << a.r, C = 1u << a.logC, CP = C > 1 ? C + 1 : 1, LS = N * CP;
+    const unsigned log_OP = a.log_O;                                  // log2(N_1 .. N_{P-1})
+    const unsigned r1 = a.passes > 1 ? a.rad[0] : 0;
+    const uint32_t rest_count = 1u << (log_OP - r1);
+    const uint32_t j1_0 = (blockIdx.x / rest_count) << a.logC, rest = blockIdx.x % rest_count;
+    // digit reversal of (j_2 .. j_{P-1})
+    uint32_t revp = 0;
+    {
+        uint32_t tmp = rest;
+        unsigned shift_total = 0;
+        for (unsigned d = 1; d + 1 < a.passes; d++) shift_total += a.rad[d];
+        for (unsigned d = a.passes - 1; d-- > 1;) {       // d = P-2 .. 1  (0-based digit index of j_{d+1})
+            shift_total -= a.rad[d];
+            revp += (tmp & ((1u << a.rad[d]) - 1)) << shift_total;
+            tmp >>= a.rad[d];
+        }
+    }
+    for (uint32_t e = threadIdx.x; e < N * C; e += blockDim.x) {
+        const uint32_t cidx = e >> a.r, ip = e & (N - 1);
+        const size_t o = (size_t)(j1_0 + cidx) * rest_count + rest;
+        F x = F::load(src + ((o << a.r) + ip) * F::N);
+        sm_store(sm, LS, ip * CP + cidx, x);
+    }
+    __syncthreads();
+    tile_dft<F>(sm, LS, CP, a.r, a.logC, a.stage_tw);
+    F scale;
+    if (a.scale) scale = F::load(a.scale);
+    const size_t out_base = (size_t)j1_0 + ((size_t)revp << r1);
+    for (uint32_t e = threadIdx.x; e < N * C; e += blockDim.x) {
+        const uint32_t jp = e >> a.logC, cidx = e & (C - 1);
+        const uint32_t pos = __brev(jp) >> (32 - a.r);
+        F x = sm_load<F>(sm, LS, pos * CP + cidx);
+        if (a.scale) x = x * scale;
+        x.canon().store(dst + (out_base + cidx + ((size_t)jp << log_OP)) * F::N);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+
+struct NttCacheEntry {
+    int device;
+    unsigned log_n;
+    bool inverse;
+    std::array<uint32_t, 8> omega;
+    uint32_t *d_tab;
+    NttTableLayout layout;
+};
+
+static std::mutex g_ntt_mutex;
+static std::vector<NttCacheEntry *> g_ntt_cache;
+
+#define PB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[panda-b200] CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); return e_; } } while (0)
+
+static cudaError_t ntt_get_tables(const NttShape &shape, const void *omega_host, bool inverse, cudaStream_t stream, NttCacheEntry **out) {
+    int dev = 0;
+    PB_CUDA(cudaGetDevice(&dev));
+    std::array<uint32_t, 8> om;
+    memcpy(om.data(), omega_host, 32);
+    std::lock_guard<std::mutex> lock(g_ntt_mutex);
+    for (auto *e : g_ntt_cache)
+        if (e->device == dev && e->log_n == shape.log_n && e->inverse == inverse && e->omega == om) { *out = e; return cudaSuccess; }
+    auto *e = new NttCacheEntry();
+    e->device = dev; e->log_n = shape.log_n; e->inverse = inverse; e->omega = om;
+    e->layout = ntt_table_layout(shape);
+    e->d_tab = nullptr;
+    cudaError_t err = cudaMalloc((void **)&e->d_tab, e->layout.words * 4);
+    if (err != cudaSuccess) { delete e; return err; }
+    // e->omega lives as long as the cache entry, so the async copy's source stays valid
+    err = cudaMemcpyAsync(e->d_tab, e->omega.data(), 32, cudaMemcpyHostToDevice, stream);
+    if (err == cudaSuccess) {
+        const NttTableLayout &t = e->layout;
+        k_ntt_tables<Bn254Fr><<<64, 128, 0, stream>>>(e->d_tab, shape.log_n, t.lo_bits, t.hi_bits, t.r_a, t.r_b, t.off_lo, t.off_hi, t.off_sa,
+                                                    t.off_sb, t.off_scale, inverse ? 1 : 0);
+        err = cudaGetLastError();
+    }
+    if (err != cudaSuccess) { cudaFree(e->d_tab); delete e; return err; }
+    if (g_ntt_cache.size() >= 16) {            // bounded: drop the oldest entry (its stream work has long been queued)
+        NttCacheEntry *old = g_ntt_cache.front();
+        g_ntt_cache.erase(g_ntt_cache.begin());
+        cudaFree(old->d_tab);                  // cudaFree synchronises with outstanding work on the buffer
+        delete old;
+    }
+    g_ntt_cache.push_back(e);
+    *out = e;
+    return cudaSuccess;
+}
+
+cudaError_t ntt_release_tables() {
+    std::lock_guard<std::mutex> lock(g_ntt_mutex);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto *e : g_ntt_cache) {
+        cudaSetDevice(e->device);
+        cudaFree(e->d_tab);
+        delete e;
+    }
+    g_ntt_cache.clear();
+    cudaSetDevice(cur);
+    return cudaSuccess;
+}
+
+cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, const void *omega_host, bool inverse,
+                    cudaStream_t stream, unsigned *result_in_dst) {
+    (void)field;
+    if (log_n > 28 || !omega_host) return cudaErrorInvalidValue;      // 2-adicity of BN254 Fr (paramter.cuh:241)
+    const NttShape shape = ntt_shape(log_n);
+    if (result_in_dst) *result_in_dst = shape.passes & 1;
+    if (shape.passes == 0) return cudaSuccess;                         // n = 1: the transform is the identity
+    NttCacheEntry *tab = nullptr;
+    PB_CUDA(ntt_get_tables(shape, omega_host, inverse, stream, &tab));
+    const NttTableLayout &t = tab->layout;
+
+    static bool attr_done[64] = {};
+    int dev = 0;
+    PB_CUDA(cudaGetDevice(&dev));
+    const size_t max_smem = (size_t)8 * (256 * 9) * 4;
+    if (dev < 64 && !attr_done[dev]) {
+        PB_CUDA(cudaFuncSetAttribute(k_ntt_cols<Bn254Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        PB_CUDA(cudaFuncSetAttribute(k_ntt_last<Bn254Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        attr_done[dev] = true;
+    }
+
+    uint32_t *src = (uint32_t *)d_src, *dst = (uint32_t *)d_dst;
+    unsigned log_O = 0;
+    for (unsigned p = 0; p < shape.passes; p++) {
+        NttPassArgs a{};
+        a.log_n = log_n; a.r = shape.r[p]; a.log_O = log_O; a.lo_bits = t.lo_bits; a.passes = shape.passes;
+        for (unsigned d = 0; d < 4; d++) a.rad[d] = shape.r[d];
+        a.log_M = log_n - log_O - a.r;
+        a.stage_tw = tab->d_tab + (a.r == t.r_a ? t.off_sa : t.off_sb);
+        a.t_lo = tab->d_tab + t.off_lo; a.t_hi = tab->d_tab + t.off_hi;
+        a.scale = nullptr;
+        const bool last = p + 1 == shape.passes;
+        if (!last) {
+            a.logC = a.log_M < 3 ? a.log_M : 3;
+            const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
+            const size_t smem = (size_t)8 * ((size_t)(1u << a.r) * CP) * 4;
+            const uint32_t blocks = 1u << (log_O + a.log_M - a.logC);
+            k_ntt_cols<Bn254Fr><<<blocks, NTT_THREADS, smem, stream>>>(src, dst, a);
+        } else {
+            const unsigned r1 = shape.passes > 1 ? shape.r[0] : 0;
+            a.logC = r1 < 3 ? r1 : 3;
+            if (inverse) a.scale = tab->d_tab + t.off_scale;
+            const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
+            const size_t smem = (size_t)8 * ((size_t)(1u << a.r) * CP) * 4;
+            const uint32_t blocks = 1u << (log_O - a.logC);
+            k_ntt_last<Bn254Fr><<<blocks, NTT_THREADS, smem, stream>>>(src, dst, a);
+        }
+        PB_CUDA(cudaGetLastError());
+        log_O += a.r;
+        std::swap(src, dst);
+    }
+    return cudaSuccess;
+}
+
+}  // namespace pb
