@@ -96,8 +96,9 @@ typedef panda_msm_configuration msm_configuration;
 panda_error panda_msm_setup_bn254(void);
 panda_error panda_msm_execute_bn254(const panda_msm_configuration exec_cfg);
 /* Reference: CPU debug path taking HOST pointers for bases / scalars / results (msm_host.cuh:267-370).
- * Here the same contract (host pointers in, 96-byte Jacobian/projective result out, synchronous) is served by
- * staging through the device; the host buffers are not modified. */
+ * Here the same contract (host pointers in, 96-byte result out, synchronous) is served by staging through the
+ * device; the host buffers are not modified.  Like the reference (msm_host.cuh:372-383 never reads the coordinate
+ * flag) the result is always Jacobian. */
 panda_error panda_msm_execute_bn254_host(const panda_msm_configuration exec_cfg);
 panda_error panda_msm_tear_down(void);
 

@@ -496,9 +496,11 @@ int po_msm(int cid, const void *bases, const void *scalars, size_t n, unsigned c
     return 0;
 }
 
-/* the reference host entry point's shape: n = 2^log_n, BIT_S = 16, single thread */
+/* the reference host entry point's shape: n = 2^log_n, BIT_S = 16, single thread.  Like core_msm_execute_bn254_host
+ * (msm_host.cuh:372-383), which never reads msm_result_coordinate_type, the result is always Jacobian. */
 int po_msm_reference(int cid, const void *bases, const void *scalars, unsigned log_n, int coord, void *out) {
-    return po_msm(cid, bases, scalars, (size_t)1 << log_n, 16, 1, coord, out);
+    (void)coord;
+    return po_msm(cid, bases, scalars, (size_t)1 << log_n, 16, 1, 0, out);
 }
 
 /* k * P by double-and-add; k canonical (NOT Montgomery), nl64 limbs; P affine Montgomery; out Jacobian */

@@ -296,12 +296,18 @@ PB_DEV bool fe_equal(const Fe<P> &a, const Fe<P> &b) { return (a - b).is_zero();
 template <class P>
 PB_DEV Fe<P> fe_inverse(const Fe<P> &a) {
     Fe<P> acc = Fe<P>::one(), base = a;
-    // exponent p - 2, bit by bit (p odd, p - 2 only changes limb 0 unless mod(0) < 2, which never happens)
+    // exponent p - 2, bit by bit; the borrow of "- 2" is propagated through the (compile-time) limbs
     #pragma unroll 1
     for (int i = 0; i < P::BITS; i++) {
         uint32_t limb = 0;
+        bool borrow = true;                       // subtracting 2 from limb 0
         #pragma unroll
-        for (int k = 0; k < P::N; k++) if (k == (i >> 5)) limb = P::mod(k) - (k == 0 ? 2u : 0u);
+        for (int k = 0; k < P::N; k++) {
+            const uint32_t sub = k == 0 ? 2u : (borrow ? 1u : 0u);
+            const uint32_t v = P::mod(k) - sub;
+            borrow = k == 0 ? P::mod(0) < 2u : (borrow && P::mod(k) == 0u);
+            if (k == (i >> 5)) limb = v;
+        }
         if ((limb >> (i & 31)) & 1) acc = acc * base;
         base = base.sqr();
     }

@@ -51,9 +51,13 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, uint32_t c_override, uint32_t s
     p.c = best_c;
     p.windows = windows_for(bits, p.c);
     p.nb = 1u << (p.c - 1);
+    // segment length: about one average bucket, so that most buckets end up with one or two partial sums, but
+    // never so long that the accumulation kernel has fewer than ~4 waves of threads (148 SMs x 384 threads)
     uint64_t entries = (uint64_t)n * p.windows;
-    uint32_t L = seg_override ? seg_override : pow2_floor(std::max<uint64_t>(1, entries / (148ull * 512 * 8)));
-    L = std::min<uint32_t>(std::max<uint32_t>(L, 8), 128);
+    uint32_t L = pow2_floor(std::max<uint64_t>(1, n / p.nb));
+    L = std::min<uint32_t>(L, pow2_floor(std::max<uint64_t>(1, entries / (148ull * 384 * 4))));
+    L = std::min<uint32_t>(std::max<uint32_t>(L, 8), 512);
+    if (seg_override) L = seg_override;
     p.seg_len = L;
     p.segs_pw = n ? (n + L - 1) / L : 0;
     uint32_t m = pow2_floor(std::max<uint64_t>(1, ((uint64_t)p.windows * p.nb) / 65536));
@@ -63,9 +67,10 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, uint32_t c_override, uint32_t s
 
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
-    p.off_counts = off;  off = align(off + (size_t)p.windows * p.nb * 4);
+    p.off_counts = off;  off = align(off + (size_t)p.windows * p.nb * 4 + 4);      // + the big-bucket counter
     p.off_offsets = off; off = align(off + (size_t)p.windows * (p.nb + 1) * 4);
     p.off_cursor = off;  off = align(off + (size_t)p.windows * p.nb * 4);
+    p.off_biglist = off; off = align(off + (size_t)p.windows * p.nb * 4);
     p.off_digits = off;  off = align(off + (size_t)p.windows * n * 2);
     p.off_sorted = off;  off = align(off + (size_t)p.windows * n * 4);
     p.off_slots = off;   off = align(off + (size_t)p.windows * ((size_t)p.segs_pw + p.nb) * 4 * fq_bytes);

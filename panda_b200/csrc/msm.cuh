@@ -24,7 +24,7 @@ struct MsmPlan {
     uint32_t chunk;        // m: buckets folded serially by one reduction thread
     uint32_t chunks_pw;    // nb / m
     // workspace layout (byte offsets into one arena)
-    size_t off_counts, off_offsets, off_cursor, off_digits, off_sorted, off_slots, off_chunks, off_wsums, bytes;
+    size_t off_counts, off_offsets, off_cursor, off_biglist, off_digits, off_sorted, off_slots, off_chunks, off_wsums, bytes;
 };
 
 // window width / segment length selection; c_override = 0 -> cost model

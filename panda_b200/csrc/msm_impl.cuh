@@ -24,6 +24,8 @@ static constexpr uint32_t DIGIT_SKIP = 0xFFFFu;     // digit 0: contributes noth
 static constexpr int ACC_THREADS = 128;
 static constexpr int RED_THREADS = 128;
 static constexpr int WIN_THREADS = 256;
+static constexpr int BIG_THREADS = 256;
+static constexpr uint32_t BIG_SPAN = 8;             // buckets with more partial slots than this are pre-reduced by a whole CTA
 
 // ----------------------------------------------------------------------------------------------------
 // K1: scalars -> signed window digits (window-major, 16 bit) + per-(window,bucket) counts.
@@ -52,9 +54,10 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
     }
 }
 
-// K2: per-window exclusive scan of the bucket counts -> offsets[w][0..nb], cursor[w][0..nb-1].
-static __global__ void __launch_bounds__(1024) k_scan(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t *__restrict__ offsets,
-                                               uint32_t *__restrict__ cursor) {
+// K2: per-window exclusive scan of the bucket counts -> offsets[w][0..nb], cursor[w][0..nb-1].  Buckets whose entries
+// span more than BIG_SPAN accumulation segments (the short top window, skewed scalars) are appended to big_list.
+static __global__ void __launch_bounds__(1024) k_scan(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t L, uint32_t *__restrict__ offsets,
+                                                      uint32_t *__restrict__ cursor, uint32_t *__restrict__ big_count, uint32_t *__restrict__ big_list) {
     __shared__ uint32_t warp_tot[32];
     const uint32_t w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t *cw = counts + (size_t)w * nb;
@@ -77,7 +80,10 @@ static __global__ void __launch_bounds__(1024) k_scan(const uint32_t *__restrict
         }
         __syncthreads();
         const uint32_t excl = running + (warp ? warp_tot[warp - 1] : 0) + incl - v;
-        if (idx < nb) { ow[idx] = excl; kw[idx] = excl; }
+        if (idx < nb) {
+            ow[idx] = excl; kw[idx] = excl;
+            if (v && (excl + v - 1) / L - excl / L + 1 > BIG_SPAN) big_list[atomicAdd(big_count, 1u)] = w * nb + idx;
+        }
         running += warp_tot[31];
         __syncthreads();
     }
@@ -173,7 +179,9 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const uint8_t *__
         const uint32_t j = t * m + i;
         const uint32_t o0 = __ldg(ow + j), o1 = __ldg(ow + j + 1);
         if (o1 > o0) {
-            const uint32_t s0 = o0 / L, s1 = (o1 - 1) / L;
+            const uint32_t s0 = o0 / L;
+            uint32_t s1 = (o1 - 1) / L;
+            if (s1 - s0 + 1 > BIG_SPAN) s1 = s0;       // already folded into its first slot by k_reduce_big
 #pragma unroll 1
             for (uint32_t s = s0; s <= s1; s++) {
                 Pt part = Pt::load(slot_w + ((size_t)s + j) * Pt::BYTES);
@@ -207,6 +215,49 @@ PB_DEV Xyzz<F> shfl_down_pt(const Xyzz<F> &p, int delta) {
         r.zzz.l[i] = __shfl_down_sync(0xffffffffu, p.zzz.l[i], delta);
     }
     return r;
+}
+
+// K4b: one CTA per oversized bucket folds all of its partial slots into the first one (strided serial sums,
+// then a shuffle tree per warp and one more across the warps).
+template <class C>
+__global__ void __launch_bounds__(BIG_THREADS) k_reduce_big(uint8_t *__restrict__ slots, const uint32_t *__restrict__ offsets,
+                                                           const uint32_t *__restrict__ big_count, const uint32_t *__restrict__ big_list,
+                                                           uint32_t nb, uint32_t L, uint32_t segs_pw) {
+    using Fq = typename C::Fq;
+    using Pt = Xyzz<Fq>;
+    __shared__ uint4 sh_raw[(BIG_THREADS / 32) * Pt::BYTES / 16];
+    uint8_t *sh = reinterpret_cast<uint8_t *>(sh_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t count = *big_count;
+    for (uint32_t e = blockIdx.x; e < count; e += gridDim.x) {
+        const uint32_t id = big_list[e], w = id / nb, j = id % nb;
+        const uint32_t *ow = offsets + (size_t)w * (nb + 1);
+        uint8_t *slot_w = slots + (size_t)w * ((size_t)segs_pw + nb) * Pt::BYTES;
+        const uint32_t s0 = ow[j] / L, s1 = (ow[j + 1] - 1) / L;
+        Pt acc = Pt::identity();
+#pragma unroll 1
+        for (uint32_t s = s0 + tid; s <= s1; s += BIG_THREADS) {
+            Pt part = Pt::load(slot_w + ((size_t)s + j) * Pt::BYTES);
+            add_cold(acc, part);
+        }
+#pragma unroll 1
+        for (int o = 16; o > 0; o >>= 1) {
+            Pt t = shfl_down_pt(acc, o);
+            if (lane + o < 32) add_cold(acc, t);
+        }
+        __syncthreads();                               // every read of slot s0 + j above is done; smem is free
+        if (lane == 0) acc.store(sh + (size_t)warp * Pt::BYTES);
+        __syncthreads();
+        if (warp == 0) {
+            Pt v = lane < BIG_THREADS / 32 ? Pt::load(sh + (size_t)lane * Pt::BYTES) : Pt::identity();
+#pragma unroll 1
+            for (int o = 4; o > 0; o >>= 1) {
+                Pt t = shfl_down_pt(v, o);
+                if (lane + o < BIG_THREADS / 32) add_cold(v, t);
+            }
+            if (lane == 0) v.store(slot_w + ((size_t)s0 + j) * Pt::BYTES);
+        }
+    }
 }
 
 template <class F>
@@ -289,7 +340,8 @@ __global__ void __launch_bounds__(WIN_THREADS) k_window_reduce(const uint8_t *__
     }
 }
 
-// K7: Horner over the windows, conversion to the reference's result coordinates, canonical store.
+// K7: Horner over the windows (Jacobian doublings, the cheapest form: 2M + 5S), conversion to the reference's result
+// coordinates, canonical store.  One thread: (W-1)*c dependent doublings are inherent to the window method.
 template <class C>
 __global__ void k_final(const uint8_t *__restrict__ wsums, uint32_t W, uint32_t c, int coord, uint8_t *__restrict__ result) {
     using Fq = typename C::Fq;
@@ -298,7 +350,10 @@ __global__ void k_final(const uint8_t *__restrict__ wsums, uint32_t W, uint32_t 
     Pt acc = Pt::load(wsums + (size_t)(W - 1) * Pt::BYTES);
 #pragma unroll 1
     for (uint32_t w = W - 1; w-- > 0;) {
-        acc = mul_pow2(acc, c);
+        Jacobian<Fq> j = Jacobian<Fq>::from_xyzz(acc);
+#pragma unroll 1
+        for (uint32_t i = 0; i < c; i++) j = j.dbl();
+        acc = j.to_xyzz();
         Pt sw = Pt::load(wsums + (size_t)w * Pt::BYTES);
         add_cold(acc, sw);
     }
@@ -355,6 +410,7 @@ cudaError_t msm_run_t(CurveId curve, const void *bases, const void *scalars, uin
     if (pool) PB_CUDA(cudaMallocFromPoolAsync((void **)&ws, p.bytes, pool, stream));
     else PB_CUDA(cudaMallocAsync((void **)&ws, p.bytes, stream));
     uint32_t *counts = (uint32_t *)(ws + p.off_counts), *offsets = (uint32_t *)(ws + p.off_offsets), *cursor = (uint32_t *)(ws + p.off_cursor);
+    uint32_t *big_count = counts + (size_t)p.windows * p.nb, *big_list = (uint32_t *)(ws + p.off_biglist);   // the counter is zeroed with the counts
     uint16_t *digits = (uint16_t *)(ws + p.off_digits);
     uint32_t *sorted = (uint32_t *)(ws + p.off_sorted);
     uint8_t *slots = ws + p.off_slots, *chunks = ws + p.off_chunks, *wsums = ws + p.off_wsums;
@@ -362,14 +418,14 @@ cudaError_t msm_run_t(CurveId curve, const void *bases, const void *scalars, uin
     StageTimer tm(timings != nullptr, stream);
     cudaError_t err = cudaSuccess;
     do {
-        if ((err = cudaMemsetAsync(counts, 0, (size_t)p.windows * p.nb * 4, stream)) != cudaSuccess) break;
+        if ((err = cudaMemsetAsync(counts, 0, (size_t)p.windows * p.nb * 4 + 4, stream)) != cudaSuccess) break;
         tm.mark();
         {
             const uint32_t blocks = std::min<uint32_t>((n + 255) / 256, 148 * 8);
             k_digits<C><<<blocks, 256, 0, stream>>>((const uint32_t *)scalars, n, p.c, p.windows, p.nb, digits, counts);
         }
         tm.mark();
-        k_scan<<<p.windows, 1024, 0, stream>>>(counts, p.nb, offsets, cursor);
+        k_scan<<<p.windows, 1024, 0, stream>>>(counts, p.nb, p.seg_len, offsets, cursor, big_count, big_list);
         tm.mark();
         {
             dim3 grid(std::min<uint32_t>((n + 255) / 256, 148 * 8), p.windows);
@@ -381,6 +437,7 @@ cudaError_t msm_run_t(CurveId curve, const void *bases, const void *scalars, uin
             const uint32_t blocks = (uint32_t)((threads + ACC_THREADS - 1) / ACC_THREADS);
             k_accumulate<C><<<blocks, ACC_THREADS, 0, stream>>>((const uint8_t *)bases, sorted, offsets, n, p.nb, p.seg_len, p.segs_pw, p.windows, slots);
         }
+        k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, stream>>>(slots, offsets, big_count, big_list, p.nb, p.seg_len, p.segs_pw);
         tm.mark();
         {
             const uint32_t threads = p.windows * p.chunks_pw;

@@ -114,6 +114,7 @@ static panda_error msm_execute_host(pb::CurveId curve, const panda_msm_configura
         if ((e = cudaMemcpyAsync(d + off_s, cfg.scalars, scalars_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
         panda_msm_configuration dc = cfg;
         dc.bases = d; dc.scalars = d + off_s; dc.results = d + off_r;
+        dc.msm_result_coordinate_type = JACOBIAN;   // the reference host path never reads the flag (msm_host.cuh:372-383)
         if ((e = (cudaError_t)msm_execute(curve, dc, n)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(cfg.results, d + off_r, 3 * fq, cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
         e = cudaStreamSynchronize(s);

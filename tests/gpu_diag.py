@@ -9,7 +9,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle as O
 from panda_b200 import gpu_ffi as ffi
-from tests.gpu_util import DevBuf, msm_device
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gpu_util import DevBuf, msm_device
 
 NULLS = ffi.PandaStream.null()
 

@@ -1,0 +1,83 @@
+"""-m gpu: the device field / curve arithmetic, one operation at a time, against the oracle (bit-exact after
+canonicalisation; curve results compared after normalising to affine)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FIELD_OPS = [(0, "mul", 2), (1, "add", 2), (2, "sub", 2), (3, "sqr", 1), (4, "from_mont", 1), (5, "to_mont", 1), (6, "inv", 1), (7, "neg", 1)]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from panda_b200 import gpu_ffi as ffi
+    import gpu_util
+
+    return ffi, gpu_util
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_field_ops_bit_exact(oracle, dev, fid):
+    ffi, gu = dev
+    n = 8192
+    fb = oracle.field_bytes(fid)
+    a = oracle.gen_scalars(fid, 11 + fid, n)
+    b = oracle.gen_scalars(fid, 99 + fid, n)
+    one = oracle.field_const(fid, 1)
+    minus1 = oracle.f_neg(fid, one)
+    p_minus_1_raw = oracle.field_const(fid, 0).copy(); p_minus_1_raw[0] -= 1        # the largest canonical value
+    for i, v in enumerate([np.zeros(fb, np.uint8), one, minus1, p_minus_1_raw]):
+        a[i * fb:(i + 1) * fb] = v
+        b[(3 - i) * fb:(4 - i) * fb] = v
+    da, db, do = gu.DevBuf.from_numpy(a), gu.DevBuf.from_numpy(b), gu.DevBuf(a.size)
+    ofn = {"mul": oracle.f_mul, "add": oracle.f_add, "sub": oracle.f_sub, "sqr": oracle.f_sqr, "from_mont": oracle.f_from_mont,
+           "to_mont": oracle.f_to_mont, "inv": oracle.f_inv, "neg": oracle.f_neg}
+    for op, name, arity in FIELD_OPS:
+        cnt = 512 if name == "inv" else n
+        assert ffi.lib.panda_debug_field_op(fid, op, da.ptr, db.ptr, do.ptr, cnt, ffi.PandaStream.null()) == 0
+        assert ffi.lib.panda_stream_synchronize(ffi.PandaStream.null()) == 0
+        got = do.to_numpy(cnt * fb)
+        exp = ofn[name](fid, a[:cnt * fb], b[:cnt * fb]) if arity == 2 else ofn[name](fid, a[:cnt * fb])
+        assert (got == exp).all(), f"field {fid} {name}"
+
+
+def _rand_jac(oracle, cid, seed, n):
+    fq, fb = oracle.FQ_OF[cid], oracle.FQ_BYTES[cid]
+    aff = oracle.gen_bases(cid, seed, n).reshape(n, 2 * fb)
+    lam = oracle.gen_scalars(fq, seed + 1, n).reshape(n, fb)
+    l2 = oracle.f_sqr(fq, lam).reshape(n, fb)
+    l3 = oracle.f_mul(fq, l2, lam).reshape(n, fb)
+    x = oracle.f_mul(fq, np.ascontiguousarray(aff[:, :fb]), l2).reshape(n, fb)
+    y = oracle.f_mul(fq, np.ascontiguousarray(aff[:, fb:]), l3).reshape(n, fb)
+    return np.concatenate([x, y, lam], axis=1).copy(), aff.copy()
+
+
+@pytest.mark.parametrize("cid", [0, 1])
+def test_curve_ops_match_reference_formulas(oracle, dev, cid):
+    """XYZZ madd / add / dbl and Jacobian dbl / to_homogeneous vs the restated reference formulas
+    (projective.cuh:163-314, 66-77), including p = inf, q = inf, p == q (doubling) and p == -q."""
+    ffi, gu = dev
+    fb, fq = oracle.FQ_BYTES[cid], oracle.FQ_OF[cid]
+    n = 1024
+    P, PA = _rand_jac(oracle, cid, 5, n)
+    Q, QA = _rand_jac(oracle, cid, 77, n)
+    P[0, 2 * fb:] = 0
+    Q[1, 2 * fb:] = 0; QA[1, :] = 0
+    Q[2] = P[2]; QA[2] = PA[2]
+    Q[3] = P[3]; Q[3, fb:2 * fb] = oracle.f_neg(fq, P[3, fb:2 * fb].copy()); QA[3] = PA[3]; QA[3, fb:] = oracle.f_neg(fq, PA[3, fb:].copy())
+    P[4, 2 * fb:] = 0; Q[4, 2 * fb:] = 0; QA[4, :] = 0            # inf + inf
+    p, q, qa = P.reshape(-1), Q.reshape(-1), QA.reshape(-1)
+    dp, dq, dqa, do = gu.DevBuf.from_numpy(p), gu.DevBuf.from_numpy(q), gu.DevBuf.from_numpy(qa), gu.DevBuf(p.size)
+    cases = [(0, dqa, lambda: oracle.jac_madd(cid, p, qa), False), (1, dq, lambda: oracle.jac_add(cid, p, q), False),
+             (2, dq, lambda: oracle.jac_dbl(cid, p), False), (3, dq, lambda: oracle.jac_dbl(cid, p), True),
+             (4, dq, lambda: oracle.jac_to_projective(cid, p), True)]
+    for op, second, expf, bit_exact in cases:
+        assert ffi.lib.panda_debug_curve_op(cid, op, dp.ptr, second.ptr, do.ptr, n, ffi.PandaStream.null()) == 0
+        assert ffi.lib.panda_stream_synchronize(ffi.PandaStream.null()) == 0
+        got, exp = do.to_numpy(), expf()
+        if op == 4:
+            assert (oracle.proj_to_affine(cid, got) == oracle.proj_to_affine(cid, exp)).all()
+        else:
+            assert (oracle.jac_to_affine(cid, got) == oracle.jac_to_affine(cid, exp)).all(), f"curve {cid} op {op}"
+        if bit_exact:        # same formula as the reference -> the very same representative
+            assert (got == exp).all()

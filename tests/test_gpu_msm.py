@@ -1,0 +1,236 @@
+"""-m gpu: MSM parity through the C ABI and the host API.  Bit-exact with the oracle / the reference's golden vector
+after normalising to affine (the comparison the reference's own test makes, tests/test.rs:106-108)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from panda_b200 import gpu_ffi as ffi
+    import gpu_util
+
+    return ffi, gpu_util
+
+
+def affine(oracle, cid, res, coord=0):
+    return oracle.proj_to_affine(cid, res) if coord == 1 else oracle.jac_to_affine(cid, res)
+
+
+def test_golden_k13(oracle, dev, golden_k13):
+    """src/cuda/test/data/msm/k13: 8192 copies of the generator (every second addition into a bucket is a doubling)."""
+    _ffi, gu = dev
+    for coord in (0, 1):
+        got = gu.msm_device(golden_k13["bases"], golden_k13["scalars"], 1 << 13, coord)
+        assert (affine(oracle, 0, got, coord) == golden_k13["result_affine"]).all()
+
+
+@pytest.mark.parametrize("k", list(range(0, 17)))
+def test_sweep_against_oracle(oracle, dev, k):
+    """k = 10..=20 is the reference's own sweep (tests/test.rs:51-52); smaller k exercise the short-window plans."""
+    _ffi, gu = dev
+    n = 1 << k
+    bases = oracle.gen_bases(0, oracle.seed_for(k), n)
+    scal = oracle.gen_scalars(1, oracle.seed_for(k) + 1, n)
+    exp = oracle.jac_to_affine(0, oracle.msm(0, bases, scal, n, c=min(max(k, 4), 13)))
+    for coord in (0, 1):
+        assert (affine(oracle, 0, gu.msm_device(bases, scal, n, coord), coord) == exp).all()
+
+
+@pytest.mark.parametrize("k", [17, 18, 19, 20])
+def test_sweep_closed_form(oracle, dev, k):
+    _ffi, gu = dev
+    n = 1 << k
+    bases = oracle.gen_bases(0, oracle.seed_for(k), n)
+    scal = oracle.gen_scalars(1, oracle.seed_for(k) + 1, n)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, oracle.seed_for(k), scal, n))
+    assert (oracle.jac_to_affine(0, gu.msm_device(bases, scal, n)) == exp).all()
+
+
+def test_full_size_2_24_closed_form_and_linearity(oracle, dev):
+    """BASELINE.json's size: closed form, plus linearity MSM(s1 + s2) == MSM(s1) + MSM(s2) on the same bases."""
+    ffi, gu = dev
+    k, n = 24, 1 << 24
+    bases = oracle.gen_bases(0, oracle.seed_for(k), n)
+    s1 = oracle.gen_scalars(1, oracle.seed_for(k) + 1, n)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, oracle.seed_for(k), s1, n))
+    d_b, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf(96)
+    stream, pool = ffi.PandaStream.new(), ffi.PandaMemPool.new(0)
+
+    def run(scal):
+        d_s = gu.DevBuf.from_numpy(scal)
+        cfg = ffi.MSMConfiguration(pool, stream, d_b.ptr, d_s.ptr, d_r.ptr, k, 0)
+        assert ffi.lib.panda_msm_execute_bn254(cfg) == 0
+        stream.sync()
+        d_s.free()
+        return d_r.to_numpy()
+
+    r1 = run(s1)
+    assert (oracle.jac_to_affine(0, r1) == exp).all()
+    s2 = oracle.gen_scalars(1, 4242, n)
+    r2 = run(s2)
+    r12 = run(oracle.f_add(1, s1, s2))
+    assert (oracle.jac_to_affine(0, r12) == oracle.jac_to_affine(0, oracle.jac_add(0, r1, r2))).all()
+
+
+def test_edge_cases(oracle, dev):
+    """zero scalars, s = 1, s = r - 1, identity bases (x == 0), duplicate bases, P / -P pairs, all-zero input."""
+    _ffi, gu = dev
+    n = 1 << 8
+    bases = oracle.gen_bases(0, 21, n).reshape(n, 64).copy()
+    scal = oracle.gen_scalars(1, 22, n).reshape(n, 32).copy()
+    one = oracle.field_const(1, 1)
+    scal[0] = 0; scal[1] = one; scal[2] = oracle.f_neg(1, one)
+    bases[3] = 0
+    bases[5] = bases[4]
+    bases[7] = bases[6]; bases[7, 32:] = oracle.f_neg(0, bases[6, 32:].copy()); scal[7] = scal[6]
+    exp = oracle.jac_to_affine(0, oracle.msm(0, bases, scal, n, c=8))
+    for coord in (0, 1):
+        assert (affine(oracle, 0, gu.msm_device(bases.reshape(-1), scal.reshape(-1), n, coord), coord) == exp).all()
+    z = gu.msm_device(bases.reshape(-1), np.zeros(n * 32, np.uint8), n)
+    assert not z[64:].any()                                      # identity: z == 0
+    ident = gu.msm_device(np.zeros(n * 64, np.uint8), scal.reshape(-1), n)
+    assert not ident[64:].any()
+
+
+@pytest.mark.parametrize("mode", ["all_equal", "small", "two_values", "top_heavy"])
+def test_skewed_scalars(oracle, dev, mode):
+    """scalar distributions that put most points into a few buckets (the oversized-bucket path)"""
+    _ffi, gu = dev
+    k, n = 14, 1 << 14
+    bases = oracle.gen_bases(0, 5, n)
+    base = oracle.gen_scalars(1, 6, n).reshape(n, 32).copy()
+    if mode == "all_equal":
+        base[:] = base[0]
+    elif mode == "small":
+        small = np.zeros((n, 32), np.uint8); small[:, 0] = np.arange(n) % 3      # canonical 0,1,2
+        base = oracle.f_to_mont(1, small.reshape(-1)).reshape(n, 32)
+    elif mode == "two_values":
+        base[::2] = base[0]; base[1::2] = base[1]
+    else:   # r - 1 - small: the top window is full for every scalar
+        small = np.zeros((n, 32), np.uint8); small[:, 0] = np.arange(n) % 7 + 1
+        base = oracle.f_neg(1, oracle.f_to_mont(1, small.reshape(-1))).reshape(n, 32)
+    exp = oracle.jac_to_affine(0, oracle.msm(0, bases, base.reshape(-1), n, c=10))
+    assert (oracle.jac_to_affine(0, gu.msm_device(bases, base.reshape(-1), n)) == exp).all()
+
+
+@pytest.mark.parametrize("n", [1, 3, 1000, 5000, (1 << 15) + 17])
+def test_arbitrary_point_count(oracle, dev, n):
+    """panda_msm_execute_bn254_n: the shard entry point (n need not be a power of two)"""
+    _ffi, gu = dev
+    bases = oracle.gen_bases(0, 33, n)
+    scal = oracle.gen_scalars(1, 34, n)
+    exp = oracle.jac_to_affine(0, oracle.msm(0, bases, scal, n, c=10))
+    assert (oracle.jac_to_affine(0, gu.msm_device(bases, scal, n)) == exp).all()
+
+
+@pytest.mark.parametrize("c,seg", [(8, 8), (11, 32), (13, 8), (16, 64), (16, 512), (12, 0)])
+def test_window_and_segment_choices_agree(oracle, dev, c, seg):
+    _ffi, gu = dev
+    k, n = 13, 1 << 13
+    bases = oracle.gen_bases(0, 50, n)
+    scal = oracle.gen_scalars(1, 51, n)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, 50, scal, n))
+    got = gu.msm_device(bases, scal, n, c_override=c, seg_override=seg)
+    assert (oracle.jac_to_affine(0, got) == exp).all()
+
+
+@pytest.mark.parametrize("k", [4, 10, 13, 16])
+def test_bls12_377(oracle, dev, k):
+    """second curve through the same templated pipeline (12-limb Fq, 253-bit Fr)"""
+    _ffi, gu = dev
+    n = 1 << k
+    bases = oracle.gen_bases(1, oracle.seed_for(k), n)
+    scal = oracle.gen_scalars(3, oracle.seed_for(k) + 1, n)
+    exp = oracle.jac_to_affine(1, oracle.expected_progression_msm(1, oracle.seed_for(k), scal, n))
+    for coord in (0, 1):
+        assert (affine(oracle, 1, gu.msm_device(bases, scal, n, coord, curve=1), coord) == exp).all()
+
+
+def test_inputs_are_not_modified_and_calls_repeat(oracle, dev):
+    """cached scalars / bases stay intact (the reference converts scalars in place, msm_cuda.cuh:155) and a second call on
+    the same cached input returns the same point"""
+    ffi, gu = dev
+    k, n = 12, 1 << 12
+    bases = oracle.gen_bases(0, 60, n); scal = oracle.gen_scalars(1, 61, n)
+    d_b, d_s, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf.from_numpy(scal), gu.DevBuf(96)
+    stream = ffi.PandaStream.new()
+    cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), stream, d_b.ptr, d_s.ptr, d_r.ptr, k, 0)
+    outs = []
+    for _ in range(3):
+        assert ffi.lib.panda_msm_execute_bn254(cfg) == 0
+        stream.sync()
+        outs.append(oracle.jac_to_affine(0, d_r.to_numpy()))
+    assert (d_s.to_numpy() == scal).all() and (d_b.to_numpy() == bases).all()
+    assert (outs[0] == outs[1]).all() and (outs[1] == outs[2]).all()
+    assert (outs[0] == oracle.jac_to_affine(0, oracle.expected_progression_msm(0, 60, scal, n))).all()
+
+
+def test_error_behaviour(dev):
+    ffi, _gu = dev
+    cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), ffi.PandaStream.null(), None, None, None, 4, 0)
+    assert ffi.lib.panda_msm_execute_bn254(cfg) != 0           # null pointers -> a cudaError_t, not a crash
+
+
+def test_host_api_all_variants(oracle, dev):
+    """the mirror of src/gpu_manager/unit.rs: host slices in, 96 result bytes out -- the calls the reference's Rust tests make"""
+    from panda_b200 import gpu_manager as gm
+
+    assert gm.get_device_number() >= 1
+    info = gm.device_info(0)
+    assert 0 < info.free <= info.total
+    k, n = 12, 1 << 12
+    bases = oracle.gen_bases(0, 70, n); scal = oracle.gen_scalars(1, 71, n)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, 70, scal, n))
+    m = gm.PandaGpuManager.new(0)
+    try:
+        assert (oracle.jac_to_affine(0, gm.panda_msm_bn254_gpu(m, scal, bases)) == exp).all()
+        bi = m.cache_bases(bases)
+        si = m.cache_scalars(scal)
+        assert (oracle.jac_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_bases(m, scal, bi)) == exp).all()
+        assert (oracle.jac_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_scalars(m, si, bases)) == exp).all()
+        for _ in range(2):      # cached input survives repeated use
+            assert (oracle.jac_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_input(m, si, bi)) == exp).all()
+        assert (oracle.jac_to_affine(0, gm.panda_msm_bn254_gpu_host(m, scal, bases)) == exp).all()
+        m.set_config(gm.PandaMSMResultCoordinateType.Projective)
+        assert (oracle.proj_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_input(m, si, bi)) == exp).all()
+        from panda_b200.gpu_ffi import PandaGpuError
+        with pytest.raises(PandaGpuError):
+            gm.panda_msm_bn254_gpu_with_cached_input(m, 5, bi)          # BasesIndexErr, unit.rs:283-285
+    finally:
+        m.deinit()
+
+
+def test_host_api_init_all(oracle, dev, golden_k13):
+    """PandaGpuManager::init_all(.., MSM, Some(&[bases]), None) then the host-pointer path -- tests/test.rs:131-166"""
+    from panda_b200 import gpu_manager as gm
+
+    m = gm.PandaGpuManager.init_all(0, gm.PandaGpuManagerInitUnitType.PandaGpuManagerInitUnitTypeMSM, [golden_k13["bases"]], None)
+    try:
+        r = gm.panda_msm_bn254_gpu_host(m, golden_k13["scalars"], golden_k13["bases"])
+        assert (oracle.jac_to_affine(0, r) == golden_k13["result_affine"]).all()
+        r = gm.panda_msm_bn254_gpu_with_cached_bases(m, golden_k13["scalars"], 0)
+        assert (oracle.jac_to_affine(0, r) == golden_k13["result_affine"]).all()
+    finally:
+        m.deinit()
+    from panda_b200.gpu_ffi import PandaGpuError
+    with pytest.raises(PandaGpuError):
+        gm.PandaGpuManager.init_all(0, gm.PandaGpuManagerInitUnitType.PandaGpuManagerInitUnitTypeMSM, None, None)   # MSMBasesAddrError
+
+
+def test_combine_partials(oracle, dev):
+    """panda_msm_combine_bn254: the tail of the sharded MSM"""
+    ffi, gu = dev
+    n, parts = 1 << 10, 4
+    bases = oracle.gen_bases(0, 80, n); scal = oracle.gen_scalars(1, 81, n)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, 80, scal, n))
+    step = n // parts
+    partials = np.concatenate([gu.msm_device(bases[i * step * 64:(i + 1) * step * 64], scal[i * step * 32:(i + 1) * step * 32], step) for i in range(parts)])
+    d_p, d_o = gu.DevBuf.from_numpy(partials), gu.DevBuf(96)
+    for coord in (0, 1):
+        assert ffi.lib.panda_msm_combine_bn254(d_p.ptr, parts, d_o.ptr, coord, ffi.PandaStream.null()) == 0
+        assert ffi.lib.panda_stream_synchronize(ffi.PandaStream.null()) == 0
+        assert (affine(oracle, 0, d_o.to_numpy(), coord) == exp).all()

@@ -1,0 +1,113 @@
+"""-m gpu: NTT parity.  The reference's kernels are compiled out (fft.cu:18-35,89-101,117-168), so bit-exactness is
+defined against the oracle's DFT (oracle/panda_oracle.c po_ntt == po_dft_at): forward, natural order in and out, no
+scaling, caller's omega, canonical Montgomery outputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from panda_b200 import gpu_ffi as ffi
+    import gpu_util
+
+    return ffi, gpu_util
+
+
+def run_ntt(ffi, gu, x, k, omega, inverse=False, v1=True):
+    dsrc, ddst = gu.DevBuf.from_numpy(x), gu.DevBuf(max(x.size, 32))
+    flag = C.c_uint(99)
+    om = np.ascontiguousarray(omega).copy()
+    s = ffi.PandaStream.null()
+    if v1:
+        cfg = ffi.NttconfigurationV1(ffi.PandaMemPool.null(), s, dsrc.ptr, ddst.ptr, om.ctypes.data, k, C.pointer(flag))
+        rc = (ffi.lib.panda_intt_execute_bn254_v1 if inverse else ffi.lib.panda_ntt_execute_bn254_v1)(cfg)
+    else:
+        assert ffi.lib.panda_ntt_setup_bn254(om.ctypes.data) == 0
+        cfg = ffi.NTTConfiguration(ffi.PandaMemPool.null(), s, dsrc.ptr, ddst.ptr, k, C.pointer(flag))
+        rc = ffi.lib.panda_ntt_execute_bn254(cfg)
+    assert rc == 0
+    assert flag.value == ((k + 7) // 8) & 1          # fft.cu:193-211: passes & 1 with MAX_LOG2_RADIX = 8
+    assert ffi.lib.panda_stream_synchronize(s) == 0
+    out = (ddst if flag.value else dsrc).to_numpy(x.size)
+    dsrc.free(); ddst.free()
+    return out
+
+
+@pytest.mark.parametrize("k", list(range(0, 21)))
+def test_forward_matches_oracle(oracle, dev, k):
+    ffi, gu = dev
+    x = oracle.gen_scalars(1, 1000 + k, 1 << k)
+    w = oracle.omega_bn254(k)
+    assert (run_ntt(ffi, gu, x, k, w) == oracle.ntt(1, x, k, w)).all()
+
+
+@pytest.mark.parametrize("k", [3, 11, 18])
+def test_setup_then_execute_v0(oracle, dev, k):
+    """panda_ntt_setup_bn254(omega) + panda_ntt_execute_bn254: the init_ntt / panda_ntt_bn254_gpu shape (wrapper.rs:199-210)"""
+    ffi, gu = dev
+    x = oracle.gen_scalars(1, 7 + k, 1 << k)
+    w = oracle.omega_bn254(k)
+    assert (run_ntt(ffi, gu, x, k, w, v1=False) == oracle.ntt(1, x, k, w)).all()
+    assert ffi.lib.panda_ntt_tear_down() == 0
+    cfg = ffi.NTTConfiguration(ffi.PandaMemPool.null(), ffi.PandaStream.null(), None, None, k, C.pointer(C.c_uint(0)))
+    assert ffi.lib.panda_ntt_execute_bn254(cfg) != 0          # executing after tear_down without setup is an error, not UB
+
+
+@pytest.mark.parametrize("k", [1, 8, 9, 16, 17, 20, 22])
+def test_inverse_round_trip(oracle, dev, k):
+    ffi, gu = dev
+    x = oracle.gen_scalars(1, 2000 + k, 1 << k)
+    w = oracle.omega_bn254(k)
+    y = run_ntt(ffi, gu, x, k, w)
+    assert (run_ntt(ffi, gu, y, k, w, inverse=True) == x).all()
+
+
+def test_full_size_2_24(oracle, dev):
+    """BASELINE.json's size: DFT definition at spot indices (O(n) each), linearity, round trip"""
+    ffi, gu = dev
+    k, n = 24, 1 << 24
+    x = oracle.gen_scalars(1, 31337, n)
+    w = oracle.omega_bn254(k)
+    y = run_ntt(ffi, gu, x, k, w)
+    for j in (0, 1, n // 2, n - 1, 0x5A5A5A, 123457):
+        assert (oracle.dft_at(1, x, k, w, j) == y[j * 32:(j + 1) * 32]).all()
+    assert (run_ntt(ffi, gu, y, k, w, inverse=True) == x).all()
+    x2 = oracle.gen_scalars(1, 4711, n)
+    y2 = run_ntt(ffi, gu, x2, k, w)
+    assert (run_ntt(ffi, gu, oracle.f_add(1, x, x2), k, w) == oracle.f_add(1, y, y2)).all()
+
+
+def test_special_inputs(oracle, dev):
+    ffi, gu = dev
+    k, n = 10, 1 << 10
+    w = oracle.omega_bn254(k)
+    one = oracle.field_const(1, 1)
+    delta = np.zeros(n * 32, np.uint8); delta[:32] = one
+    assert (run_ntt(ffi, gu, delta, k, w) == np.tile(one, n)).all()               # DFT(delta) = all ones
+    const = np.tile(one, n)
+    y = run_ntt(ffi, gu, const, k, w)
+    nm = oracle.f_to_mont(1, np.frombuffer(n.to_bytes(32, "little"), np.uint8).copy())
+    assert (y[:32] == nm).all() and not y[32:].any()                             # DFT(1) = n * delta
+    assert not run_ntt(ffi, gu, np.zeros(n * 32, np.uint8), k, w).any()
+
+
+def test_host_api_ntt(oracle, dev):
+    """panda_ntt_bn254_gpu / _v1 of src/gpu_manager/unit.rs:418-543: host slice transformed in place"""
+    from panda_b200 import gpu_manager as gm
+
+    k, n = 14, 1 << 14
+    x = oracle.gen_scalars(1, 555, n)
+    w = oracle.omega_bn254(k)
+    exp = oracle.ntt(1, x, k, w)
+    m = gm.PandaGpuManager.init_all(0, gm.PandaGpuManagerInitUnitType.PandaGpuManagerInitUnitTypeNTT, None, w)
+    try:
+        a = x.copy(); gm.panda_ntt_bn254_gpu(m, a, k)
+        assert (a == exp).all()
+        b = x.copy(); gm.panda_ntt_bn254_gpu_v1(m, b, w, k)
+        assert (b == exp).all()
+    finally:
+        m.deinit()
