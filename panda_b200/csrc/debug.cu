@@ -72,20 +72,23 @@ __global__ void k_imad_peak(unsigned iters, uint32_t seed, uint32_t *sink) {
 }
 
 __global__ void k_imad_wide_peak(unsigned iters, uint32_t seed, unsigned long long *sink) {
-    unsigned long long a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+    // 16 independent accumulators per thread, each step one 32 x 32 + 64 -> 64 multiply-add (IMAD.WIDE.U32)
+    unsigned long long a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = (unsigned long long)(seed + threadIdx.x) * (2 * k + 3);
     const uint32_t m = seed | 1;
 #pragma unroll 1
     for (unsigned i = 0; i < iters; i++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            // 32 x 32 + 64 -> 64: one IMAD.WIDE.U32 each
-            a0 = (unsigned long long)(uint32_t)a1 * m + a0; a1 = (unsigned long long)(uint32_t)a2 * m + a1;
-            a2 = (unsigned long long)(uint32_t)a3 * m + a2; a3 = (unsigned long long)(uint32_t)a0 * m + a3;
-            a4 = (unsigned long long)(uint32_t)a5 * m + a4; a5 = (unsigned long long)(uint32_t)a6 * m + a5;
-            a6 = (unsigned long long)(uint32_t)a7 * m + a6; a7 = (unsigned long long)(uint32_t)a4 * m + a7;
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) a[k] = (unsigned long long)(uint32_t)a[k] * m + a[k];
         }
     }
-    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678ull) sink[0] = a0;
+    unsigned long long x = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) x ^= a[k];
+    if (x == 0x12345678ull) sink[0] = x;
 }
 
 __global__ void __launch_bounds__(256) k_modmul_peak(unsigned iters, uint32_t seed, uint32_t *sink) {
