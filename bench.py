@@ -303,17 +303,18 @@ def run_own_arm(args):
     # ---- per-kernel attribution (rank 0): CUDA events on the launching stream, a separate instrumented pass
     peaks, peak_kind = load_peaks()
     stage = (C.c_float * 7)()
+    info = (C.c_uint * 3)()
     d_r = torch.empty(96, dtype=torch.uint8, device=dev)
     cfg = ffi.MSMConfiguration(pool, ffi.PandaStream(stream), bases_d.data_ptr(), scal_d.data_ptr(), d_r.data_ptr(), 0, 0)
     stages = np.zeros(7)
     reps = 3
     for _ in range(reps):
-        assert ffi.lib.panda_debug_msm_timed(0, cfg, n_local, 0, 0, stage) == 0
+        assert ffi.lib.panda_debug_msm_timed(0, cfg, n_local, 0, 0, -1, stage, info) == 0
         stages += np.array(list(stage))
     stages /= reps
     names = ["digits", "scan", "scatter", "accumulate", "bucket_reduce", "window_reduce", "final"]
     plan = ffi.MsmPlanInfo()
-    ffi.lib.panda_debug_msm_plan(0, n_local, 0, 0, C.byref(plan))
+    ffi.lib.panda_debug_msm_plan(0, n_local, info[0], info[1], 0, C.byref(plan))
     W = plan.windows
     entries = n_local * W                                   # mixed additions (zero digits are ~2^-c of them)
     acc_ms = float(stages[3])

@@ -33,15 +33,20 @@ panda_error panda_debug_curve_op(int curve_id, int op, const void *p, const void
 typedef struct panda_debug_msm_plan_info {
     unsigned window_bits, windows, buckets_per_window, segment_len, segments_per_window, reduce_chunk;
     size_t workspace_bytes;
+    unsigned folded, bucket_sets, groups;   /* folded = 1: plan for a precomputed 2^(c*j)*P table (one bucket set) */
+    size_t table_bytes;
 } panda_debug_msm_plan_info;
-/* the plan msm_execute would use for n points (c_override / seg_override = 0: automatic) */
-panda_error panda_debug_msm_plan(int curve_id, size_t n, unsigned c_override, unsigned seg_override, panda_debug_msm_plan_info *out);
+/* the plan msm_execute would use for n points (c_override / seg_override = 0: automatic); folded selects the table plan */
+panda_error panda_debug_msm_plan(int curve_id, size_t n, int folded, unsigned c_override, unsigned seg_override, panda_debug_msm_plan_info *out);
 
-/* MSM with explicit window width / segment length and per-stage device times.
+/* MSM with explicit window width / segment length / table mode and per-stage device times.
+ * table_mode: -1 default (env PANDA_MSM_PRECOMPUTE, else auto), 0 never use tables, 1 auto (table after the second sighting of the
+ * same bases), 2 eager (table at first sight).
  * stage_ms (HOST float[7], may be NULL): digits, scan, scatter, accumulate, bucket_reduce, window_reduce, final.
- * Synchronises the stream when stage_ms != NULL. */
+ * info (HOST unsigned[3], may be NULL): folded, window bits, windows actually used.
+ * Synchronises the stream when stage_ms or info is given. */
 panda_error panda_debug_msm_timed(int curve_id, const panda_msm_configuration cfg, size_t n, unsigned c_override, unsigned seg_override,
-                                  float *stage_ms);
+                                  int table_mode, float *stage_ms, unsigned *info);
 
 /* Integer-pipe microbenchmarks on the current device (synchronous).
  * kind 0: independent IMAD (32-bit) chains, 1: independent IMAD.WIDE chains, 2: Montgomery products (BN254 Fq) in

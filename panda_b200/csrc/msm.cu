@@ -1,21 +1,30 @@
 // msm.cu -- Pippenger MSM for sm_100a: signed-digit windows, counting sort of point indices by bucket,
 // load-balanced bucket accumulation (XYZZ mixed additions), parallel running-sum bucket reduction with
-// warp-shuffle stitching, on-device window combination.  See msm.cuh / DESIGN.md.
+// warp-shuffle stitching, on-device window combination; for bases that are reused across calls, a table of
+// 2^(c*j) * P multiples folds all windows into one bucket set.  See msm.cuh / DESIGN.md.
 //
 // Replaces src/cuda/core/unit/msm/msm_cuda.cuh:552-769 of the reference (kernels :148-282, :373-497 and
 // the host-side Horner :59-77).  Written from scratch for B200; nothing here is derived from that code.
-// This file holds the plan (window width, segment length, workspace layout) and the per-curve dispatch;
-// the kernels live in msm_impl.cuh.
+// This file holds the plan (window width, segment length, workspace layout), the table cache and the per-curve
+// dispatch; the kernels live in msm_impl.cuh.
 #include "msm.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
 
 namespace pb {
 
-cudaError_t msm_run_bn254(const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord, cudaMemPool_t pool,
-                          cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings);
-cudaError_t msm_run_bls12_377(const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord, cudaMemPool_t pool,
-                              cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings);
+// per-curve instantiations (msm_bn254.cu / msm_bls12_377.cu)
+cudaError_t msm_pipeline_bn254(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
+                               cudaStream_t stream, MsmStageTimes *timings);
+cudaError_t msm_pipeline_bls12_377(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
+                                   cudaStream_t stream, MsmStageTimes *timings);
+cudaError_t msm_build_table_bn254(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream);
+cudaError_t msm_build_table_bls12_377(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream);
+cudaError_t msm_fingerprint_launch(const void *data, size_t bytes, unsigned long long *d_out, cudaStream_t stream);
 cudaError_t msm_combine_bn254(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream);
 cudaError_t msm_combine_bls12_377(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream);
 
@@ -32,59 +41,198 @@ static uint32_t windows_for(uint32_t bits, uint32_t c) {
 
 static uint32_t pow2_floor(uint64_t v) { uint32_t r = 1; while ((uint64_t)r * 2 <= v) r *= 2; return r; }
 
-MsmPlan msm_make_plan(CurveId curve, uint32_t n, uint32_t c_override, uint32_t seg_override) {
+MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget) {
     const uint32_t bits = curve == CURVE_BLS12_377 ? 253 : 254;
     const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
     MsmPlan p{};
     p.n = n;
-    uint32_t best_c = 8;
-    if (c_override >= 8 && c_override <= 16) best_c = c_override;
-    else {
-        double best = 1e300;
-        for (uint32_t c = 8; c <= 16; c++) {
-            double W = windows_for(bits, c), nb = (double)(1u << (c - 1));
-            // modmul counts: mixed add 10, bucket combine + running sums ~ (2 + 1.5) full adds of 14
-            double cost = (double)n * W * 10.0 + W * nb * 3.5 * 14.0;
-            if (cost < best) { best = cost; best_c = c; }
+    p.folded = folded ? 1 : 0;
+    const uint32_t c_lo = 8, c_hi = folded ? 23 : 16;          // windowed digit codes are 16 bit
+    uint32_t best_c = 0;
+    double best = 1e300;
+    for (uint32_t c = c_lo; c <= c_hi; c++) {
+        if (c_override && c != c_override) continue;
+        const double W = windows_for(bits, c), nb = (double)(1u << (c - 1));
+        if (W > 32) continue;
+        if (folded) {
+            if ((double)n * W >= 2147483648.0) continue;                            // table index + sign must fit 32 bits
+            if ((double)n * W * 2 * fq_bytes > (double)table_budget) continue;
         }
+        // modmul counts: mixed add 10; bucket combine + running sums ~3.5 full adds of 14 per bucket (the reduction kernels
+        // run at about half the accumulate kernel's rate, hence the factor 2); folded mode has a single bucket set
+        const double cost = (double)n * W * 10.0 + (folded ? 1.0 : W) * nb * 3.5 * 14.0 * 2.0;
+        if (cost < best) { best = cost; best_c = c; }
     }
+    if (!best_c) { p.c = 0; return p; }                         // no feasible plan (folded table would not fit)
     p.c = best_c;
     p.windows = windows_for(bits, p.c);
     p.nb = 1u << (p.c - 1);
+    p.sets = folded ? 1 : p.windows;
+    p.stride = folded ? n * p.windows : n;
+    p.table_bytes = folded ? (size_t)n * p.windows * 2 * fq_bytes : 0;
     // segment length: about one average bucket, so that most buckets end up with one or two partial sums, but
     // never so long that the accumulation kernel has fewer than ~4 waves of threads (148 SMs x 384 threads)
-    uint64_t entries = (uint64_t)n * p.windows;
-    uint32_t L = pow2_floor(std::max<uint64_t>(1, n / p.nb));
+    const uint64_t entries = (uint64_t)n * p.windows;
+    uint32_t L = pow2_floor(std::max<uint64_t>(1, entries / ((uint64_t)p.nb * p.sets)));
     L = std::min<uint32_t>(L, pow2_floor(std::max<uint64_t>(1, entries / (148ull * 384 * 4))));
     L = std::min<uint32_t>(std::max<uint32_t>(L, 8), 512);
     if (seg_override) L = seg_override;
     p.seg_len = L;
-    p.segs_pw = n ? (n + L - 1) / L : 0;
-    uint32_t m = pow2_floor(std::max<uint64_t>(1, ((uint64_t)p.windows * p.nb) / 65536));
+    p.segs_ps = p.stride ? (p.stride + L - 1) / L : 0;
+    uint32_t m = pow2_floor(std::max<uint64_t>(1, ((uint64_t)p.sets * p.nb) / 65536));
     m = std::min<uint32_t>(std::min<uint32_t>(m, 32), p.nb);
     p.chunk = m;
-    p.chunks_pw = p.nb / m;
+    p.chunks_ps = p.nb / m;
+    p.groups = std::min<uint32_t>(32, std::max<uint32_t>(1, p.chunks_ps / 1024));
 
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
-    p.off_counts = off;  off = align(off + (size_t)p.windows * p.nb * 4 + 4);      // + the big-bucket counter
-    p.off_offsets = off; off = align(off + (size_t)p.windows * (p.nb + 1) * 4);
-    p.off_cursor = off;  off = align(off + (size_t)p.windows * p.nb * 4);
-    p.off_biglist = off; off = align(off + (size_t)p.windows * p.nb * 4);
-    p.off_digits = off;  off = align(off + (size_t)p.windows * n * 2);
-    p.off_sorted = off;  off = align(off + (size_t)p.windows * n * 4);
-    p.off_slots = off;   off = align(off + (size_t)p.windows * ((size_t)p.segs_pw + p.nb) * 4 * fq_bytes);
-    p.off_chunks = off;  off = align(off + (size_t)p.windows * p.chunks_pw * 2 * 4 * fq_bytes);
-    p.off_wsums = off;   off = align(off + (size_t)p.windows * 4 * fq_bytes);
+    p.off_counts = off;  off = align(off + (size_t)p.sets * p.nb * 4 + 4);      // + the big-bucket counter
+    p.off_offsets = off; off = align(off + (size_t)p.sets * (p.nb + 1) * 4);
+    p.off_cursor = off;  off = align(off + (size_t)p.sets * p.nb * 4);
+    p.off_biglist = off; off = align(off + (size_t)p.sets * p.nb * 4);
+    p.off_tiles = off;   off = align(off + (size_t)p.sets * ((p.nb + 4095) / 4096) * 4);
+    p.off_digits = off;  off = align(off + (folded ? 0 : (size_t)p.windows * n * 2));
+    p.off_sorted = off;  off = align(off + (size_t)p.sets * p.stride * 4);
+    p.off_slots = off;   off = align(off + (size_t)p.sets * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);
+    p.off_chunks = off;  off = align(off + (size_t)p.sets * p.chunks_ps * 2 * 4 * fq_bytes);
+    p.off_gsums = off;   off = align(off + (size_t)p.sets * p.groups * 2 * 4 * fq_bytes);
     p.bytes = off;
     return p;
 }
 
+// ----------------------------------------------------------------------------------------------------
+// table cache for reused bases
+
+struct TableEntry {
+    int device;
+    CurveId curve;
+    const void *bases;
+    uint32_t n;
+    unsigned long long fingerprint;
+    unsigned sightings;
+    void *table;            // nullptr until built
+    uint32_t c, windows;
+    size_t bytes;
+    cudaEvent_t ready;      // recorded after the build; other streams wait on it
+    unsigned long long last_use;
+};
+
+static std::mutex g_table_mutex;
+static std::vector<TableEntry> g_tables;
+static unsigned long long g_use_clock = 0;
+static constexpr size_t MAX_TABLES = 4;
+
+static void drop_table(TableEntry &e) {
+    if (e.table) { cudaFree(e.table); e.table = nullptr; }      // cudaFree waits for outstanding work on the buffer
+    if (e.ready) { cudaEventDestroy(e.ready); e.ready = nullptr; }
+}
+
+cudaError_t msm_release_tables() {
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &e : g_tables) { cudaSetDevice(e.device); drop_table(e); }
+    g_tables.clear();
+    cudaSetDevice(cur);
+    return cudaSuccess;
+}
+
+static int default_table_mode() {
+    static int mode = [] {
+        const char *e = getenv("PANDA_MSM_PRECOMPUTE");
+        if (!e || !*e) return (int)MSM_TABLE_AUTO;
+        int v = atoi(e);
+        return v < 0 || v > 2 ? (int)MSM_TABLE_AUTO : v;
+    }();
+    return mode;
+}
+
+#define PB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[panda-b200] CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); return e_; } } while (0)
+
+static cudaError_t run_pipeline(CurveId curve, const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord,
+                                cudaMemPool_t pool, cudaStream_t stream, MsmStageTimes *timings) {
+    if (timings) { timings->folded = (int)p.folded; timings->c = p.c; timings->windows = p.windows; }
+    if (curve == CURVE_BLS12_377) return msm_pipeline_bls12_377(p, points, scalars, result, coord, pool, stream, timings);
+    return msm_pipeline_bn254(p, points, scalars, result, coord, pool, stream, timings);
+}
 
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
-                    cudaMemPool_t pool, cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings) {
-    if (curve == CURVE_BLS12_377) return msm_run_bls12_377(bases, scalars, n, result, coord, pool, stream, c_override, seg_override, timings);
-    return msm_run_bn254(bases, scalars, n, result, coord, pool, stream, c_override, seg_override, timings);
+                    cudaMemPool_t pool, cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings, int table_mode) {
+    const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
+    if (n == 0) {   // empty sum: the identity, all-zero like the reference (msm_cuda.cuh:395,405)
+        PB_CUDA(cudaMemsetAsync(result, 0, 3 * fq_bytes, stream));
+        return cudaSuccess;
+    }
+    if (table_mode == MSM_TABLE_DEFAULT) table_mode = default_table_mode();
+    if (table_mode != MSM_TABLE_OFF && n >= 1024) {
+        int dev = 0;
+        PB_CUDA(cudaGetDevice(&dev));
+        // 1. content fingerprint of the bases (one pass over n * 64 bytes at HBM speed, 8 bytes read back)
+        unsigned long long *d_fp = nullptr, fp = 0;
+        PB_CUDA(cudaMallocAsync((void **)&d_fp, 8, stream));
+        cudaError_t e = msm_fingerprint_launch(bases, (size_t)n * 2 * fq_bytes, d_fp, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&fp, d_fp, 8, cudaMemcpyDeviceToHost, stream);
+        cudaError_t f = cudaFreeAsync(d_fp, stream);
+        if (e == cudaSuccess) e = f;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        PB_CUDA(e);
+
+        std::unique_lock<std::mutex> lock(g_table_mutex);
+        TableEntry *hit = nullptr;
+        for (auto &t : g_tables)
+            if (t.device == dev && t.curve == curve && t.bases == bases && t.n == n) { hit = &t; break; }
+        if (hit && hit->fingerprint != fp) {      // same pointer, different points: forget what we knew
+            drop_table(*hit);
+            hit->fingerprint = fp; hit->sightings = 0;
+        }
+        if (!hit) {
+            if (g_tables.size() >= MAX_TABLES) {  // evict the least recently used entry
+                size_t victim = 0;
+                for (size_t i = 1; i < g_tables.size(); i++) if (g_tables[i].last_use < g_tables[victim].last_use) victim = i;
+                int cur = 0; cudaGetDevice(&cur); cudaSetDevice(g_tables[victim].device);
+                drop_table(g_tables[victim]);
+                cudaSetDevice(cur);
+                g_tables.erase(g_tables.begin() + victim);
+            }
+            g_tables.push_back(TableEntry{dev, curve, bases, n, fp, 0, nullptr, 0, 0, 0, nullptr, 0});
+            hit = &g_tables.back();
+        }
+        hit->sightings++;
+        hit->last_use = ++g_use_clock;
+        const bool want = table_mode == MSM_TABLE_EAGER || hit->sightings >= 2;
+        if (!hit->table && want) {
+            size_t free_b = 0, total_b = 0;
+            PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const size_t budget = free_b > ((size_t)6 << 30) ? (free_b - ((size_t)4 << 30)) / 2 : 0;   // leave room for workspaces
+            MsmPlan fp_plan = msm_make_plan(curve, n, true, c_override > 16 ? c_override : 0, 0, budget);
+            if (fp_plan.c) {
+                void *tab = nullptr;
+                if (cudaMalloc(&tab, fp_plan.table_bytes) == cudaSuccess) {
+                    cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, tab, stream)
+                                                              : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, tab, stream);
+                    cudaEvent_t ev = nullptr;
+                    if (be == cudaSuccess) be = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                    if (be == cudaSuccess) be = cudaEventRecord(ev, stream);
+                    if (be != cudaSuccess) { cudaFree(tab); if (ev) cudaEventDestroy(ev); return be; }
+                    hit->table = tab; hit->c = fp_plan.c; hit->windows = fp_plan.windows; hit->bytes = fp_plan.table_bytes; hit->ready = ev;
+                } else {
+                    cudaGetLastError();            // out of memory: stay on the windowed path
+                }
+            }
+        }
+        if (hit->table) {
+            const void *table = hit->table;
+            const uint32_t tc = hit->c;
+            cudaEvent_t ready = hit->ready;
+            lock.unlock();
+            PB_CUDA(cudaStreamWaitEvent(stream, ready, 0));
+            MsmPlan p = msm_make_plan(curve, n, true, tc, seg_override);
+            return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings);
+        }
+    }
+    MsmPlan p = msm_make_plan(curve, n, false, c_override <= 16 ? c_override : 0, seg_override);
+    return run_pipeline(curve, p, bases, scalars, result, coord, pool, stream, timings);
 }
 
 cudaError_t msm_combine(CurveId curve, const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream) {

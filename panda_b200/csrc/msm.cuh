@@ -16,31 +16,48 @@ enum CoordType { COORD_JACOBIAN = 0, COORD_PROJECTIVE = 1 };   // curve.cuh:23-2
 
 struct MsmPlan {
     uint32_t n;            // points
-    uint32_t c;            // window width in bits (signed digits), 1 <= c <= 16
-    uint32_t windows;      // W
-    uint32_t nb;           // buckets per window = 2^(c-1)
+    uint32_t c;            // window width in bits (signed digits)
+    uint32_t windows;      // W digit windows per scalar
+    uint32_t nb;           // buckets per bucket set = 2^(c-1)
+    uint32_t folded;       // 1: precomputed 2^(c*j)*P table, every window feeds ONE bucket set; 0: one bucket set per window
+    uint32_t sets;         // bucket sets: 1 (folded) or W
+    uint32_t stride;       // sorted-entry capacity per set: W*n (folded) or n
     uint32_t seg_len;      // L: sorted entries handled by one accumulation thread
-    uint32_t segs_pw;      // ceil(n / L) segments per window
+    uint32_t segs_ps;      // ceil(stride / L) segments per set
     uint32_t chunk;        // m: buckets folded serially by one reduction thread
-    uint32_t chunks_pw;    // nb / m
+    uint32_t chunks_ps;    // nb / m
+    uint32_t groups;       // CTAs per set in the group-reduce stage (<= 32, divides chunks_ps)
     // workspace layout (byte offsets into one arena)
-    size_t off_counts, off_offsets, off_cursor, off_biglist, off_digits, off_sorted, off_slots, off_chunks, off_wsums, bytes;
+    size_t off_counts, off_offsets, off_cursor, off_biglist, off_tiles, off_digits, off_sorted, off_slots, off_chunks, off_gsums, bytes;
+    size_t table_bytes;    // folded: size of the precomputed table (W * n affine points)
 };
 
-// window width / segment length selection; c_override = 0 -> cost model
-MsmPlan msm_make_plan(CurveId curve, uint32_t n, uint32_t c_override, uint32_t seg_override);
+// window width / segment length selection; c_override = 0 -> cost model.  table_budget: bytes available for a table (folded only).
+MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget = ~(size_t)0);
 
 // Per-stage device timings (ms) filled when msm_run is called with timings != nullptr (adds event syncs;
 // the benchmark harness uses it to attribute time to kernels -- never set on the product path).
-struct MsmStageTimes { float digits, scan, scatter, accumulate, bucket_reduce, window_reduce, final; };
+struct MsmStageTimes { float digits, scan, scatter, accumulate, bucket_reduce, window_reduce, final; int folded; unsigned c, windows; };
+
+// How reused bases are handled (PANDA_MSM_PRECOMPUTE = 0 | 1 | 2 overrides the default AUTO):
+//   OFF   never build tables
+//   AUTO  a (device pointer, n) pair seen a second time with an identical 64-bit content fingerprint gets a table of
+//         2^(c*j) * P multiples (built once, ~10 MSMs of arithmetic, W*n*64 bytes), used from then on
+//   EAGER build at first sight
+enum MsmTableMode { MSM_TABLE_OFF = 0, MSM_TABLE_AUTO = 1, MSM_TABLE_EAGER = 2, MSM_TABLE_DEFAULT = -1 };
 
 // bases: n affine points (x||y Montgomery), scalars: n x 32 B (Montgomery), result: 3 field elements.
-// pool may be nullptr (default pool).  Asynchronous on `stream`.
+// pool may be nullptr (default pool).  Asynchronous on `stream` except for an 8-byte fingerprint read-back when the
+// table cache is enabled.
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result,
                     CoordType coord, cudaMemPool_t pool, cudaStream_t stream,
-                    uint32_t c_override = 0, uint32_t seg_override = 0, MsmStageTimes *timings = nullptr);
+                    uint32_t c_override = 0, uint32_t seg_override = 0, MsmStageTimes *timings = nullptr,
+                    int table_mode = MSM_TABLE_DEFAULT);
 
 // result = sum of `count` Jacobian partials (the per-GPU results of a sharded MSM), then coordinate conversion.
 cudaError_t msm_combine(CurveId curve, const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream);
+
+// drops every cached table (all devices); synchronises
+cudaError_t msm_release_tables();
 
 }  // namespace pb

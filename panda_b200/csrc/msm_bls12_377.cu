@@ -3,9 +3,12 @@
 
 namespace pb {
 
-cudaError_t msm_run_bls12_377(const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord, cudaMemPool_t pool,
-                         cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings) {
-    return msm_run_t<Bls377>(CURVE_BLS12_377, bases, scalars, n, result, coord, pool, stream, c_override, seg_override, timings);
+cudaError_t msm_pipeline_bls12_377(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
+                            cudaStream_t stream, MsmStageTimes *timings) {
+    return msm_pipeline_t<Bls377>(p, points, scalars, result, coord, pool, stream, timings);
+}
+cudaError_t msm_build_table_bls12_377(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream) {
+    return msm_build_table_t<Bls377>(bases, n, c, W, table, stream);
 }
 cudaError_t msm_combine_bls12_377(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream) {
     return msm_combine_t<Bls377>(partials, count, result, coord, stream);

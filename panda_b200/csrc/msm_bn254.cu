@@ -3,12 +3,18 @@
 
 namespace pb {
 
-cudaError_t msm_run_bn254(const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord, cudaMemPool_t pool,
-                         cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings) {
-    return msm_run_t<Bn254>(CURVE_BN254, bases, scalars, n, result, coord, pool, stream, c_override, seg_override, timings);
+cudaError_t msm_pipeline_bn254(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
+                            cudaStream_t stream, MsmStageTimes *timings) {
+    return msm_pipeline_t<Bn254>(p, points, scalars, result, coord, pool, stream, timings);
+}
+cudaError_t msm_build_table_bn254(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream) {
+    return msm_build_table_t<Bn254>(bases, n, c, W, table, stream);
 }
 cudaError_t msm_combine_bn254(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream) {
     return msm_combine_t<Bn254>(partials, count, result, coord, stream);
+}
+cudaError_t msm_fingerprint_launch(const void *data, size_t bytes, unsigned long long *d_out, cudaStream_t stream) {
+    return msm_fingerprint(data, bytes, d_out, stream);
 }
 
 }  // namespace pb

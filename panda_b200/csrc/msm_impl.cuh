@@ -28,72 +28,137 @@ static constexpr int BIG_THREADS = 256;
 static constexpr uint32_t BIG_SPAN = 8;             // buckets with more partial slots than this are pre-reduced by a whole CTA
 
 // ----------------------------------------------------------------------------------------------------
-// K1: scalars -> signed window digits (window-major, 16 bit) + per-(window,bucket) counts.
-// HBM-bound: 32 B read + 2W B written per scalar, W reductions into an L2-resident histogram.
+// Signed-digit recoding of one canonical scalar, shared by the histogram and the scatter kernels.
+// Calls f(window, magnitude (1 .. 2^(c-1)), negative) for every non-zero digit.
+template <class Fr, class F>
+PB_DEV void for_each_digit(Fr s, uint32_t c, uint32_t W, uint32_t nb, F &&f) {
+    uint32_t carry = 0;
+    const uint32_t mask = (1u << c) - 1;
+    for (uint32_t w = 0; w < W; w++) {
+        uint32_t v = (s.l[0] & mask) + carry;
+#pragma unroll
+        for (int k = 0; k < Fr::N - 1; k++) s.l[k] = __funnelshift_r(s.l[k], s.l[k + 1], c);
+        s.l[Fr::N - 1] >>= c;
+        uint32_t mag = v, neg = 0;
+        carry = 0;
+        if (w + 1 < W && v > nb) { mag = (1u << c) - v; neg = 1; carry = 1; }   // the top window is never recoded
+        if (mag) f(w, mag, neg);
+    }
+}
 
-template <class C>
+// K1: scalars -> per-bucket counts (and, in windowed mode, the 16-bit digit codes, window-major).
+// FOLDED (precomputed 2^(c*j) * P tables): every window feeds the single bucket set, nothing is stored.
+// HBM / L2-atomic bound: 32 B read (+ 2W B written) per scalar, W reductions into an L2-resident histogram.
+template <class C, bool FOLDED>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb,
                                                 uint16_t *__restrict__ digits, uint32_t *__restrict__ counts) {
     using Fr = typename C::Fr;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; input untouched
-        uint32_t carry = 0;
-        const uint32_t mask = (1u << c) - 1;
-        for (uint32_t w = 0; w < W; w++) {
-            uint32_t v = (s.l[0] & mask) + carry;
-#pragma unroll
-            for (int k = 0; k < Fr::N - 1; k++) s.l[k] = __funnelshift_r(s.l[k], s.l[k + 1], c);
-            s.l[Fr::N - 1] >>= c;
-            uint32_t mag = v, neg = 0;
-            carry = 0;
-            if (w + 1 < W && v > nb) { mag = (1u << c) - v; neg = 1; carry = 1; }
-            uint32_t code = mag ? ((mag - 1) | (neg << 15)) : DIGIT_SKIP;
-            digits[(size_t)w * n + i] = (uint16_t)code;
-            if (mag) atomicAdd(&counts[(size_t)w * nb + (mag - 1)], 1u);
+        Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; the input is left untouched
+        if (FOLDED) {
+            for_each_digit(s, c, W, nb, [&](uint32_t, uint32_t mag, uint32_t) { atomicAdd(&counts[mag - 1], 1u); });
+        } else {
+            uint32_t next_w = 0;
+            for_each_digit(s, c, W, nb, [&](uint32_t w, uint32_t mag, uint32_t neg) {
+                for (; next_w < w; next_w++) digits[(size_t)next_w * n + i] = (uint16_t)DIGIT_SKIP;
+                digits[(size_t)w * n + i] = (uint16_t)((mag - 1) | (neg << 15));
+                next_w = w + 1;
+                atomicAdd(&counts[(size_t)w * nb + (mag - 1)], 1u);
+            });
+            for (; next_w < W; next_w++) digits[(size_t)next_w * n + i] = (uint16_t)DIGIT_SKIP;
         }
     }
 }
 
-// K2: per-window exclusive scan of the bucket counts -> offsets[w][0..nb], cursor[w][0..nb-1].  Buckets whose entries
-// span more than BIG_SPAN accumulation segments (the short top window, skewed scalars) are appended to big_list.
-static __global__ void __launch_bounds__(1024) k_scan(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t L, uint32_t *__restrict__ offsets,
-                                                      uint32_t *__restrict__ cursor, uint32_t *__restrict__ big_count, uint32_t *__restrict__ big_list) {
+// K2a/b/c: exclusive scan of the bucket counts of every bucket set -> offsets[set][0..nb], cursor[set][0..nb-1].
+// Three small launches (tile sums, scan of the tile sums, apply) so that a 2^21-bucket set is scanned by 512 CTAs.
+// Buckets whose entries span more than BIG_SPAN accumulation segments are appended to big_list.
+static constexpr uint32_t SCAN_TILE = 4096;
+
+static __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t tiles_ps, uint32_t *__restrict__ tile_sums) {
     __shared__ uint32_t warp_tot[32];
-    const uint32_t w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t *cw = counts + (size_t)w * nb;
-    uint32_t *ow = offsets + (size_t)w * (nb + 1);
-    uint32_t *kw = cursor + (size_t)w * nb;
-    uint32_t running = 0;
-    for (uint32_t base = 0; base < nb; base += 1024) {
-        const uint32_t idx = base + tid;
-        const uint32_t v = idx < nb ? cw[idx] : 0;
-        uint32_t incl = v;
+    const uint32_t set = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const uint32_t *cw = counts + (size_t)set * nb;
+    uint32_t v = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t t = warp_tot[lane];
+    for (int k = 0; k < 4; k++) { const uint32_t idx = tile * SCAN_TILE + k * 1024 + tid; if (idx < nb) v += cw[idx]; }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, t, o); if ((int)lane >= o) t += u; }
-            warp_tot[lane] = t;
-        }
-        __syncthreads();
-        const uint32_t excl = running + (warp ? warp_tot[warp - 1] : 0) + incl - v;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) warp_tot[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        v = warp_tot[tid];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (tid == 0) tile_sums[(size_t)set * tiles_ps + tile] = v;
+    }
+}
+
+// one CTA per set: exclusive scan of its (<= 1024) tile sums in place; the set total goes to offsets[set][nb]
+static __global__ void __launch_bounds__(1024) k_scan_tops(uint32_t *__restrict__ tile_sums, uint32_t tiles_ps, uint32_t nb, uint32_t *__restrict__ offsets) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t set = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *ts = tile_sums + (size_t)set * tiles_ps;
+    const uint32_t v = tid < tiles_ps ? ts[tid] : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t t = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, t, o); if ((int)lane >= o) t += u; }
+        warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const uint32_t excl = (warp ? warp_tot[warp - 1] : 0) + incl - v;
+    if (tid < tiles_ps) ts[tid] = excl;
+    if (tid == 0) offsets[(size_t)set * (nb + 1) + nb] = warp_tot[31];
+}
+
+static __global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ tile_sums, uint32_t nb,
+                                                            uint32_t tiles_ps, uint32_t L, uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
+                                                            uint32_t *__restrict__ big_count, uint32_t *__restrict__ big_list) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t set = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t *cw = counts + (size_t)set * nb;
+    uint32_t *ow = offsets + (size_t)set * (nb + 1);
+    uint32_t *kw = cursor + (size_t)set * nb;
+    // thread owns 4 consecutive counts
+    const uint32_t base = tile * SCAN_TILE + tid * 4;
+    uint32_t c4[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) c4[k] = base + k < nb ? cw[base + k] : 0;
+    const uint32_t v = c4[0] + c4[1] + c4[2] + c4[3];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t t = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, t, o); if ((int)lane >= o) t += u; }
+        warp_tot[lane] = t;
+    }
+    __syncthreads();
+    uint32_t excl = tile_sums[(size_t)set * tiles_ps + tile] + (warp ? warp_tot[warp - 1] : 0) + incl - v;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t idx = base + k;
         if (idx < nb) {
             ow[idx] = excl; kw[idx] = excl;
-            if (v && (excl + v - 1) / L - excl / L + 1 > BIG_SPAN) big_list[atomicAdd(big_count, 1u)] = w * nb + idx;
+            if (c4[k] && (excl + c4[k] - 1) / L - excl / L + 1 > BIG_SPAN) big_list[atomicAdd(big_count, 1u)] = set * nb + idx;
         }
-        running += warp_tot[31];
-        __syncthreads();
+        excl += c4[k];
     }
-    if (tid == 0) ow[nb] = running;
 }
 
-// K3: scatter point indices (with the digit's sign in bit 31) into their bucket's range.  blockIdx.y = window, so
-// one window's 4n-byte output range is being filled at a time and stays in L2 while it is written.
+// K3 (windowed): scatter point indices (digit sign in bit 31) into their bucket's range.  blockIdx.y = window, so one window's
+// 4n-byte output range is being filled at a time and stays in L2 while it is written.
 static __global__ void __launch_bounds__(256) k_scatter(const uint16_t *__restrict__ digits, uint32_t n, uint32_t nb,
-                                                 uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+                                                        uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
     const uint32_t w = blockIdx.y;
     const uint16_t *dw = digits + (size_t)w * n;
     uint32_t *kw = cursor + (size_t)w * nb;
@@ -106,13 +171,27 @@ static __global__ void __launch_bounds__(256) k_scatter(const uint16_t *__restri
     }
 }
 
-// K4: bucket accumulation.  Thread (w, s) owns sorted entries [s*L, (s+1)*L) of window w -- a fixed amount
+// K3 (folded): digits are recomputed from the scalar (cheaper than storing 32-bit codes); entry = table index w*n + i.
+template <class C>
+__global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb,
+                                                        uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+    using Fr = typename C::Fr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();
+        for_each_digit(s, c, W, nb, [&](uint32_t w, uint32_t mag, uint32_t neg) {
+            const uint32_t pos = atomicAdd(&cursor[mag - 1], 1u);
+            sorted[pos] = (w * n + i) | (neg << 31);
+        });
+    }
+}
+
+// K4: bucket accumulation.  Thread (w, s) owns sorted entries [s*L, (s+1)*L) of bucket set w -- a fixed amount
 // of work whatever the bucket sizes are -- and emits one partial sum per bucket it touches into slot
 // (s + bucket), which is unique and makes a bucket's partials contiguous.
 // IMAD-bound: 10 modmul = 1370 IMAD per entry; 4 B index + 64 B (96 B) gathered point read per entry.
 template <class C>
 __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
-                                                           const uint32_t *__restrict__ offsets, uint32_t n, uint32_t nb, uint32_t L,
+                                                           const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
                                                            uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
     using Fq = typename C::Fq;
     using Pt = Xyzz<Fq>;
@@ -125,7 +204,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint8_t *__res
     const uint32_t start = s * L;
     if (start >= cnt) return;
     const uint32_t end = min(start + L, cnt);
-    const uint32_t *sw = sorted + (size_t)w * n;
+    const uint32_t *sw = sorted + (size_t)w * stride;
     uint8_t *slot_w = slots + ((size_t)w * ((size_t)segs_pw + nb) + s) * Pt::BYTES;
 
     uint32_t lo = 0, hi = nb;          // largest b with offsets[b] <= start
@@ -287,25 +366,28 @@ PB_DEV void warp_running_sums(Xyzz<F> &P, Xyzz<F> &R, Xyzz<F> &wR, uint32_t lane
     }
 }
 
-// K6: one CTA per window stitches the chunk sums:  S_w = sum_t Lc_t + m * sum_t t * Rc_t.
+// K6: group reduce.  CTA (g, set) stitches the chunk sums [g*cpg, (g+1)*cpg) of one bucket set:
+//   S_g = sum_t Lc_t + m * sum_t t_local * Rc_t,   Rtot_g = sum_t Rc_t
+// Thread-serial running sums over q items, then warp-shuffle suffix scans across lanes and across warps.
 template <class C>
-__global__ void __launch_bounds__(WIN_THREADS) k_window_reduce(const uint8_t *__restrict__ chunks, uint32_t chunks_pw, uint32_t log2m,
-                                                              uint8_t *__restrict__ wsums) {
+__global__ void __launch_bounds__(WIN_THREADS) k_group_reduce(const uint8_t *__restrict__ chunks, uint32_t chunks_ps, uint32_t cpg, uint32_t log2m,
+                                                             uint8_t *__restrict__ gsums) {
     using Fq = typename C::Fq;
     using Pt = Xyzz<Fq>;
     __shared__ uint4 sh_raw[(WIN_THREADS / 32) * 2 * Pt::BYTES / 16];
     uint8_t *sh = reinterpret_cast<uint8_t *>(sh_raw);
-    const uint32_t w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t q = chunks_pw > WIN_THREADS ? chunks_pw / WIN_THREADS : 1;     // items per thread (power of two)
+    const uint32_t g = blockIdx.x, set = blockIdx.y, groups = gridDim.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t q = cpg > WIN_THREADS ? cpg / WIN_THREADS : 1;     // items per thread (power of two)
     uint32_t log2q = 0; while ((1u << log2q) < q) log2q++;
-    const uint8_t *cw = chunks + (size_t)w * chunks_pw * 2 * Pt::BYTES;
+    const uint8_t *cw = chunks + ((size_t)set * chunks_ps + (size_t)g * cpg) * 2 * Pt::BYTES;
 
     // thread-serial part: P = sum Lc + m * sum_i i*Rc_i,  R = sum Rc   over this thread's q items
     Pt A = Pt::identity(), run = Pt::identity(), tri = Pt::identity();
 #pragma unroll 1
     for (uint32_t i = q; i-- > 0;) {
         const uint32_t t = tid * q + i;
-        if (t < chunks_pw) {
+        if (t < cpg) {
             Pt lc = Pt::load(cw + (size_t)t * 2 * Pt::BYTES);
             Pt rc = Pt::load(cw + (size_t)t * 2 * Pt::BYTES + Pt::BYTES);
             add_cold(A, lc);
@@ -316,7 +398,7 @@ __global__ void __launch_bounds__(WIN_THREADS) k_window_reduce(const uint8_t *__
     Pt P = A;
     if (q > 1) add_cold(P, mul_pow2(tri, log2m));
     Pt R = run, wR;
-    // S_w = sum_j P_j + (m*q) * sum_j j * R_j        (j = thread index)
+    // S_g = sum_j P_j + (m*q) * sum_j j * R_j        (j = thread index)
     warp_running_sums(P, R, wR, lane);
     if (lane == 0) {
         // sum_j j*R_j over the block = sum_warp ( wR_warp + 32*warp*R_warp )
@@ -335,31 +417,113 @@ __global__ void __launch_bounds__(WIN_THREADS) k_window_reduce(const uint8_t *__
         warp_running_sums(P2, R2, wR2, lane);
         if (lane == 0) {
             add_cold(P2, mul_pow2(wR2, log2m + log2q + 5));
-            P2.store(wsums + (size_t)w * Pt::BYTES);
+            uint8_t *out = gsums + ((size_t)set * groups + g) * 2 * Pt::BYTES;
+            P2.store(out);
+            R2.store(out + Pt::BYTES);
         }
     }
 }
 
-// K7: Horner over the windows (Jacobian doublings, the cheapest form: 2M + 5S), conversion to the reference's result
-// coordinates, canonical store.  One thread: (W-1)*c dependent doublings are inherent to the window method.
+// K7: one warp.  Per bucket set: S_set = sum_g S_g + (m * cpg) * sum_g g * Rtot_g (one more shuffle stitch over <= 32 groups);
+// then Horner over the sets (windowed mode: (W-1)*c dependent Jacobian doublings, inherent to the window method; folded
+// mode: a single set, no doublings), conversion to the reference's result coordinates, canonical store.
 template <class C>
-__global__ void k_final(const uint8_t *__restrict__ wsums, uint32_t W, uint32_t c, int coord, uint8_t *__restrict__ result) {
+__global__ void __launch_bounds__(32) k_final(const uint8_t *__restrict__ gsums, uint32_t sets, uint32_t groups, uint32_t log2_group_unit, uint32_t c,
+                                              int coord, uint8_t *__restrict__ result) {
     using Fq = typename C::Fq;
     using Pt = Xyzz<Fq>;
-    if (threadIdx.x || blockIdx.x) return;
-    Pt acc = Pt::load(wsums + (size_t)(W - 1) * Pt::BYTES);
+    const uint32_t lane = threadIdx.x;
+    Pt acc = Pt::identity();
 #pragma unroll 1
-    for (uint32_t w = W - 1; w-- > 0;) {
-        Jacobian<Fq> j = Jacobian<Fq>::from_xyzz(acc);
+    for (uint32_t set = sets; set-- > 0;) {
+        Pt P = Pt::identity(), R = Pt::identity(), wR;
+        if (lane < groups) {
+            const uint8_t *in = gsums + ((size_t)set * groups + lane) * 2 * Pt::BYTES;
+            P = Pt::load(in);
+            R = Pt::load(in + Pt::BYTES);
+        }
+        if (groups > 1) {
+            warp_running_sums(P, R, wR, lane);
+            if (lane == 0) add_cold(P, mul_pow2(wR, log2_group_unit));
+        }
+        if (lane == 0) {
+            if (set + 1 < sets) {          // acc = 2^c * acc + S_set
+                Jacobian<Fq> j = Jacobian<Fq>::from_xyzz(acc);
 #pragma unroll 1
-        for (uint32_t i = 0; i < c; i++) j = j.dbl();
-        acc = j.to_xyzz();
-        Pt sw = Pt::load(wsums + (size_t)w * Pt::BYTES);
-        add_cold(acc, sw);
+                for (uint32_t i = 0; i < c; i++) j = j.dbl();
+                acc = j.to_xyzz();
+            }
+            add_cold(acc, P);
+        }
     }
-    Jacobian<Fq> j = Jacobian<Fq>::from_xyzz(acc);
-    if (coord == COORD_PROJECTIVE) j = j.to_homogeneous();
-    j.store_canonical(result);
+    if (lane == 0) {
+        Jacobian<Fq> j = Jacobian<Fq>::from_xyzz(acc);
+        if (coord == COORD_PROJECTIVE) j = j.to_homogeneous();
+        j.store_canonical(result);
+    }
+}
+
+// ---- precomputed tables for reused bases ------------------------------------------------------------------------
+// table[j*n + i] = 2^(c*j) * P_i (affine), j < W: every window then feeds ONE bucket set and the final Horner disappears.
+// One thread per point: (W-1)*c Jacobian doublings, the W-1 intermediate points kept in local memory, one shared inversion
+// (Montgomery's trick) to normalise them.  Run once per cached base set (~10 MSMs worth of arithmetic).
+template <class C>
+__global__ void __launch_bounds__(128) k_build_table(const uint8_t *__restrict__ bases, uint32_t n, uint32_t c, uint32_t W, uint8_t *__restrict__ table) {
+    using Fq = typename C::Fq;
+    using Af = Affine<Fq>;
+    constexpr int MAXW = 32;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Af p = Af::load(bases + (size_t)i * Af::BYTES);
+    uint32_t *t0 = reinterpret_cast<uint32_t *>(table + (size_t)i * Af::BYTES);
+    p.x.store(t0); p.y.store(t0 + Fq::N);
+    if (p.is_identity()) {                 // identity stays identity in every table row
+        for (uint32_t j = 1; j < W; j++) {
+            uint32_t *t = reinterpret_cast<uint32_t *>(table + ((size_t)j * n + i) * Af::BYTES);
+            Fq::zero().store(t); Fq::zero().store(t + Fq::N);
+        }
+        return;
+    }
+    Jacobian<Fq> q; q.x = p.x; q.y = p.y; q.z = Fq::one();
+    Jacobian<Fq> pts[MAXW];
+    Fq prefix[MAXW];
+    Fq run = Fq::one();
+#pragma unroll 1
+    for (uint32_t j = 1; j < W; j++) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < c; k++) q = q.dbl();
+        pts[j] = q;
+        prefix[j] = run;                   // product of z_1 .. z_{j-1}
+        run = run * q.z;
+    }
+    Fq inv = fe_inverse(run);              // z is never 0 here: P has odd prime order, so 2^k * P is not the identity
+#pragma unroll 1
+    for (uint32_t j = W - 1; j >= 1; j--) {
+        const Fq zinv = inv * prefix[j];
+        inv = inv * pts[j].z;
+        const Fq zi2 = zinv.sqr();
+        const Fq x = pts[j].x * zi2;
+        const Fq y = pts[j].y * (zi2 * zinv);
+        uint32_t *t = reinterpret_cast<uint32_t *>(table + ((size_t)j * n + i) * Af::BYTES);
+        x.canon().store(t); y.canon().store(t + Fq::N);
+    }
+}
+
+// 64-bit fingerprint of a device buffer (order-sensitive multiply-xorshift mix, combined by addition): guards the table
+// cache against a caller that reuses a device pointer for different bases.
+static __global__ void __launch_bounds__(256) k_fingerprint(const uint4 *__restrict__ data, size_t count16, unsigned long long *__restrict__ out) {
+    unsigned long long h = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(data + i);
+        unsigned long long x = ((unsigned long long)v.x | ((unsigned long long)v.y << 32)) ^ (0x9E3779B97F4A7C15ull * (i + 1));
+        unsigned long long y = ((unsigned long long)v.z | ((unsigned long long)v.w << 32)) + 0xD1B54A32D192ED03ull * (i + 7);
+        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+        y ^= y >> 31; y *= 0x94D049BB133111EBull; y ^= y >> 29;
+        h += x ^ (y * 0x2545F4914F6CDD1Dull);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_down_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, h);
 }
 
 // sum of Jacobian partials (sharded MSM): one thread, a handful of additions
@@ -397,67 +561,69 @@ struct StageTimer {
     float ms(int i) { float t = 0; cudaEventElapsedTime(&t, ev[i], ev[i + 1]); return t; }
 };
 
+// Runs the pipeline described by `p`.  `points` is the caller's bases (windowed) or the precomputed table (folded).
 template <class C>
-cudaError_t msm_run_t(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
-                             cudaMemPool_t pool, cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings) {
+cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
+                           cudaStream_t stream, MsmStageTimes *timings) {
     using Pt = Xyzz<typename C::Fq>;
-    if (n == 0) {   // empty sum: the identity, all-zero like the reference (msm_cuda.cuh:395,405)
-        PB_CUDA(cudaMemsetAsync(result, 0, Jacobian<typename C::Fq>::BYTES, stream));
-        return cudaSuccess;
-    }
-    const MsmPlan p = msm_make_plan(curve, n, c_override, seg_override);
+    const uint32_t n = p.n;
     uint8_t *ws = nullptr;
     if (pool) PB_CUDA(cudaMallocFromPoolAsync((void **)&ws, p.bytes, pool, stream));
     else PB_CUDA(cudaMallocAsync((void **)&ws, p.bytes, stream));
     uint32_t *counts = (uint32_t *)(ws + p.off_counts), *offsets = (uint32_t *)(ws + p.off_offsets), *cursor = (uint32_t *)(ws + p.off_cursor);
-    uint32_t *big_count = counts + (size_t)p.windows * p.nb, *big_list = (uint32_t *)(ws + p.off_biglist);   // the counter is zeroed with the counts
+    uint32_t *big_count = counts + (size_t)p.sets * p.nb, *big_list = (uint32_t *)(ws + p.off_biglist);   // the counter is zeroed with the counts
+    uint32_t *tile_sums = (uint32_t *)(ws + p.off_tiles);
     uint16_t *digits = (uint16_t *)(ws + p.off_digits);
     uint32_t *sorted = (uint32_t *)(ws + p.off_sorted);
-    uint8_t *slots = ws + p.off_slots, *chunks = ws + p.off_chunks, *wsums = ws + p.off_wsums;
+    uint8_t *slots = ws + p.off_slots, *chunks = ws + p.off_chunks, *gsums = ws + p.off_gsums;
 
     StageTimer tm(timings != nullptr, stream);
     cudaError_t err = cudaSuccess;
     do {
-        if ((err = cudaMemsetAsync(counts, 0, (size_t)p.windows * p.nb * 4 + 4, stream)) != cudaSuccess) break;
+        if ((err = cudaMemsetAsync(counts, 0, (size_t)p.sets * p.nb * 4 + 4, stream)) != cudaSuccess) break;
+        tm.mark();
+        const uint32_t sblocks = std::min<uint32_t>((n + 255) / 256, 148 * 8);
+        if (p.folded) k_digits<C, true><<<sblocks, 256, 0, stream>>>((const uint32_t *)scalars, n, p.c, p.windows, p.nb, digits, counts);
+        else k_digits<C, false><<<sblocks, 256, 0, stream>>>((const uint32_t *)scalars, n, p.c, p.windows, p.nb, digits, counts);
         tm.mark();
         {
-            const uint32_t blocks = std::min<uint32_t>((n + 255) / 256, 148 * 8);
-            k_digits<C><<<blocks, 256, 0, stream>>>((const uint32_t *)scalars, n, p.c, p.windows, p.nb, digits, counts);
+            const uint32_t tiles_ps = (p.nb + SCAN_TILE - 1) / SCAN_TILE;
+            k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, stream>>>(counts, p.nb, tiles_ps, tile_sums);
+            k_scan_tops<<<p.sets, 1024, 0, stream>>>(tile_sums, tiles_ps, p.nb, offsets);
+            k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, stream>>>(counts, tile_sums, p.nb, tiles_ps, p.seg_len, offsets, cursor, big_count, big_list);
         }
         tm.mark();
-        k_scan<<<p.windows, 1024, 0, stream>>>(counts, p.nb, p.seg_len, offsets, cursor, big_count, big_list);
+        if (p.folded) k_scatter_folded<C><<<sblocks, 256, 0, stream>>>((const uint32_t *)scalars, n, p.c, p.windows, p.nb, cursor, sorted);
+        else k_scatter<<<dim3(sblocks, p.windows), 256, 0, stream>>>(digits, n, p.nb, cursor, sorted);
         tm.mark();
         {
-            dim3 grid(std::min<uint32_t>((n + 255) / 256, 148 * 8), p.windows);
-            k_scatter<<<grid, 256, 0, stream>>>(digits, n, p.nb, cursor, sorted);
-        }
-        tm.mark();
-        {
-            const uint64_t threads = (uint64_t)p.windows * p.segs_pw;
+            const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
             const uint32_t blocks = (uint32_t)((threads + ACC_THREADS - 1) / ACC_THREADS);
-            k_accumulate<C><<<blocks, ACC_THREADS, 0, stream>>>((const uint8_t *)bases, sorted, offsets, n, p.nb, p.seg_len, p.segs_pw, p.windows, slots);
+            k_accumulate<C><<<blocks, ACC_THREADS, 0, stream>>>((const uint8_t *)points, sorted, offsets, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots);
         }
-        k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, stream>>>(slots, offsets, big_count, big_list, p.nb, p.seg_len, p.segs_pw);
+        k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, stream>>>(slots, offsets, big_count, big_list, p.nb, p.seg_len, p.segs_ps);
+        tm.mark();
+        uint32_t log2m = 0; while ((1u << log2m) < p.chunk) log2m++;
+        {
+            const uint32_t threads = p.sets * p.chunks_ps;
+            k_bucket_reduce<C><<<(threads + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, stream>>>(slots, offsets, p.nb, p.seg_len, p.segs_ps,
+                                                                                                   p.sets, p.chunk, p.chunks_ps, chunks);
+        }
+        tm.mark();
+        const uint32_t cpg = p.chunks_ps / p.groups;
+        k_group_reduce<C><<<dim3(p.groups, p.sets), WIN_THREADS, 0, stream>>>(chunks, p.chunks_ps, cpg, log2m, gsums);
         tm.mark();
         {
-            const uint32_t threads = p.windows * p.chunks_pw;
-            k_bucket_reduce<C><<<(threads + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, stream>>>(slots, offsets, p.nb, p.seg_len, p.segs_pw,
-                                                                                                   p.windows, p.chunk, p.chunks_pw, chunks);
+            uint32_t log2cpg = 0; while ((1u << log2cpg) < cpg) log2cpg++;
+            k_final<C><<<1, 32, 0, stream>>>(gsums, p.sets, p.groups, log2m + log2cpg, p.c, (int)coord, (uint8_t *)result);
         }
-        tm.mark();
-        {
-            uint32_t log2m = 0; while ((1u << log2m) < p.chunk) log2m++;
-            k_window_reduce<C><<<p.windows, WIN_THREADS, 0, stream>>>(chunks, p.chunks_pw, log2m, wsums);
-        }
-        tm.mark();
-        k_final<C><<<1, 32, 0, stream>>>(wsums, p.windows, p.c, (int)coord, (uint8_t *)result);
         tm.mark();
         err = cudaGetLastError();
     } while (0);
     cudaError_t ferr = cudaFreeAsync(ws, stream);
     if (err == cudaSuccess) err = ferr;
     if (err != cudaSuccess) {
-        fprintf(stderr, "[panda-b200] msm_run failed: %s\n", cudaGetErrorString(err));
+        fprintf(stderr, "[panda-b200] msm pipeline failed: %s\n", cudaGetErrorString(err));
         return err;
     }
     if (timings) {
@@ -469,6 +635,18 @@ cudaError_t msm_run_t(CurveId curve, const void *bases, const void *scalars, uin
     return cudaSuccess;
 }
 
+template <class C>
+cudaError_t msm_build_table_t(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream) {
+    k_build_table<C><<<(n + 127) / 128, 128, 0, stream>>>((const uint8_t *)bases, n, c, W, (uint8_t *)table);
+    return cudaGetLastError();
+}
+
+inline cudaError_t msm_fingerprint(const void *data, size_t bytes, unsigned long long *d_out, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(d_out, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    k_fingerprint<<<148 * 8, 256, 0, stream>>>((const uint4 *)data, bytes / 16, d_out);
+    return cudaGetLastError();
+}
 
 template <class C>
 cudaError_t msm_combine_t(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream) {

@@ -125,7 +125,7 @@ static panda_error msm_execute_host(pb::CurveId curve, const panda_msm_configura
 
 panda_error panda_msm_setup_bn254(void) { return panda_success; }          // nothing to prepare: msm_cuda.cuh:786-795 is empty too
 panda_error panda_msm_setup_bls12_377(void) { return panda_success; }
-panda_error panda_msm_tear_down(void) { return panda_success; }             // idempotent (wrapper.rs:297-312 calls it once per base set)
+panda_error panda_msm_tear_down(void) { return perr(pb::msm_release_tables()); }   // idempotent (wrapper.rs:297-312 calls it once per base set); drops cached tables
 
 panda_error panda_msm_execute_bn254(const panda_msm_configuration cfg) { return msm_execute(pb::CURVE_BN254, cfg, (size_t)1 << cfg.log_scalars_count); }
 panda_error panda_msm_execute_bn254_n(const panda_msm_configuration cfg, size_t n) { return msm_execute(pb::CURVE_BN254, cfg, n); }
@@ -193,23 +193,26 @@ panda_error panda_ntt_tear_down(void) {
 
 // ---- diagnostics (include/panda_debug.h) --------------------------------------------------------------------------
 
-panda_error panda_debug_msm_plan(int curve, size_t n, unsigned c_override, unsigned seg_override, panda_debug_msm_plan_info *out) {
+panda_error panda_debug_msm_plan(int curve, size_t n, int folded, unsigned c_override, unsigned seg_override, panda_debug_msm_plan_info *out) {
     if (!out) return perr(cudaErrorInvalidValue);
-    pb::MsmPlan p = pb::msm_make_plan(curve == 1 ? pb::CURVE_BLS12_377 : pb::CURVE_BN254, (uint32_t)n, c_override, seg_override);
+    pb::MsmPlan p = pb::msm_make_plan(curve == 1 ? pb::CURVE_BLS12_377 : pb::CURVE_BN254, (uint32_t)n, folded != 0, c_override, seg_override);
     out->window_bits = p.c; out->windows = p.windows; out->buckets_per_window = p.nb; out->segment_len = p.seg_len;
-    out->segments_per_window = p.segs_pw; out->reduce_chunk = p.chunk; out->workspace_bytes = p.bytes;
+    out->segments_per_window = p.segs_ps; out->reduce_chunk = p.chunk; out->workspace_bytes = p.bytes;
+    out->folded = p.folded; out->bucket_sets = p.sets; out->groups = p.groups; out->table_bytes = p.table_bytes;
     return panda_success;
 }
 
-panda_error panda_debug_msm_timed(int curve, const panda_msm_configuration cfg, size_t n, unsigned c_override, unsigned seg_override, float *stage_ms) {
+panda_error panda_debug_msm_timed(int curve, const panda_msm_configuration cfg, size_t n, unsigned c_override, unsigned seg_override, int table_mode,
+                                  float *stage_ms, unsigned *info) {
     pb::MsmStageTimes t{};
     pb::CoordType coord = cfg.msm_result_coordinate_type == PROJECTIVE ? pb::COORD_PROJECTIVE : pb::COORD_JACOBIAN;
     cudaError_t e = pb::msm_run(curve == 1 ? pb::CURVE_BLS12_377 : pb::CURVE_BN254, cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, coord,
-                                cu(cfg.mem_pool), cu(cfg.stream), c_override, seg_override, stage_ms ? &t : nullptr);
+                                cu(cfg.mem_pool), cu(cfg.stream), c_override, seg_override, (stage_ms || info) ? &t : nullptr, table_mode);
     if (stage_ms) {
         stage_ms[0] = t.digits; stage_ms[1] = t.scan; stage_ms[2] = t.scatter; stage_ms[3] = t.accumulate;
         stage_ms[4] = t.bucket_reduce; stage_ms[5] = t.window_reduce; stage_ms[6] = t.final;
     }
+    if (info) { info[0] = (unsigned)t.folded; info[1] = t.c; info[2] = t.windows; }
     return perr(e);
 }
 

@@ -167,6 +167,10 @@ class MsmPlanInfo(C.Structure):  # include/panda_debug.h
         ("segments_per_window", C.c_uint),
         ("reduce_chunk", C.c_uint),
         ("workspace_bytes", C.c_size_t),
+        ("folded", C.c_uint),
+        ("bucket_sets", C.c_uint),
+        ("groups", C.c_uint),
+        ("table_bytes", C.c_size_t),
     ]
 
 
@@ -228,8 +232,8 @@ SIGNATURES: dict[str, list] = {
     # diagnostics (include/panda_debug.h)
     "panda_debug_field_op": [_int, _int, _vp, _vp, _vp, SizeT, PandaStream],
     "panda_debug_curve_op": [_int, _int, _vp, _vp, _vp, SizeT, PandaStream],
-    "panda_debug_msm_plan": [_int, SizeT, _uint, _uint, C.POINTER(MsmPlanInfo)],
-    "panda_debug_msm_timed": [_int, MSMConfiguration, SizeT, _uint, _uint, C.POINTER(C.c_float)],
+    "panda_debug_msm_plan": [_int, SizeT, _int, _uint, _uint, C.POINTER(MsmPlanInfo)],
+    "panda_debug_msm_timed": [_int, MSMConfiguration, SizeT, _uint, _uint, _int, C.POINTER(C.c_float), C.POINTER(_uint)],
     "panda_debug_int_peak": [_int, _uint, C.POINTER(C.c_float), C.POINTER(C.c_ulonglong)],
 }
 

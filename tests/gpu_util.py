@@ -43,15 +43,15 @@ class DevBuf:
 
 
 def msm_device(bases: np.ndarray, scalars: np.ndarray, n: int, coord: int = 0, curve: int = 0, stream=None, pool=None,
-               c_override: int = 0, seg_override: int = 0, timed: bool = False):
+               c_override: int = 0, seg_override: int = 0, timed: bool = False, table_mode: int = -1):
     """Run the CUDA MSM through the C ABI on host arrays; returns the 3-element result (numpy bytes) [and stage ms]."""
     fq = 48 if curve == 1 else 32
     d_b, d_s, d_r = DevBuf.from_numpy(bases), DevBuf.from_numpy(scalars), DevBuf(3 * fq)
     stream = stream or ffi.PandaStream.null()
     cfg = ffi.MSMConfiguration(pool or ffi.PandaMemPool.null(), stream, d_b.ptr, d_s.ptr, d_r.ptr, max(n.bit_length() - 1, 0), coord)
     stage = (C.c_float * 7)()
-    if timed or c_override or seg_override:
-        rc = ffi.lib.panda_debug_msm_timed(curve, cfg, n, c_override, seg_override, stage if timed else None)
+    if timed or c_override or seg_override or table_mode != -1:
+        rc = ffi.lib.panda_debug_msm_timed(curve, cfg, n, c_override, seg_override, table_mode, stage if timed else None, None)
     elif n & (n - 1) == 0 and n > 0:
         rc = (ffi.lib.panda_msm_execute_bls12_377 if curve == 1 else ffi.lib.panda_msm_execute_bn254)(cfg)
     else:

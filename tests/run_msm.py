@@ -17,6 +17,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cid = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 c_over = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 seg_over = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+table_mode = int(sys.argv[6]) if len(sys.argv) > 6 else -1
 n = 1 << k
 fq = O.FQ_BYTES[cid]
 t = time.time()
@@ -29,15 +30,15 @@ stream = ffi.PandaStream.new()
 pool = ffi.PandaMemPool.new(0)
 cfg = ffi.MSMConfiguration(pool, stream, d_b.ptr, d_s.ptr, d_r.ptr, k, 0)
 plan = ffi.MsmPlanInfo()
-ffi.lib.panda_debug_msm_plan(cid, n, c_over, seg_over, C.byref(plan))
-print(f"plan: c={plan.window_bits} W={plan.windows} nb={plan.buckets_per_window} L={plan.segment_len} m={plan.reduce_chunk} ws={plan.workspace_bytes / 2**20:.0f} MiB")
 stage = (C.c_float * 7)()
+info = (C.c_uint * 3)()
 for r in range(reps):
     t0 = time.time()
-    rc = ffi.lib.panda_debug_msm_timed(cid, cfg, n, c_over, seg_over, stage)
+    rc = ffi.lib.panda_debug_msm_timed(cid, cfg, n, c_over, seg_over, table_mode, stage, info)
     assert rc == 0, rc
     tot = sum(stage)
-    print(f"rep {r}: total {tot:.3f} ms  {n / tot / 1e3:.1f} Mpts/s  stages[digits,scan,scatter,accum,bucket,window,final]={[round(x, 3) for x in stage]} wall={1e3 * (time.time() - t0):.1f} ms", flush=True)
+    ffi.lib.panda_debug_msm_plan(cid, n, info[0], info[1], seg_over, C.byref(plan))
+    print(f"rep {r}: [folded={info[0]} c={info[1]} W={info[2]} nb={plan.buckets_per_window} L={plan.segment_len} m={plan.reduce_chunk} G={plan.groups} ws={plan.workspace_bytes / 2**20:.0f} MiB table={plan.table_bytes / 2**30:.1f} GiB] total {tot:.3f} ms  {n / tot / 1e3:.1f} Mpts/s  stages[digits,scan,scatter,accum,bucket,window,final]={[round(x, 3) for x in stage]} wall={1e3 * (time.time() - t0):.1f} ms", flush=True)
 got = d_r.to_numpy()
 print("closed-form match:", bool((O.jac_to_affine(cid, got) == exp).all()))
 # untimed API path with events around it

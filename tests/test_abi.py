@@ -66,7 +66,7 @@ def test_msm_plan_selection():
     p = ffi.MsmPlanInfo()
     for curve, bits in ((0, 254), (1, 253)):
         for k in list(range(0, 27)):
-            assert ffi.lib.panda_debug_msm_plan(curve, 1 << k, 0, 0, C.byref(p)) == 0
+            assert ffi.lib.panda_debug_msm_plan(curve, 1 << k, 0, 0, 0, C.byref(p)) == 0
             c, W, nb = p.window_bits, p.windows, p.buckets_per_window
             assert 8 <= c <= 16 and nb == 1 << (c - 1) and W <= 32
             # signed digits: the windows below the top one cover (W-1)*c bits, the top window (no recoding) must hold the
@@ -75,10 +75,16 @@ def test_msm_plan_selection():
             assert top_bits <= c - 1 and (W - 1) * c < bits + c
             assert p.segment_len >= 8 and p.segments_per_window == -(-(1 << k) // p.segment_len)
             assert nb % p.reduce_chunk == 0
-    ffi.lib.panda_debug_msm_plan(0, 1 << 24, 0, 0, C.byref(p))
-    assert (p.window_bits, p.windows) == (16, 16)
-    ffi.lib.panda_debug_msm_plan(0, 1 << 20, 13, 32, C.byref(p))      # overrides are honoured
+    ffi.lib.panda_debug_msm_plan(0, 1 << 24, 0, 0, 0, C.byref(p))
+    assert (p.window_bits, p.windows, p.folded, p.bucket_sets) == (16, 16, 0, 16)
+    ffi.lib.panda_debug_msm_plan(0, 1 << 20, 0, 13, 32, C.byref(p))      # overrides are honoured
     assert (p.window_bits, p.segment_len) == (13, 32)
+    # folded plans (precomputed 2^(c*j)*P tables): one bucket set, table index + sign fit 32 bits
+    for k in (10, 16, 20, 24, 26):
+        assert ffi.lib.panda_debug_msm_plan(0, 1 << k, 1, 0, 0, C.byref(p)) == 0
+        assert p.folded == 1 and p.bucket_sets == 1 and p.windows * (1 << k) < 2 ** 31
+        assert p.table_bytes == p.windows * (1 << k) * 64
+        assert 254 - (p.windows - 1) * p.window_bits <= p.window_bits - 1
 
 
 def test_host_api_fails_loudly_without_a_device():

@@ -234,3 +234,47 @@ def test_combine_partials(oracle, dev):
         assert ffi.lib.panda_msm_combine_bn254(d_p.ptr, parts, d_o.ptr, coord, ffi.PandaStream.null()) == 0
         assert ffi.lib.panda_stream_synchronize(ffi.PandaStream.null()) == 0
         assert (affine(oracle, 0, d_o.to_numpy(), coord) == exp).all()
+
+
+@pytest.mark.parametrize("k,curve", [(10, 0), (13, 0), (16, 0), (12, 1)])
+def test_precomputed_table_modes_agree(oracle, dev, k, curve):
+    """reused bases: the 2^(c*j)*P table path (one bucket set, no Horner) returns the same point as the windowed path"""
+    _ffi, gu = dev
+    n = 1 << k
+    bases = oracle.gen_bases(curve, 90 + k, n)
+    scal = oracle.gen_scalars(3 if curve else 1, 91 + k, n)
+    exp = oracle.jac_to_affine(curve, oracle.expected_progression_msm(curve, 90 + k, scal, n))
+    for mode in (0, 2):                        # never / eager
+        for coord in (0, 1):
+            got = gu.msm_device(bases, scal, n, coord, curve=curve, table_mode=mode)
+            assert (affine(oracle, curve, got, coord) == exp).all(), (mode, coord)
+
+
+def test_table_cache_follows_the_bases_not_the_pointer(oracle, dev):
+    """AUTO mode builds a table at the second sighting of (pointer, n, fingerprint); rewriting the buffer with other points
+    must not reuse the stale table, and edge-case bases (identity, duplicates, P/-P) survive the table build"""
+    ffi, gu = dev
+    k, n = 12, 1 << 12
+    d_b, d_s, d_r = gu.DevBuf(n * 64), gu.DevBuf(n * 32), gu.DevBuf(96)
+    stream = ffi.PandaStream.new()
+    cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), stream, d_b.ptr, d_s.ptr, d_r.ptr, k, 0)
+    info = (C.c_uint * 3)()
+    for seed in (100, 101):
+        bases = oracle.gen_bases(0, seed, n).reshape(n, 64).copy()
+        bases[3] = 0                                                 # identity
+        bases[5] = bases[4]                                          # duplicate
+        bases[7] = bases[6]; bases[7, 32:] = oracle.f_neg(0, bases[6, 32:].copy())
+        scal = oracle.gen_scalars(1, seed + 50, n).reshape(n, 32).copy()
+        scal[7] = scal[6]
+        exp = oracle.jac_to_affine(0, oracle.msm(0, bases.reshape(-1), scal.reshape(-1), n, c=10))
+        assert ffi.lib.panda_memcpy(d_b.ptr, bases.ctypes.data, n * 64) == 0
+        assert ffi.lib.panda_memcpy(d_s.ptr, scal.ctypes.data, n * 32) == 0
+        folded = []
+        for _ in range(3):
+            assert ffi.lib.panda_debug_msm_timed(0, cfg, n, 0, 0, 1, None, info) == 0
+            folded.append(info[0])
+            assert (oracle.jac_to_affine(0, d_r.to_numpy()) == exp).all()
+        assert folded == [0, 1, 1]
+    assert ffi.lib.panda_msm_tear_down() == 0                        # drops the tables; idempotent
+    assert ffi.lib.panda_msm_tear_down() == 0
+    assert ffi.lib.panda_debug_msm_timed(0, cfg, n, 0, 0, 1, None, info) == 0 and info[0] == 0
