@@ -153,6 +153,33 @@ panda_error panda_msm_combine_bls12_377(const void *partials, unsigned count, vo
 /* Inverse transform: x = (1/n) * DFT_{omega^-1}(y); omega is the FORWARD root (host pointer), same flag contract. */
 panda_error panda_intt_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cfg);
 
+/* Batched transform: `batch` independent 2^log_n-point (I)NTTs stored back to back in d_src (d_dst: same size); same omega /
+ * flag contract as panda_ntt_execute_bn254_v1 (flag tells which buffer holds all `batch` results).  inverse != 0: omega^-1 and
+ * the 1/2^log_n scale.  Building block of polynomial-batch provers and of the multi-GPU four-step transform. */
+panda_error panda_ntt_batch_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cfg, unsigned batch, int inverse);
+
+/* Exchange step of the four-step transform n = n1 * n2 sharded over the GPUs of one box (no reference
+ * precedent).  Reads the 2^log_rows x 2^log_cols row-major matrix d_src, multiplies element (r, c) by
+ * omega^((row_offset + r) * c)  (omega: HOST pointer, primitive 2^log_n-th root, NULL = no twiddle; inverse != 0: omega^-1),
+ * and writes it transposed: column block h (of `parts` equal blocks, parts a power of two <= 16) goes to
+ * dst[h][(c mod block) * ld + col_offset + r].  dst is a HOST array of `parts` DEVICE pointers: per-rank staging chunks for an
+ * all-to-all, or peer-mapped buffers of the other GPUs (the kernel then stores over NVLink straight into the consumer's row
+ * layout).  parts = 1 without omega is a plain transpose.  Asynchronous on `stream`. */
+typedef struct panda_ntt_exchange_configuration {
+    panda_stream stream;
+    const void *d_src;
+    unsigned log_rows, log_cols;
+    unsigned row_offset;
+    unsigned log_n;
+    const void *omega;
+    int inverse;
+    unsigned parts;
+    void *const *dst;
+    size_t ld;
+    size_t col_offset;
+} panda_ntt_exchange_configuration;
+panda_error panda_ntt_exchange_bn254(const panda_ntt_exchange_configuration *cfg);
+
 /* Library identification: "panda-b200 <version> sm_100a". */
 const char *panda_version(void);
 

@@ -21,6 +21,7 @@ namespace pb {
 
 static constexpr int NTT_THREADS = 256;
 static constexpr unsigned NTT_MAX_RADIX_LOG = 8;      // fft.cu:10 MAX_LOG2_RADIX
+static constexpr unsigned NTT_MAX_PARTS = 16;         // destination buffers of the exchange step (GPUs of one box)
 
 struct NttShape {
     unsigned log_n, passes;
@@ -155,6 +156,7 @@ PB_DEV void tile_dft(uint32_t *sm, uint32_t LS, uint32_t CP, unsigned r, unsigne
 
 struct NttPassArgs {
     unsigned log_n, r, log_M, log_O, logC, lo_bits;
+    unsigned log_bpt;                 // last pass: log2(CTAs per transform); the CTA index above that is the batch row
     unsigned passes, rad[4];          // all radices (last pass: digit reversal)
     const uint32_t *stage_tw, *t_lo, *t_hi, *scale;
 };
@@ -199,7 +201,10 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(const uint32_t *__rest
     const unsigned log_OP = a.log_O;                                  // log2(N_1 .. N_{P-1})
     const unsigned r1 = a.passes > 1 ? a.rad[0] : 0;
     const uint32_t rest_count = 1u << (log_OP - r1);
-    const uint32_t j1_0 = (blockIdx.x / rest_count) << a.logC, rest = blockIdx.x % rest_count;
+    const uint32_t bid = blockIdx.x & ((1u << a.log_bpt) - 1);
+    src += ((size_t)(blockIdx.x >> a.log_bpt) << a.log_n) * F::N;      // batch row (contiguous transforms)
+    dst += ((size_t)(blockIdx.x >> a.log_bpt) << a.log_n) * F::N;
+    const uint32_t j1_0 = (bid / rest_count) << a.logC, rest = bid % rest_count;
     // digit reversal of (j_2 .. j_{P-1})
     uint32_t revp = 0;
     {
@@ -229,6 +234,57 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(const uint32_t *__rest
         F x = sm_load<F>(sm, LS, pos * CP + cidx);
         if (a.scale) x = x * scale;
         x.canon().store(dst + (out_base + cidx + ((size_t)jp << log_OP)) * F::N);
+    }
+}
+
+// ---- exchange step of the four-step transform -----------------------------------------------------
+// dst[h][(c mod Cp) * ld + col_off + r] = src[r][c] * omega^((row0 + r) * c)      h = c / Cp, Cp = cols / parts
+// i.e. a tiled transpose of the rows x cols matrix `src` fused with the four-step twiddle, whose column blocks land in
+// `parts` destination buffers: per-rank staging chunks for an NCCL all-to-all, or peer-mapped buffers of the other GPUs
+// (NVLink stores straight into the consumer's row layout).  With parts = 1 and no twiddle it is a plain transpose.
+// HBM / NVLink bound: 32 B read + 32 B written per element in 512-byte runs; 2 modmul per element for the twiddle.
+struct NttExchangeArgs {
+    const uint32_t *src;
+    unsigned log_rows, log_cols, log_part_cols, row0;
+    uint32_t *dst[NTT_MAX_PARTS];
+    size_t ld, col_off;
+    const uint32_t *t_lo, *t_hi;      // nullptr: no twiddle
+    unsigned lo_bits, log_n;
+};
+
+template <class P>
+__global__ void __launch_bounds__(256) k_ntt_exchange(const NttExchangeArgs a) {
+    using F = Fe<P>;
+    constexpr uint32_t T = 16, TP = T + 1;
+    __shared__ uint32_t sm[F::N * T * TP];
+    const uint32_t rows = 1u << a.log_rows, cols = 1u << a.log_cols;
+    const uint32_t tiles_c = (cols + T - 1) / T;
+    const uint32_t r_base = (blockIdx.x / tiles_c) * T, c_base = (blockIdx.x % tiles_c) * T;
+    {
+        const uint32_t tr = threadIdx.x / T, tc = threadIdx.x % T;
+        const uint32_t r = r_base + tr, c = c_base + tc;
+        if (r < rows && c < cols) {
+            F x = F::load(a.src + ((size_t)r * cols + c) * F::N);
+            if (a.t_lo) {
+                const uint64_t prod = (uint64_t)(a.row0 + r) * c;
+                const uint32_t ex = (uint32_t)(prod & (((uint64_t)1 << a.log_n) - 1));
+                if (ex) {
+                    F tw = F::load(a.t_hi + (size_t)(ex >> a.lo_bits) * F::N) * F::load(a.t_lo + (size_t)(ex & ((1u << a.lo_bits) - 1)) * F::N);
+                    x = (x * tw).canon();
+                }
+            }
+            sm_store(sm, T * TP, tc * TP + tr, x);
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t oc = threadIdx.x / T, orow = threadIdx.x % T;
+        const uint32_t r = r_base + orow, c = c_base + oc;
+        if (r < rows && c < cols) {
+            F x = sm_load<F>(sm, T * TP, oc * TP + orow);
+            const uint32_t h = c >> a.log_part_cols, cl = c & ((1u << a.log_part_cols) - 1);
+            x.store(a.dst[h] + ((size_t)cl * a.ld + a.col_off + r) * F::N);
+        }
     }
 }
 
@@ -297,9 +353,10 @@ cudaError_t ntt_release_tables() {
 }
 
 cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, const void *omega_host, bool inverse,
-                    cudaStream_t stream, unsigned *result_in_dst) {
+                    cudaStream_t stream, unsigned *result_in_dst, unsigned batch) {
     (void)field;
     if (log_n > 28 || !omega_host) return cudaErrorInvalidValue;      // 2-adicity of BN254 Fr (paramter.cuh:241)
+    if (batch == 0 || ((uint64_t)batch << log_n) > ((uint64_t)1 << 31)) return cudaErrorInvalidValue;
     const NttShape shape = ntt_shape(log_n);
     if (result_in_dst) *result_in_dst = shape.passes & 1;
     if (shape.passes == 0) return cudaSuccess;                         // n = 1: the transform is the identity
@@ -332,7 +389,7 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
             a.logC = a.log_M < 3 ? a.log_M : 3;
             const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
             const size_t smem = (size_t)8 * ((size_t)(1u << a.r) * CP) * 4;
-            const uint32_t blocks = 1u << (log_O + a.log_M - a.logC);
+            const uint32_t blocks = batch << (log_O + a.log_M - a.logC);   // batch rows extend the outer index: (t * 2^log_O + o)
             k_ntt_cols<Bn254Fr><<<blocks, NTT_THREADS, smem, stream>>>(src, dst, a);
         } else {
             const unsigned r1 = shape.passes > 1 ? shape.r[0] : 0;
@@ -340,7 +397,8 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
             if (inverse) a.scale = tab->d_tab + t.off_scale;
             const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
             const size_t smem = (size_t)8 * ((size_t)(1u << a.r) * CP) * 4;
-            const uint32_t blocks = 1u << (log_O - a.logC);
+            a.log_bpt = log_O - a.logC;
+            const uint32_t blocks = batch << a.log_bpt;
             k_ntt_last<Bn254Fr><<<blocks, NTT_THREADS, smem, stream>>>(src, dst, a);
         }
         PB_CUDA(cudaGetLastError());
@@ -348,6 +406,29 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
         std::swap(src, dst);
     }
     return cudaSuccess;
+}
+
+cudaError_t ntt_exchange(NttField field, const void *d_src, unsigned log_rows, unsigned log_cols, unsigned row_offset, const void *omega_host,
+                         unsigned log_n, bool inverse, unsigned parts, void *const *dst, size_t ld, size_t col_offset, cudaStream_t stream) {
+    (void)field;
+    if (!d_src || !dst || parts == 0 || parts > NTT_MAX_PARTS || (parts & (parts - 1)) || log_rows + log_cols > 31) return cudaErrorInvalidValue;
+    unsigned log_parts = 0; while ((1u << log_parts) < parts) log_parts++;
+    if (log_parts > log_cols) return cudaErrorInvalidValue;
+    NttExchangeArgs a{};
+    a.src = (const uint32_t *)d_src;
+    a.log_rows = log_rows; a.log_cols = log_cols; a.log_part_cols = log_cols - log_parts; a.row0 = row_offset;
+    for (unsigned h = 0; h < parts; h++) { if (!dst[h]) return cudaErrorInvalidValue; a.dst[h] = (uint32_t *)dst[h]; }
+    a.ld = ld; a.col_off = col_offset;
+    if (omega_host) {
+        if (log_n > 28) return cudaErrorInvalidValue;
+        NttCacheEntry *tab = nullptr;
+        PB_CUDA(ntt_get_tables(ntt_shape(log_n), omega_host, inverse, stream, &tab));
+        a.t_lo = tab->d_tab + tab->layout.off_lo; a.t_hi = tab->d_tab + tab->layout.off_hi;
+        a.lo_bits = tab->layout.lo_bits; a.log_n = log_n;
+    }
+    const uint32_t tiles_r = ((1u << log_rows) + 15) / 16, tiles_c = ((1u << log_cols) + 15) / 16;
+    k_ntt_exchange<Bn254Fr><<<tiles_r * tiles_c, 256, 0, stream>>>(a);
+    return cudaGetLastError();
 }
 
 }  // namespace pb

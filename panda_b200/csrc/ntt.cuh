@@ -17,8 +17,16 @@ enum NttField { NTT_BN254_FR = 0 };
 // inverse: transform with omega^-1 and scale by 1/n.
 // *result_in_dst: 1 if the output is in d_dst, 0 if in d_src (both buffers are used as ping-pong storage).
 // Asynchronous on `stream` (twiddle tables are built on first use of an (omega, log_n) pair and cached per device).
+// batch: number of independent 2^log_n-point transforms stored back to back in d_src (d_dst has the same size).
 cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, const void *omega_host, bool inverse,
-                    cudaStream_t stream, unsigned *result_in_dst);
+                    cudaStream_t stream, unsigned *result_in_dst, unsigned batch = 1);
+
+// Exchange step of the four-step (multi-GPU) transform: tiled transpose of the 2^log_rows x 2^log_cols matrix d_src fused
+// with the twiddle omega^((row_offset + r) * c) (omega_host = nullptr: none; omega of order 2^log_n, inverse: omega^-1);
+// column block h of `parts` equal blocks is written to dst[h][(c mod block) * ld + col_offset + r].  dst is a HOST array of
+// device pointers (local staging chunks or peer-mapped buffers).  Asynchronous on `stream`.
+cudaError_t ntt_exchange(NttField field, const void *d_src, unsigned log_rows, unsigned log_cols, unsigned row_offset, const void *omega_host,
+                         unsigned log_n, bool inverse, unsigned parts, void *const *dst, size_t ld, size_t col_offset, cudaStream_t stream);
 
 // frees the cached twiddle tables of every device
 cudaError_t ntt_release_tables();

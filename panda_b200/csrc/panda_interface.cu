@@ -183,6 +183,18 @@ panda_error panda_intt_execute_bn254_v1(const panda_ntt_configuration_v1 cfg) {
     if (!cfg.d_omega) return perr(cudaErrorInvalidValue);
     return ntt_execute(cfg.d_src, cfg.d_dst, cfg.log_n, cfg.d_omega, true, cfg.stream, cfg.flag);
 }
+panda_error panda_ntt_batch_execute_bn254_v1(const panda_ntt_configuration_v1 cfg, unsigned batch, int inverse) {
+    if (!cfg.d_omega || !cfg.flag || !cfg.d_src || !cfg.d_dst) return perr(cudaErrorInvalidValue);
+    unsigned in_dst = 0;
+    cudaError_t e = pb::ntt_run(pb::NTT_BN254_FR, cfg.d_src, cfg.d_dst, cfg.log_n, cfg.d_omega, inverse != 0, cu(cfg.stream), &in_dst, batch);
+    *static_cast<unsigned *>(cfg.flag) = in_dst;
+    return perr(e);
+}
+panda_error panda_ntt_exchange_bn254(const panda_ntt_exchange_configuration *cfg) {
+    if (!cfg) return perr(cudaErrorInvalidValue);
+    return perr(pb::ntt_exchange(pb::NTT_BN254_FR, cfg->d_src, cfg->log_rows, cfg->log_cols, cfg->row_offset, cfg->omega, cfg->log_n, cfg->inverse != 0,
+                                 cfg->parts, cfg->dst, cfg->ld, cfg->col_offset, cu(cfg->stream)));
+}
 panda_error panda_ntt_tear_down(void) {
     {
         std::lock_guard<std::mutex> lock(g_omega_mutex);

@@ -155,6 +155,23 @@ class NttconfigurationV1(C.Structure):  # common.rs:198-208 (56 bytes)
     ]
 
 
+class NttExchangeConfiguration(C.Structure):  # include/panda_interface.h (addition: four-step exchange step)
+    _fields_ = [
+        ("stream", PandaStream),
+        ("d_src", C.c_void_p),
+        ("log_rows", C.c_uint),
+        ("log_cols", C.c_uint),
+        ("row_offset", C.c_uint),
+        ("log_n", C.c_uint),
+        ("omega", C.c_void_p),
+        ("inverse", C.c_int),
+        ("parts", C.c_uint),
+        ("dst", C.POINTER(C.c_void_p)),
+        ("ld", C.c_size_t),
+        ("col_offset", C.c_size_t),
+    ]
+
+
 PandaHostFn = C.CFUNCTYPE(None, C.c_void_p)
 
 
@@ -229,6 +246,8 @@ SIGNATURES: dict[str, list] = {
     "panda_msm_combine_bn254": [_vp, _uint, _vp, _int, PandaStream],
     "panda_msm_combine_bls12_377": [_vp, _uint, _vp, _int, PandaStream],
     "panda_intt_execute_bn254_v1": [NttconfigurationV1],
+    "panda_ntt_batch_execute_bn254_v1": [NttconfigurationV1, _uint, _int],
+    "panda_ntt_exchange_bn254": [C.POINTER(NttExchangeConfiguration)],
     # diagnostics (include/panda_debug.h)
     "panda_debug_field_op": [_int, _int, _vp, _vp, _vp, SizeT, PandaStream],
     "panda_debug_curve_op": [_int, _int, _vp, _vp, _vp, SizeT, PandaStream],
