@@ -33,7 +33,7 @@ panda_error panda_debug_curve_op(int curve_id, int op, const void *p, const void
 typedef struct panda_debug_msm_plan_info {
     unsigned window_bits, windows, buckets_per_window, segment_len, segments_per_window, reduce_chunk;
     size_t workspace_bytes;
-    unsigned folded, bucket_sets, groups;   /* folded = 1: plan for a precomputed 2^(c*j)*P table (one bucket set) */
+    unsigned folded, bucket_sets, groups, phases;   /* folded = 1: plan for a precomputed 2^(c*j)*P table (one bucket set) */
     size_t table_bytes;
 } panda_debug_msm_plan_info;
 /* the plan msm_execute would use for n points (c_override / seg_override = 0: automatic); folded selects the table plan */

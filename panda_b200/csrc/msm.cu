@@ -79,11 +79,21 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     if (seg_override) L = seg_override;
     p.seg_len = L;
     p.segs_ps = p.stride ? (p.stride + L - 1) / L : 0;
-    uint32_t m = pow2_floor(std::max<uint64_t>(1, ((uint64_t)p.sets * p.nb) / 65536));
+    // reduction: ~2^18 threads fold m buckets each (about 7 waves of 2 x 128-thread CTAs per SM at the kernel's 200+ registers),
+    // then CTAs of 256 threads stitch 1024 chunk sums each; more than 32 such groups get one more stitch level
+    uint32_t m = pow2_floor(std::max<uint64_t>(1, ((uint64_t)p.sets * p.nb) / 262144));
     m = std::min<uint32_t>(std::min<uint32_t>(m, 32), p.nb);
     p.chunk = m;
     p.chunks_ps = p.nb / m;
-    p.groups = std::min<uint32_t>(32, std::max<uint32_t>(1, p.chunks_ps / 1024));
+    p.groups = std::min<uint32_t>(256, std::max<uint32_t>(1, p.chunks_ps / 1024));
+    // folded scatter passes: the slice of the sorted list written by one pass should stay in L2 (126 MB); measured on B200 at
+    // 2^24 (768 MiB list): 8 passes 4.1 ms, 16 passes 5.5 ms, 32 passes 8.3 ms, 1 pass 7.1 ms -- each pass re-reads the codes
+    p.phases = 1;
+    if (folded) {
+        static const uint32_t forced = [] { const char *e = getenv("PANDA_MSM_PHASES"); return e ? (uint32_t)atoi(e) : 0u; }();
+        while (p.phases < p.nb && (uint64_t)p.stride * 4 / p.phases > ((uint64_t)128 << 20)) p.phases *= 2;
+        if (forced) p.phases = std::min<uint32_t>(pow2_floor(forced), p.nb);
+    }
 
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
@@ -92,11 +102,11 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.off_cursor = off;  off = align(off + (size_t)p.sets * p.nb * 4);
     p.off_biglist = off; off = align(off + (size_t)p.sets * p.nb * 4);
     p.off_tiles = off;   off = align(off + (size_t)p.sets * ((p.nb + 4095) / 4096) * 4);
-    p.off_digits = off;  off = align(off + (folded ? 0 : (size_t)p.windows * n * 2));
+    p.off_digits = off;  off = align(off + (size_t)p.windows * n * (folded ? 4 : 2));
     p.off_sorted = off;  off = align(off + (size_t)p.sets * p.stride * 4);
     p.off_slots = off;   off = align(off + (size_t)p.sets * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);
     p.off_chunks = off;  off = align(off + (size_t)p.sets * p.chunks_ps * 2 * 4 * fq_bytes);
-    p.off_gsums = off;   off = align(off + (size_t)p.sets * p.groups * 2 * 4 * fq_bytes);
+    p.off_gsums = off;   off = align(off + (size_t)p.sets * (p.groups + 1) * 2 * 4 * fq_bytes);   // + the second stitch level
     p.bytes = off;
     return p;
 }

@@ -26,7 +26,8 @@ struct MsmPlan {
     uint32_t segs_ps;      // ceil(stride / L) segments per set
     uint32_t chunk;        // m: buckets folded serially by one reduction thread
     uint32_t chunks_ps;    // nb / m
-    uint32_t groups;       // CTAs per set in the group-reduce stage (<= 32, divides chunks_ps)
+    uint32_t groups;       // CTAs per set in the group-reduce stage (<= 256, divides chunks_ps)
+    uint32_t phases;       // folded scatter: passes over the codes, one bucket range each (L2-resident output slice)
     // workspace layout (byte offsets into one arena)
     size_t off_counts, off_offsets, off_cursor, off_biglist, off_tiles, off_digits, off_sorted, off_slots, off_chunks, off_gsums, bytes;
     size_t table_bytes;    // folded: size of the precomputed table (W * n affine points)

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <type_traits>
 
 namespace pb {
 
@@ -46,27 +47,29 @@ PB_DEV void for_each_digit(Fr s, uint32_t c, uint32_t W, uint32_t nb, F &&f) {
     }
 }
 
-// K1: scalars -> per-bucket counts (and, in windowed mode, the 16-bit digit codes, window-major).
-// FOLDED (precomputed 2^(c*j) * P tables): every window feeds the single bucket set, nothing is stored.
-// HBM / L2-atomic bound: 32 B read (+ 2W B written) per scalar, W reductions into an L2-resident histogram.
+// K1: scalars -> per-bucket counts and the digit codes, window-major (code[w*n + i]).
+// Windowed: 16-bit codes (|d|-1, sign in bit 15), 0xFFFF = zero digit.  FOLDED (precomputed 2^(c*j) * P tables, every
+// window feeds the single bucket set, c up to 23): 32-bit codes (|d|-1, sign in bit 31), 0xFFFFFFFF = zero digit.
+// HBM / L2-atomic bound: 32 B read + 2W (4W) B written per scalar, W reductions into an L2-resident histogram.
+static constexpr uint32_t CODE_SKIP32 = 0xFFFFFFFFu;
 template <class C, bool FOLDED>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb,
-                                                uint16_t *__restrict__ digits, uint32_t *__restrict__ counts) {
+                                                void *__restrict__ codes_out, uint32_t *__restrict__ counts) {
     using Fr = typename C::Fr;
+    using Code = typename std::conditional<FOLDED, uint32_t, uint16_t>::type;
+    Code *codes = static_cast<Code *>(codes_out);
+    constexpr Code SKIP = FOLDED ? (Code)CODE_SKIP32 : (Code)DIGIT_SKIP;
+    constexpr int SIGN_BIT = FOLDED ? 31 : 15;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; the input is left untouched
-        if (FOLDED) {
-            for_each_digit(s, c, W, nb, [&](uint32_t, uint32_t mag, uint32_t) { atomicAdd(&counts[mag - 1], 1u); });
-        } else {
-            uint32_t next_w = 0;
-            for_each_digit(s, c, W, nb, [&](uint32_t w, uint32_t mag, uint32_t neg) {
-                for (; next_w < w; next_w++) digits[(size_t)next_w * n + i] = (uint16_t)DIGIT_SKIP;
-                digits[(size_t)w * n + i] = (uint16_t)((mag - 1) | (neg << 15));
-                next_w = w + 1;
-                atomicAdd(&counts[(size_t)w * nb + (mag - 1)], 1u);
-            });
-            for (; next_w < W; next_w++) digits[(size_t)next_w * n + i] = (uint16_t)DIGIT_SKIP;
-        }
+        uint32_t next_w = 0;
+        for_each_digit(s, c, W, nb, [&](uint32_t w, uint32_t mag, uint32_t neg) {
+            for (; next_w < w; next_w++) codes[(size_t)next_w * n + i] = SKIP;
+            codes[(size_t)w * n + i] = (Code)((mag - 1) | (neg << SIGN_BIT));
+            next_w = w + 1;
+            atomicAdd(&counts[(FOLDED ? (size_t)0 : (size_t)w * nb) + (mag - 1)], 1u);
+        });
+        for (; next_w < W; next_w++) codes[(size_t)next_w * n + i] = SKIP;
     }
 }
 
@@ -171,17 +174,29 @@ static __global__ void __launch_bounds__(256) k_scatter(const uint16_t *__restri
     }
 }
 
-// K3 (folded): digits are recomputed from the scalar (cheaper than storing 32-bit codes); entry = table index w*n + i.
-template <class C>
-__global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb,
-                                                        uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
-    using Fr = typename C::Fr;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();
-        for_each_digit(s, c, W, nb, [&](uint32_t w, uint32_t mag, uint32_t neg) {
-            const uint32_t pos = atomicAdd(&cursor[mag - 1], 1u);
-            sorted[pos] = (w * n + i) | (neg << 31);
-        });
+// K3 (folded): one bucket set of up to 2^22 buckets; the sorted list (4*W*n bytes) is far larger than L2, so the scatter
+// runs in `phases` passes over the codes (blockIdx.y = phase): pass p only places the entries of bucket range p, whose
+// slice of the sorted list (<= 128 MiB) stays in L2 while its 4-byte writes land, and reaches HBM as full lines.
+// entry = table index w*n + i = the code's own position.
+static __global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *__restrict__ codes, uint32_t total, uint32_t log2_span,
+                                                               uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+    const uint32_t phase = blockIdx.y;
+    auto place = [&](uint32_t code, uint32_t idx) {
+        if (code == CODE_SKIP32) return;
+        const uint32_t b = code & 0x7FFFFFFFu;
+        if ((b >> log2_span) != phase) return;
+        const uint32_t pos = atomicAdd(&cursor[b], 1u);
+        sorted[pos] = idx | (code & 0x80000000u);
+    };
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    if ((total & 3u) == 0) {
+        const uint4 *c4 = reinterpret_cast<const uint4 *>(codes);
+        for (uint32_t q = tid; q < total / 4; q += nthreads) {
+            const uint4 v = __ldg(c4 + q);
+            place(v.x, 4 * q); place(v.y, 4 * q + 1); place(v.z, 4 * q + 2); place(v.w, 4 * q + 3);
+        }
+    } else {
+        for (uint32_t q = tid; q < total; q += nthreads) place(__ldg(codes + q), q);
     }
 }
 
@@ -296,45 +311,80 @@ PB_DEV Xyzz<F> shfl_down_pt(const Xyzz<F> &p, int delta) {
     return r;
 }
 
-// K4b: one CTA per oversized bucket folds all of its partial slots into the first one (strided serial sums,
-// then a shuffle tree per warp and one more across the warps).
+// K4b: oversized buckets (more than BIG_SPAN partial slots: the top window's buckets in table mode, skewed scalars) are folded
+// into their first slot before the bucket reduction.  One warp per bucket (lanes stride over the slots, shuffle tree);
+// buckets with more than BIG_WARP_SPAN slots get the whole CTA (strided serial sums, a shuffle tree per warp, one across warps).
+static constexpr uint32_t BIG_WARP_SPAN = 2048;
 template <class C>
 __global__ void __launch_bounds__(BIG_THREADS) k_reduce_big(uint8_t *__restrict__ slots, const uint32_t *__restrict__ offsets,
                                                            const uint32_t *__restrict__ big_count, const uint32_t *__restrict__ big_list,
                                                            uint32_t nb, uint32_t L, uint32_t segs_pw) {
     using Fq = typename C::Fq;
     using Pt = Xyzz<Fq>;
-    __shared__ uint4 sh_raw[(BIG_THREADS / 32) * Pt::BYTES / 16];
+    constexpr uint32_t WARPS = BIG_THREADS / 32;
+    __shared__ uint4 sh_raw[WARPS * Pt::BYTES / 16];
     uint8_t *sh = reinterpret_cast<uint8_t *>(sh_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t count = *big_count;
-    for (uint32_t e = blockIdx.x; e < count; e += gridDim.x) {
-        const uint32_t id = big_list[e], w = id / nb, j = id % nb;
-        const uint32_t *ow = offsets + (size_t)w * (nb + 1);
-        uint8_t *slot_w = slots + (size_t)w * ((size_t)segs_pw + nb) * Pt::BYTES;
-        const uint32_t s0 = ow[j] / L, s1 = (ow[j + 1] - 1) / L;
-        Pt acc = Pt::identity();
+    for (uint32_t e0 = blockIdx.x * WARPS; e0 < count; e0 += gridDim.x * WARPS) {
+        // ---- warp per bucket
+        {
+            const uint32_t e = e0 + warp;
+            if (e < count) {
+                const uint32_t id = big_list[e], w = id / nb, j = id % nb;
+                const uint32_t *ow = offsets + (size_t)w * (nb + 1);
+                uint8_t *slot_w = slots + (size_t)w * ((size_t)segs_pw + nb) * Pt::BYTES;
+                const uint32_t s0 = ow[j] / L, s1 = (ow[j + 1] - 1) / L;
+                if (s1 - s0 + 1 <= BIG_WARP_SPAN) {
+                    Pt acc = Pt::identity();
 #pragma unroll 1
-        for (uint32_t s = s0 + tid; s <= s1; s += BIG_THREADS) {
-            Pt part = Pt::load(slot_w + ((size_t)s + j) * Pt::BYTES);
-            add_cold(acc, part);
-        }
+                    for (uint32_t s = s0 + lane; s <= s1; s += 32) {
+                        Pt part = Pt::load(slot_w + ((size_t)s + j) * Pt::BYTES);
+                        add_cold(acc, part);
+                    }
+                    __syncwarp();                          // every lane has read its slots (slot s0 + j is overwritten below)
 #pragma unroll 1
-        for (int o = 16; o > 0; o >>= 1) {
-            Pt t = shfl_down_pt(acc, o);
-            if (lane + o < 32) add_cold(acc, t);
-        }
-        __syncthreads();                               // every read of slot s0 + j above is done; smem is free
-        if (lane == 0) acc.store(sh + (size_t)warp * Pt::BYTES);
-        __syncthreads();
-        if (warp == 0) {
-            Pt v = lane < BIG_THREADS / 32 ? Pt::load(sh + (size_t)lane * Pt::BYTES) : Pt::identity();
-#pragma unroll 1
-            for (int o = 4; o > 0; o >>= 1) {
-                Pt t = shfl_down_pt(v, o);
-                if (lane + o < BIG_THREADS / 32) add_cold(v, t);
+                    for (int o = 16; o > 0; o >>= 1) {
+                        Pt t = shfl_down_pt(acc, o);
+                        if (lane + o < 32) add_cold(acc, t);
+                    }
+                    if (lane == 0) acc.store(slot_w + ((size_t)s0 + j) * Pt::BYTES);
+                }
             }
-            if (lane == 0) v.store(slot_w + ((size_t)s0 + j) * Pt::BYTES);
+        }
+        // ---- whole CTA for the giants (block-uniform conditions)
+#pragma unroll 1
+        for (uint32_t k = 0; k < WARPS; k++) {
+            const uint32_t e = e0 + k;
+            if (e >= count) break;
+            const uint32_t id = big_list[e], w = id / nb, j = id % nb;
+            const uint32_t *ow = offsets + (size_t)w * (nb + 1);
+            uint8_t *slot_w = slots + (size_t)w * ((size_t)segs_pw + nb) * Pt::BYTES;
+            const uint32_t s0 = ow[j] / L, s1 = (ow[j + 1] - 1) / L;
+            if (s1 - s0 + 1 <= BIG_WARP_SPAN) continue;
+            Pt acc = Pt::identity();
+#pragma unroll 1
+            for (uint32_t s = s0 + tid; s <= s1; s += BIG_THREADS) {
+                Pt part = Pt::load(slot_w + ((size_t)s + j) * Pt::BYTES);
+                add_cold(acc, part);
+            }
+#pragma unroll 1
+            for (int o = 16; o > 0; o >>= 1) {
+                Pt t = shfl_down_pt(acc, o);
+                if (lane + o < 32) add_cold(acc, t);
+            }
+            __syncthreads();                               // every read of slot s0 + j above is done; smem is free
+            if (lane == 0) acc.store(sh + (size_t)warp * Pt::BYTES);
+            __syncthreads();
+            if (warp == 0) {
+                Pt v = lane < WARPS ? Pt::load(sh + (size_t)lane * Pt::BYTES) : Pt::identity();
+#pragma unroll 1
+                for (int o = 4; o > 0; o >>= 1) {
+                    Pt t = shfl_down_pt(v, o);
+                    if (lane + o < WARPS) add_cold(v, t);
+                }
+                if (lane == 0) v.store(slot_w + ((size_t)s0 + j) * Pt::BYTES);
+            }
         }
     }
 }
@@ -593,8 +643,10 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, stream>>>(counts, tile_sums, p.nb, tiles_ps, p.seg_len, offsets, cursor, big_count, big_list);
         }
         tm.mark();
-        if (p.folded) k_scatter_folded<C><<<sblocks, 256, 0, stream>>>((const uint32_t *)scalars, n, p.c, p.windows, p.nb, cursor, sorted);
-        else k_scatter<<<dim3(sblocks, p.windows), 256, 0, stream>>>(digits, n, p.nb, cursor, sorted);
+        if (p.folded) {
+            uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
+            k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, stream>>>((const uint32_t *)digits, p.stride, log2_span, cursor, sorted);
+        } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, stream>>>(digits, n, p.nb, cursor, sorted);
         tm.mark();
         {
             const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
@@ -611,12 +663,17 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         }
         tm.mark();
         const uint32_t cpg = p.chunks_ps / p.groups;
+        uint32_t log2cpg = 0; while ((1u << log2cpg) < cpg) log2cpg++;
         k_group_reduce<C><<<dim3(p.groups, p.sets), WIN_THREADS, 0, stream>>>(chunks, p.chunks_ps, cpg, log2m, gsums);
-        tm.mark();
-        {
-            uint32_t log2cpg = 0; while ((1u << log2cpg) < cpg) log2cpg++;
-            k_final<C><<<1, 32, 0, stream>>>(gsums, p.sets, p.groups, log2m + log2cpg, p.c, (int)coord, (uint8_t *)result);
+        const uint8_t *final_in = gsums;
+        uint32_t final_groups = p.groups, final_unit = log2m + log2cpg;
+        if (p.groups > 32) {       // second stitch level: the group sums of a set are the items of ONE more CTA (unit = m * cpg)
+            uint8_t *gsums2 = gsums + (size_t)p.sets * p.groups * 2 * Pt::BYTES;
+            k_group_reduce<C><<<dim3(1, p.sets), WIN_THREADS, 0, stream>>>(gsums, p.groups, p.groups, final_unit, gsums2);
+            final_in = gsums2; final_groups = 1;
         }
+        tm.mark();
+        k_final<C><<<1, 32, 0, stream>>>(final_in, p.sets, final_groups, final_unit, p.c, (int)coord, (uint8_t *)result);
         tm.mark();
         err = cudaGetLastError();
     } while (0);

@@ -210,7 +210,7 @@ panda_error panda_debug_msm_plan(int curve, size_t n, int folded, unsigned c_ove
     pb::MsmPlan p = pb::msm_make_plan(curve == 1 ? pb::CURVE_BLS12_377 : pb::CURVE_BN254, (uint32_t)n, folded != 0, c_override, seg_override);
     out->window_bits = p.c; out->windows = p.windows; out->buckets_per_window = p.nb; out->segment_len = p.seg_len;
     out->segments_per_window = p.segs_ps; out->reduce_chunk = p.chunk; out->workspace_bytes = p.bytes;
-    out->folded = p.folded; out->bucket_sets = p.sets; out->groups = p.groups; out->table_bytes = p.table_bytes;
+    out->folded = p.folded; out->bucket_sets = p.sets; out->groups = p.groups; out->phases = p.phases; out->table_bytes = p.table_bytes;
     return panda_success;
 }
 

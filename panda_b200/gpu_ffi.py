@@ -187,6 +187,7 @@ class MsmPlanInfo(C.Structure):  # include/panda_debug.h
         ("folded", C.c_uint),
         ("bucket_sets", C.c_uint),
         ("groups", C.c_uint),
+        ("phases", C.c_uint),
         ("table_bytes", C.c_size_t),
     ]
 

@@ -38,7 +38,7 @@ for r in range(reps):
     assert rc == 0, rc
     tot = sum(stage)
     ffi.lib.panda_debug_msm_plan(cid, n, info[0], info[1], seg_over, C.byref(plan))
-    print(f"rep {r}: [folded={info[0]} c={info[1]} W={info[2]} nb={plan.buckets_per_window} L={plan.segment_len} m={plan.reduce_chunk} G={plan.groups} ws={plan.workspace_bytes / 2**20:.0f} MiB table={plan.table_bytes / 2**30:.1f} GiB] total {tot:.3f} ms  {n / tot / 1e3:.1f} Mpts/s  stages[digits,scan,scatter,accum,bucket,window,final]={[round(x, 3) for x in stage]} wall={1e3 * (time.time() - t0):.1f} ms", flush=True)
+    print(f"rep {r}: [folded={info[0]} c={info[1]} W={info[2]} nb={plan.buckets_per_window} L={plan.segment_len} m={plan.reduce_chunk} G={plan.groups} P={plan.phases} ws={plan.workspace_bytes / 2**20:.0f} MiB table={plan.table_bytes / 2**30:.1f} GiB] total {tot:.3f} ms  {n / tot / 1e3:.1f} Mpts/s  stages[digits,scan,scatter,accum,bucket,window,final]={[round(x, 3) for x in stage]} wall={1e3 * (time.time() - t0):.1f} ms", flush=True)
 got = d_r.to_numpy()
 print("closed-form match:", bool((O.jac_to_affine(cid, got) == exp).all()))
 # untimed API path with events around it
