@@ -29,7 +29,12 @@ sys.path.insert(0, ROOT)
 LOG_N = 24
 MODMUL_MACS = 136            # 2*8^2 + 8 32x32->64 multiply-adds per BN254 Montgomery product
 MADD_MODMULS = 10            # XYZZ mixed addition: 8M + 2S
-KERNELS_PER_MSM = 8          # digits, scan, scatter, accumulate, reduce_big, bucket_reduce, window_reduce, final
+
+
+def kernels_per_msm(plan) -> int:
+    """our launches in one device-resident MSM: [fingerprint] digits, scan x3, scatter, accumulate, reduce_big, bucket_reduce,
+    group_reduce (x2 when there are more than 32 groups), final"""
+    return (1 if plan.folded else 0) + 1 + 3 + 1 + 1 + 1 + 1 + (2 if plan.groups > 32 else 1) + 1
 
 
 def log(*a):
@@ -57,7 +62,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -247,12 +252,15 @@ def run_own_arm(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         step()
+        marks[i].record()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    per_step = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(args.steps)]
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -294,6 +302,43 @@ def run_own_arm(args):
     e2e_ms = float(t.item())
     ffi.lib.panda_free_host(pinned)
     mgr.deinit()
+
+    # ---- N > 1: the sharded four-step NTT at 2^26 (BASELINE.json config 4), NVLink peer stores, device-timed, max over ranks
+    sharded_ntt = None
+    if world > 1:
+        from panda_b200.sharded_ntt import ShardedNtt
+        kk = 26
+        try:
+            sn = ShardedNtt(kk, O.omega_bn254(kk).tobytes(), transport="auto")
+            xin = torch.randint(0, 256, ((1 << kk) // world * 32,), dtype=torch.uint8, device=dev)
+            xin.view(-1, 32)[:, 31] &= 0x0F                       # < 2^252 < r: valid field elements
+            y = sn.forward(xin)
+            ok_rt = bool((sn.inverse(y) == xin).all().item())
+            tms = {}
+            for name, fn, arg in (("forward", sn.forward, xin), ("inverse", sn.inverse, sn.forward(xin).clone())):
+                for _ in range(3):
+                    fn(arg)
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(5):
+                    fn(arg)
+                a1.record()
+                barrier()
+                tt = torch.tensor([a0.elapsed_time(a1) / 5], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                tms[name] = float(tt.item())
+            okt = torch.tensor([int(ok_rt)], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            xbytes = (1 << kk) // world * 32 * (world - 1) // world
+            sharded_ntt = {"metric": "bn254_fr_ntt_2^26_sharded_latency", "log_n": kk, "gpus": world, "transport": sn.transport,
+                           "forward_ms": tms["forward"], "inverse_ms": tms["inverse"], "round_trip_ok": bool(okt.item()),
+                           "exchange_bytes_per_gpu": xbytes,
+                           "exchange_GBps_lower_bound": xbytes / (tms["forward"] * 1e-3) / 1e9,
+                           "layout": "column blocks in, row blocks out (panda_b200/sharded_ntt.py)"}
+            del sn, xin, y
+        except Exception as exc:      # reported, not hidden
+            sharded_ntt = {"error": repr(exc)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -364,8 +409,8 @@ def run_own_arm(args):
                    "verified_against_closed_form": verified and e2e_ok},
         "clocks": clocks,
         "e2e": {"value": n / (e2e_ms * 1e-3) / 1e6, "unit": "Mpts/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(scal_h.size) * world,
-                "d2h_bytes_per_step": 96 * world, "api": "panda_msm_bn254_gpu_with_cached_bases (host scalars pinned, cached bases)"},
-        "gpu_launches": args.steps * world * (KERNELS_PER_MSM + (1 if world > 1 else 0)),
+                "d2h_bytes_per_step": 96 * world, "api": "panda_msm_bn254_gpu_with_cached_bases (host scalars pinned, cached bases) -> panda_msm_execute_bn254_host_scalars: chunked upload overlapped with the sort / accumulation"},
+        "gpu_launches": args.steps * world * (kernels_per_msm(plan) + (1 if world > 1 else 0)),
         "roofline": {"kernel": "k_accumulate (bucket accumulation, XYZZ mixed additions)", "bound": "int32-imad", "achieved": achieved_macs / 1e12,
                      "peak": wide_peak / 1e12, "unit": "T(32x32+64 MAC)/s", "frac": achieved_macs / wide_peak, "traffic": None,
                      "peak_source": "IMAD.WIDE issue rate measured live by panda_debug_int_peak (32-bit IMAD rate: %.2f T/s; BN254 modmul microbench: %.2f G modmul/s)"
@@ -378,11 +423,14 @@ def run_own_arm(args):
                          "hbm_stages": {"k_digits": {"GB/s": digits_bytes / (float(stages[0]) * 1e-3) / 1e9, "frac": digits_bytes / (float(stages[0]) * 1e-3) / 1e9 / hbm_peak},
                                         "k_scatter": {"GB/s": scatter_bytes / (float(stages[2]) * 1e-3) / 1e9, "frac": scatter_bytes / (float(stages[2]) * 1e-3) / 1e9 / hbm_peak}}},
         "stage_ms": {nm: float(v) for nm, v in zip(names, stages)},
+        "step_ms_rank0": [round(x, 3) for x in per_step],
         "ntt": {"metric": "bn254_fr_ntt_2^24_latency", "ms": ntt_ms, "passes": ntt_passes, "modmul_per_s": ntt_modmuls / (ntt_ms * 1e-3),
                 "frac_of_modmul_peak": ntt_modmuls / (ntt_ms * 1e-3) / modmul_peak, "hbm_GBps": ntt_passes * 64 * (1 << k) / (ntt_ms * 1e-3) / 1e9,
                 "frac_of_hbm_peak": ntt_passes * 64 * (1 << k) / (ntt_ms * 1e-3) / 1e9 / hbm_peak},
         "cpu_baseline": cpu,
     }
+    if sharded_ntt is not None:
+        line["ntt_sharded"] = sharded_ntt
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

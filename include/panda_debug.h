@@ -48,6 +48,9 @@ panda_error panda_debug_msm_plan(int curve_id, size_t n, int folded, unsigned c_
 panda_error panda_debug_msm_timed(int curve_id, const panda_msm_configuration cfg, size_t n, unsigned c_override, unsigned seg_override,
                                   int table_mode, float *stage_ms, unsigned *info);
 
+/* panda_msm_execute_*_host_scalars with an explicit table mode and chunk count (0 = automatic). */
+panda_error panda_debug_msm_streamed(int curve_id, const panda_msm_configuration cfg, size_t n, int table_mode, unsigned chunks);
+
 /* Integer-pipe microbenchmarks on the current device (synchronous).
  * kind 0: independent IMAD (32-bit) chains, 1: independent IMAD.WIDE chains, 2: Montgomery products (BN254 Fq) in
  * 4 independent chains per thread.  Fills *ms (device time of the timed launch) and *ops (instructions of that kind /

@@ -143,6 +143,15 @@ panda_error panda_msm_execute_bls12_377(const panda_msm_configuration exec_cfg);
 panda_error panda_msm_execute_bn254_n(const panda_msm_configuration exec_cfg, size_t n);
 panda_error panda_msm_execute_bls12_377_n(const panda_msm_configuration exec_cfg, size_t n);
 
+/* MSM whose scalars are still in HOST memory (cfg.scalars: host pointer, pinned for full overlap; cfg.bases / cfg.results:
+ * device pointers as in panda_msm_execute_bn254).  Replaces the copy-then-execute sequence of unit.rs:103-188
+ * (panda_msm_bn254_gpu_with_cached_bases): the library uploads the scalars in chunks on its own copy stream and sorts /
+ * accumulates chunk q while chunk q+1 is still crossing PCIe.  n need not be a power of two;
+ * cfg.log_scalars_count is ignored.  Asynchronous on cfg.stream (pinned memory); the host buffer must stay valid until the
+ * stream reaches the end of the call. */
+panda_error panda_msm_execute_bn254_host_scalars(const panda_msm_configuration exec_cfg, size_t n);
+panda_error panda_msm_execute_bls12_377_host_scalars(const panda_msm_configuration exec_cfg, size_t n);
+
 /* Sum `count` Jacobian partial results (device, count x 96 B / 144 B; e.g. the all-gathered per-GPU results of an
  * MSM sharded by point range) into `result` (device) in the requested coordinates.  Asynchronous on `stream`. */
 panda_error panda_msm_combine_bn254(const void *partials, unsigned count, void *result,

@@ -19,9 +19,9 @@ namespace pb {
 
 // per-curve instantiations (msm_bn254.cu / msm_bls12_377.cu)
 cudaError_t msm_pipeline_bn254(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
-                               cudaStream_t stream, MsmStageTimes *timings);
+                               cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed);
 cudaError_t msm_pipeline_bls12_377(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
-                                   cudaStream_t stream, MsmStageTimes *timings);
+                                   cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed);
 cudaError_t msm_build_table_bn254(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream);
 cudaError_t msm_build_table_bls12_377(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream);
 cudaError_t msm_fingerprint_launch(const void *data, size_t bytes, unsigned long long *d_out, cudaStream_t stream);
@@ -41,7 +41,7 @@ static uint32_t windows_for(uint32_t bits, uint32_t c) {
 
 static uint32_t pow2_floor(uint64_t v) { uint32_t r = 1; while ((uint64_t)r * 2 <= v) r *= 2; return r; }
 
-MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget) {
+MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget, uint32_t chunks) {
     const uint32_t bits = curve == CURVE_BLS12_377 ? 253 : 254;
     const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
     MsmPlan p{};
@@ -68,7 +68,12 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.windows = windows_for(bits, p.c);
     p.nb = 1u << (p.c - 1);
     p.sets = folded ? 1 : p.windows;
-    p.stride = folded ? n * p.windows : n;
+    // chunks (folded only): every chunk is a physical bucket set of its own (counts, sorted list, partial slots); the bucket
+    // reduction merges the chunks of a logical set
+    p.chunks = folded ? std::max<uint32_t>(1, std::min<uint32_t>(chunks, std::max<uint32_t>(1, n / 4096))) : 1;
+    p.chunk_n = p.chunks > 1 ? ((n + p.chunks - 1) / p.chunks + 3) & ~3u : n;
+    p.chunks = (n + p.chunk_n - 1) / p.chunk_n;
+    p.stride = folded ? p.chunk_n * p.windows : n;
     p.table_bytes = folded ? (size_t)n * p.windows * 2 * fq_bytes : 0;
     // segment length: about one average bucket, so that most buckets end up with one or two partial sums, but
     // never so long that the accumulation kernel has fewer than ~4 waves of threads (148 SMs x 384 threads)
@@ -97,14 +102,15 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
 
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
-    p.off_counts = off;  off = align(off + (size_t)p.sets * p.nb * 4 + 4);      // + the big-bucket counter
-    p.off_offsets = off; off = align(off + (size_t)p.sets * (p.nb + 1) * 4);
-    p.off_cursor = off;  off = align(off + (size_t)p.sets * p.nb * 4);
-    p.off_biglist = off; off = align(off + (size_t)p.sets * p.nb * 4);
-    p.off_tiles = off;   off = align(off + (size_t)p.sets * ((p.nb + 4095) / 4096) * 4);
-    p.off_digits = off;  off = align(off + (size_t)p.windows * n * (folded ? 4 : 2));
-    p.off_sorted = off;  off = align(off + (size_t)p.sets * p.stride * 4);
-    p.off_slots = off;   off = align(off + (size_t)p.sets * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);
+    const size_t phys = (size_t)p.sets * p.chunks;                              // physical bucket sets
+    p.off_counts = off;  off = align(off + phys * (p.nb + 1) * 4);              // per set: nb counts + its big-bucket counter
+    p.off_offsets = off; off = align(off + phys * (p.nb + 1) * 4);
+    p.off_cursor = off;  off = align(off + phys * p.nb * 4);
+    p.off_biglist = off; off = align(off + phys * p.nb * 4);
+    p.off_tiles = off;   off = align(off + phys * ((p.nb + 4095) / 4096) * 4);
+    p.off_digits = off;  off = align(off + (folded ? (size_t)p.chunks * p.stride * 4 : (size_t)p.windows * n * 2));
+    p.off_sorted = off;  off = align(off + phys * p.stride * 4);
+    p.off_slots = off;   off = align(off + phys * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);
     p.off_chunks = off;  off = align(off + (size_t)p.sets * p.chunks_ps * 2 * 4 * fq_bytes);
     p.off_gsums = off;   off = align(off + (size_t)p.sets * (p.groups + 1) * 2 * 4 * fq_bytes);   // + the second stitch level
     p.bytes = off;
@@ -161,10 +167,83 @@ static int default_table_mode() {
 #define PB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[panda-b200] CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); return e_; } } while (0)
 
 static cudaError_t run_pipeline(CurveId curve, const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord,
-                                cudaMemPool_t pool, cudaStream_t stream, MsmStageTimes *timings) {
+                                cudaMemPool_t pool, cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed = nullptr) {
     if (timings) { timings->folded = (int)p.folded; timings->c = p.c; timings->windows = p.windows; }
-    if (curve == CURVE_BLS12_377) return msm_pipeline_bls12_377(p, points, scalars, result, coord, pool, stream, timings);
-    return msm_pipeline_bn254(p, points, scalars, result, coord, pool, stream, timings);
+    if (curve == CURVE_BLS12_377) return msm_pipeline_bls12_377(p, points, scalars, result, coord, pool, stream, timings, feed);
+    return msm_pipeline_bn254(p, points, scalars, result, coord, pool, stream, timings, feed);
+}
+
+// Looks `bases` up in the table cache (building the table when the mode asks for it).  On return *table is the table to use
+// (with its window width in *tc and `stream` already waiting for the build) or nullptr: stay on the windowed path.
+static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, cudaStream_t stream, int table_mode, uint32_t c_override,
+                                 const void **table, uint32_t *tc) {
+    *table = nullptr;
+    const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
+    if (table_mode == MSM_TABLE_DEFAULT) table_mode = default_table_mode();
+    if (table_mode == MSM_TABLE_OFF || n < 1024) return cudaSuccess;
+    int dev = 0;
+    PB_CUDA(cudaGetDevice(&dev));
+    // 1. content fingerprint of the bases (one pass over n * 64 bytes at HBM speed, 8 bytes read back)
+    unsigned long long *d_fp = nullptr, fp = 0;
+    PB_CUDA(cudaMallocAsync((void **)&d_fp, 8, stream));
+    cudaError_t e = msm_fingerprint_launch(bases, (size_t)n * 2 * fq_bytes, d_fp, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&fp, d_fp, 8, cudaMemcpyDeviceToHost, stream);
+    cudaError_t f = cudaFreeAsync(d_fp, stream);
+    if (e == cudaSuccess) e = f;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    PB_CUDA(e);
+
+    std::unique_lock<std::mutex> lock(g_table_mutex);
+    TableEntry *hit = nullptr;
+    for (auto &t : g_tables)
+        if (t.device == dev && t.curve == curve && t.bases == bases && t.n == n) { hit = &t; break; }
+    if (hit && hit->fingerprint != fp) {      // same pointer, different points: forget what we knew
+        drop_table(*hit);
+        hit->fingerprint = fp; hit->sightings = 0;
+    }
+    if (!hit) {
+        if (g_tables.size() >= MAX_TABLES) {  // evict the least recently used entry
+            size_t victim = 0;
+            for (size_t i = 1; i < g_tables.size(); i++) if (g_tables[i].last_use < g_tables[victim].last_use) victim = i;
+            int cur = 0; cudaGetDevice(&cur); cudaSetDevice(g_tables[victim].device);
+            drop_table(g_tables[victim]);
+            cudaSetDevice(cur);
+            g_tables.erase(g_tables.begin() + victim);
+        }
+        g_tables.push_back(TableEntry{dev, curve, bases, n, fp, 0, nullptr, 0, 0, 0, nullptr, 0});
+        hit = &g_tables.back();
+    }
+    hit->sightings++;
+    hit->last_use = ++g_use_clock;
+    const bool want = table_mode == MSM_TABLE_EAGER || hit->sightings >= 2;
+    if (!hit->table && want) {
+        size_t free_b = 0, total_b = 0;
+        PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t budget = free_b > ((size_t)6 << 30) ? (free_b - ((size_t)4 << 30)) / 2 : 0;   // leave room for workspaces
+        MsmPlan fp_plan = msm_make_plan(curve, n, true, c_override > 16 ? c_override : 0, 0, budget);
+        if (fp_plan.c) {
+            void *tab = nullptr;
+            if (cudaMalloc(&tab, fp_plan.table_bytes) == cudaSuccess) {
+                cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, tab, stream)
+                                                          : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, tab, stream);
+                cudaEvent_t ev = nullptr;
+                if (be == cudaSuccess) be = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                if (be == cudaSuccess) be = cudaEventRecord(ev, stream);
+                if (be != cudaSuccess) { cudaFree(tab); if (ev) cudaEventDestroy(ev); return be; }
+                hit->table = tab; hit->c = fp_plan.c; hit->windows = fp_plan.windows; hit->bytes = fp_plan.table_bytes; hit->ready = ev;
+            } else {
+                cudaGetLastError();            // out of memory: stay on the windowed path
+            }
+        }
+    }
+    if (hit->table) {
+        *table = hit->table;
+        *tc = hit->c;
+        cudaEvent_t ready = hit->ready;
+        lock.unlock();
+        PB_CUDA(cudaStreamWaitEvent(stream, ready, 0));
+    }
+    return cudaSuccess;
 }
 
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
@@ -174,75 +253,60 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
         PB_CUDA(cudaMemsetAsync(result, 0, 3 * fq_bytes, stream));
         return cudaSuccess;
     }
-    if (table_mode == MSM_TABLE_DEFAULT) table_mode = default_table_mode();
-    if (table_mode != MSM_TABLE_OFF && n >= 1024) {
-        int dev = 0;
-        PB_CUDA(cudaGetDevice(&dev));
-        // 1. content fingerprint of the bases (one pass over n * 64 bytes at HBM speed, 8 bytes read back)
-        unsigned long long *d_fp = nullptr, fp = 0;
-        PB_CUDA(cudaMallocAsync((void **)&d_fp, 8, stream));
-        cudaError_t e = msm_fingerprint_launch(bases, (size_t)n * 2 * fq_bytes, d_fp, stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&fp, d_fp, 8, cudaMemcpyDeviceToHost, stream);
-        cudaError_t f = cudaFreeAsync(d_fp, stream);
-        if (e == cudaSuccess) e = f;
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        PB_CUDA(e);
-
-        std::unique_lock<std::mutex> lock(g_table_mutex);
-        TableEntry *hit = nullptr;
-        for (auto &t : g_tables)
-            if (t.device == dev && t.curve == curve && t.bases == bases && t.n == n) { hit = &t; break; }
-        if (hit && hit->fingerprint != fp) {      // same pointer, different points: forget what we knew
-            drop_table(*hit);
-            hit->fingerprint = fp; hit->sightings = 0;
-        }
-        if (!hit) {
-            if (g_tables.size() >= MAX_TABLES) {  // evict the least recently used entry
-                size_t victim = 0;
-                for (size_t i = 1; i < g_tables.size(); i++) if (g_tables[i].last_use < g_tables[victim].last_use) victim = i;
-                int cur = 0; cudaGetDevice(&cur); cudaSetDevice(g_tables[victim].device);
-                drop_table(g_tables[victim]);
-                cudaSetDevice(cur);
-                g_tables.erase(g_tables.begin() + victim);
-            }
-            g_tables.push_back(TableEntry{dev, curve, bases, n, fp, 0, nullptr, 0, 0, 0, nullptr, 0});
-            hit = &g_tables.back();
-        }
-        hit->sightings++;
-        hit->last_use = ++g_use_clock;
-        const bool want = table_mode == MSM_TABLE_EAGER || hit->sightings >= 2;
-        if (!hit->table && want) {
-            size_t free_b = 0, total_b = 0;
-            PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            const size_t budget = free_b > ((size_t)6 << 30) ? (free_b - ((size_t)4 << 30)) / 2 : 0;   // leave room for workspaces
-            MsmPlan fp_plan = msm_make_plan(curve, n, true, c_override > 16 ? c_override : 0, 0, budget);
-            if (fp_plan.c) {
-                void *tab = nullptr;
-                if (cudaMalloc(&tab, fp_plan.table_bytes) == cudaSuccess) {
-                    cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, tab, stream)
-                                                              : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, tab, stream);
-                    cudaEvent_t ev = nullptr;
-                    if (be == cudaSuccess) be = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-                    if (be == cudaSuccess) be = cudaEventRecord(ev, stream);
-                    if (be != cudaSuccess) { cudaFree(tab); if (ev) cudaEventDestroy(ev); return be; }
-                    hit->table = tab; hit->c = fp_plan.c; hit->windows = fp_plan.windows; hit->bytes = fp_plan.table_bytes; hit->ready = ev;
-                } else {
-                    cudaGetLastError();            // out of memory: stay on the windowed path
-                }
-            }
-        }
-        if (hit->table) {
-            const void *table = hit->table;
-            const uint32_t tc = hit->c;
-            cudaEvent_t ready = hit->ready;
-            lock.unlock();
-            PB_CUDA(cudaStreamWaitEvent(stream, ready, 0));
-            MsmPlan p = msm_make_plan(curve, n, true, tc, seg_override);
-            return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings);
-        }
+    const void *table = nullptr;
+    uint32_t tc = 0;
+    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, c_override, &table, &tc));
+    if (table) {
+        MsmPlan p = msm_make_plan(curve, n, true, tc, seg_override);
+        return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings);
     }
     MsmPlan p = msm_make_plan(curve, n, false, c_override <= 16 ? c_override : 0, seg_override);
     return run_pipeline(curve, p, bases, scalars, result, coord, pool, stream, timings);
+}
+
+// one copy stream per device for streamed scalars (created on first use, lives as long as the process)
+static cudaError_t copy_stream_for_current_device(cudaStream_t *out) {
+    static std::mutex m;
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    PB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(m);
+    if (!streams[dev]) PB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    *out = streams[dev];
+    return cudaSuccess;
+}
+
+cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_scalars, uint32_t n, void *result, CoordType coord,
+                             cudaMemPool_t pool, cudaStream_t stream, int table_mode, uint32_t chunks_override) {
+    const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
+    if (n == 0) {
+        PB_CUDA(cudaMemsetAsync(result, 0, 3 * fq_bytes, stream));
+        return cudaSuccess;
+    }
+    const void *table = nullptr;
+    uint32_t tc = 0;
+    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, 0, &table, &tc));
+    uint8_t *d_scal = nullptr;
+    if (pool) PB_CUDA(cudaMallocFromPoolAsync((void **)&d_scal, (size_t)n * 32, pool, stream));
+    else PB_CUDA(cudaMallocAsync((void **)&d_scal, (size_t)n * 32, stream));
+    cudaError_t e;
+    if (table) {
+        static const uint32_t forced = [] { const char *v = getenv("PANDA_MSM_CHUNKS"); return v ? (uint32_t)atoi(v) : 0u; }();
+        uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 19) ? 2 : 1);
+        MsmPlan p = msm_make_plan(curve, n, true, tc, 0, ~(size_t)0, chunks);
+        MsmFeed feed{host_scalars, d_scal, nullptr};
+        e = copy_stream_for_current_device(&feed.copy_stream);
+        if (e == cudaSuccess) e = run_pipeline(curve, p, table, d_scal, result, coord, pool, stream, nullptr, &feed);
+    } else {
+        e = cudaMemcpyAsync(d_scal, host_scalars, (size_t)n * 32, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) {
+            MsmPlan p = msm_make_plan(curve, n, false, 0, 0);
+            e = run_pipeline(curve, p, bases, d_scal, result, coord, pool, stream, nullptr);
+        }
+    }
+    cudaError_t f = cudaFreeAsync(d_scal, stream);
+    return e != cudaSuccess ? e : f;
 }
 
 cudaError_t msm_combine(CurveId curve, const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream) {

@@ -27,6 +27,9 @@ struct MsmPlan {
     uint32_t chunk;        // m: buckets folded serially by one reduction thread
     uint32_t chunks_ps;    // nb / m
     uint32_t groups;       // CTAs per set in the group-reduce stage (<= 256, divides chunks_ps)
+    uint32_t chunks;       // Q: point-range chunks that are sorted and accumulated separately and share the bucket reduction
+                           //    (Q > 1 only for streamed scalars: chunk q computes while chunk q+1 is still being uploaded)
+    uint32_t chunk_n;      // points per chunk (the last chunk may be shorter)
     uint32_t phases;       // folded scatter: passes over the codes, one bucket range each (L2-resident output slice)
     // workspace layout (byte offsets into one arena)
     size_t off_counts, off_offsets, off_cursor, off_biglist, off_tiles, off_digits, off_sorted, off_slots, off_chunks, off_gsums, bytes;
@@ -34,7 +37,11 @@ struct MsmPlan {
 };
 
 // window width / segment length selection; c_override = 0 -> cost model.  table_budget: bytes available for a table (folded only).
-MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget = ~(size_t)0);
+MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget = ~(size_t)0,
+                      uint32_t chunks = 1);
+
+// Scalars still in HOST memory: the pipeline uploads chunk q on copy_stream right before queueing chunk q's kernels.
+struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; };
 
 // Per-stage device timings (ms) filled when msm_run is called with timings != nullptr (adds event syncs;
 // the benchmark harness uses it to attribute time to kernels -- never set on the product path).
@@ -54,6 +61,12 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
                     CoordType coord, cudaMemPool_t pool, cudaStream_t stream,
                     uint32_t c_override = 0, uint32_t seg_override = 0, MsmStageTimes *timings = nullptr,
                     int table_mode = MSM_TABLE_DEFAULT);
+
+// Same MSM with the scalars in HOST memory (pinned for full overlap; pageable works).  With a table for `bases` the points are
+// processed in chunks that share the bucket reduction, so the upload of chunk q+1 overlaps the sort / accumulation of chunk q;
+// without one the scalars are uploaded in one piece.  Asynchronous on `stream` for pinned memory.
+cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_scalars, uint32_t n, void *result, CoordType coord,
+                             cudaMemPool_t pool, cudaStream_t stream, int table_mode = MSM_TABLE_DEFAULT, uint32_t chunks_override = 0);
 
 // result = sum of `count` Jacobian partials (the per-GPU results of a sharded MSM), then coordinate conversion.
 cudaError_t msm_combine(CurveId curve, const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream);

@@ -4,8 +4,8 @@
 namespace pb {
 
 cudaError_t msm_pipeline_bls12_377(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
-                            cudaStream_t stream, MsmStageTimes *timings) {
-    return msm_pipeline_t<Bls377>(p, points, scalars, result, coord, pool, stream, timings);
+                            cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed) {
+    return msm_pipeline_t<Bls377>(p, points, scalars, result, coord, pool, stream, timings, feed);
 }
 cudaError_t msm_build_table_bls12_377(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream) {
     return msm_build_table_t<Bls377>(bases, n, c, W, table, stream);

@@ -178,25 +178,31 @@ static __global__ void __launch_bounds__(256) k_scatter(const uint16_t *__restri
 // runs in `phases` passes over the codes (blockIdx.y = phase): pass p only places the entries of bucket range p, whose
 // slice of the sorted list (<= 128 MiB) stays in L2 while its 4-byte writes land, and reaches HBM as full lines.
 // entry = table index w*n + i = the code's own position.
-static __global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *__restrict__ codes, uint32_t total, uint32_t log2_span,
-                                                               uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+static __global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *__restrict__ codes, uint32_t nq, uint32_t W, uint32_t n_total,
+                                                               uint32_t point0, uint32_t log2_span, uint32_t *__restrict__ cursor,
+                                                               uint32_t *__restrict__ sorted) {
+    // codes[w * nq + i] belongs to point point0 + i (a chunk of the job); its table entry is w * n_total + point0 + i
     const uint32_t phase = blockIdx.y;
-    auto place = [&](uint32_t code, uint32_t idx) {
-        if (code == CODE_SKIP32) return;
-        const uint32_t b = code & 0x7FFFFFFFu;
-        if ((b >> log2_span) != phase) return;
-        const uint32_t pos = atomicAdd(&cursor[b], 1u);
-        sorted[pos] = idx | (code & 0x80000000u);
-    };
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    if ((total & 3u) == 0) {
-        const uint4 *c4 = reinterpret_cast<const uint4 *>(codes);
-        for (uint32_t q = tid; q < total / 4; q += nthreads) {
-            const uint4 v = __ldg(c4 + q);
-            place(v.x, 4 * q); place(v.y, 4 * q + 1); place(v.z, 4 * q + 2); place(v.w, 4 * q + 3);
+    for (uint32_t w = 0; w < W; w++) {
+        const uint32_t *cw = codes + (size_t)w * nq;
+        const uint32_t entry0 = w * n_total + point0;
+        auto place = [&](uint32_t code, uint32_t i) {
+            if (code == CODE_SKIP32) return;
+            const uint32_t b = code & 0x7FFFFFFFu;
+            if ((b >> log2_span) != phase) return;
+            const uint32_t pos = atomicAdd(&cursor[b], 1u);
+            sorted[pos] = (entry0 + i) | (code & 0x80000000u);
+        };
+        if ((nq & 3u) == 0) {
+            const uint4 *c4 = reinterpret_cast<const uint4 *>(cw);
+            for (uint32_t q = tid; q < nq / 4; q += nthreads) {
+                const uint4 v = __ldg(c4 + q);
+                place(v.x, 4 * q); place(v.y, 4 * q + 1); place(v.z, 4 * q + 2); place(v.w, 4 * q + 3);
+            }
+        } else {
+            for (uint32_t q = tid; q < nq; q += nthreads) place(__ldg(cw + q), q);
         }
-    } else {
-        for (uint32_t q = tid; q < total; q += nthreads) place(__ldg(codes + q), q);
     }
 }
 
@@ -254,32 +260,37 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint8_t *__res
 }
 
 // K5: bucket combine + first level of the running-sum reduction.  Thread (w, t) folds buckets
-// [t*m, (t+1)*m) of window w from the top: B_j = sum of its partial slots, run += B_j, tri += run.
+// [t*m, (t+1)*m) of logical set w from the top: B_j = sum of its partial slots over all `merge` chunks (physical set
+// q * W + w holds chunk q's partials), run += B_j, tri += run.
 // Emits Lc = sum_i (i+1) * B_{t*m+i} and Rc = sum_i B_{t*m+i}.
 template <class C>
 __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ offsets,
-                                                              uint32_t nb, uint32_t L, uint32_t segs_pw, uint32_t W, uint32_t m,
+                                                              uint32_t nb, uint32_t L, uint32_t segs_pw, uint32_t W, uint32_t merge, uint32_t m,
                                                               uint32_t chunks_pw, uint8_t *__restrict__ chunks) {
     using Fq = typename C::Fq;
     using Pt = Xyzz<Fq>;
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= W * chunks_pw) return;
     const uint32_t w = gid / chunks_pw, t = gid % chunks_pw;
-    const uint32_t *ow = offsets + (size_t)w * (nb + 1);
-    const uint8_t *slot_w = slots + (size_t)w * ((size_t)segs_pw + nb) * Pt::BYTES;
     Pt run = Pt::identity(), tri = Pt::identity();
 #pragma unroll 1
     for (uint32_t i = m; i-- > 0;) {
         const uint32_t j = t * m + i;
-        const uint32_t o0 = __ldg(ow + j), o1 = __ldg(ow + j + 1);
-        if (o1 > o0) {
-            const uint32_t s0 = o0 / L;
-            uint32_t s1 = (o1 - 1) / L;
-            if (s1 - s0 + 1 > BIG_SPAN) s1 = s0;       // already folded into its first slot by k_reduce_big
 #pragma unroll 1
-            for (uint32_t s = s0; s <= s1; s++) {
-                Pt part = Pt::load(slot_w + ((size_t)s + j) * Pt::BYTES);
-                run.add(part);
+        for (uint32_t q = 0; q < merge; q++) {
+            const size_t set = (size_t)q * W + w;
+            const uint32_t *ow = offsets + set * (nb + 1);
+            const uint8_t *slot_w = slots + set * ((size_t)segs_pw + nb) * Pt::BYTES;
+            const uint32_t o0 = __ldg(ow + j), o1 = __ldg(ow + j + 1);
+            if (o1 > o0) {
+                const uint32_t s0 = o0 / L;
+                uint32_t s1 = (o1 - 1) / L;
+                if (s1 - s0 + 1 > BIG_SPAN) s1 = s0;       // already folded into its first slot by k_reduce_big
+#pragma unroll 1
+                for (uint32_t sg = s0; sg <= s1; sg++) {
+                    Pt part = Pt::load(slot_w + ((size_t)sg + j) * Pt::BYTES);
+                    run.add(part);
+                }
             }
         }
         tri.add(run);
@@ -612,54 +623,81 @@ struct StageTimer {
 };
 
 // Runs the pipeline described by `p`.  `points` is the caller's bases (windowed) or the precomputed table (folded).
+// feed != nullptr: the scalars are still in host memory; chunk q is uploaded on feed->copy_stream right before chunk q's kernels
+// are queued, so the upload of chunk q+1 overlaps the sort / accumulation of chunk q.
 template <class C>
 cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
-                           cudaStream_t stream, MsmStageTimes *timings) {
+                           cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed) {
     using Pt = Xyzz<typename C::Fq>;
     const uint32_t n = p.n;
     uint8_t *ws = nullptr;
     if (pool) PB_CUDA(cudaMallocFromPoolAsync((void **)&ws, p.bytes, pool, stream));
     else PB_CUDA(cudaMallocAsync((void **)&ws, p.bytes, stream));
+    const size_t phys = (size_t)p.sets * p.chunks;
     uint32_t *counts = (uint32_t *)(ws + p.off_counts), *offsets = (uint32_t *)(ws + p.off_offsets), *cursor = (uint32_t *)(ws + p.off_cursor);
-    uint32_t *big_count = counts + (size_t)p.sets * p.nb, *big_list = (uint32_t *)(ws + p.off_biglist);   // the counter is zeroed with the counts
+    uint32_t *big_counts = counts + phys * p.nb, *big_list = (uint32_t *)(ws + p.off_biglist);   // the counters are zeroed with the counts
     uint32_t *tile_sums = (uint32_t *)(ws + p.off_tiles);
-    uint16_t *digits = (uint16_t *)(ws + p.off_digits);
+    uint8_t *digits = ws + p.off_digits;
     uint32_t *sorted = (uint32_t *)(ws + p.off_sorted);
     uint8_t *slots = ws + p.off_slots, *chunks = ws + p.off_chunks, *gsums = ws + p.off_gsums;
+    const uint32_t tiles_ps = (p.nb + SCAN_TILE - 1) / SCAN_TILE;
+    const size_t slot_stride = ((size_t)p.segs_ps + p.nb) * Pt::BYTES;       // per physical set
 
-    StageTimer tm(timings != nullptr, stream);
+    StageTimer tm(timings != nullptr && p.chunks == 1, stream);
+    cudaEvent_t fed = nullptr;
     cudaError_t err = cudaSuccess;
     do {
-        if ((err = cudaMemsetAsync(counts, 0, (size_t)p.sets * p.nb * 4 + 4, stream)) != cudaSuccess) break;
-        tm.mark();
-        const uint32_t sblocks = std::min<uint32_t>((n + 255) / 256, 148 * 8);
-        if (p.folded) k_digits<C, true><<<sblocks, 256, 0, stream>>>((const uint32_t *)scalars, n, p.c, p.windows, p.nb, digits, counts);
-        else k_digits<C, false><<<sblocks, 256, 0, stream>>>((const uint32_t *)scalars, n, p.c, p.windows, p.nb, digits, counts);
-        tm.mark();
-        {
-            const uint32_t tiles_ps = (p.nb + SCAN_TILE - 1) / SCAN_TILE;
-            k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, stream>>>(counts, p.nb, tiles_ps, tile_sums);
-            k_scan_tops<<<p.sets, 1024, 0, stream>>>(tile_sums, tiles_ps, p.nb, offsets);
-            k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, stream>>>(counts, tile_sums, p.nb, tiles_ps, p.seg_len, offsets, cursor, big_count, big_list);
+        if ((err = cudaMemsetAsync(counts, 0, (phys * p.nb + p.chunks) * 4, stream)) != cudaSuccess) break;
+        if (feed) {
+            if ((err = cudaEventCreateWithFlags(&fed, cudaEventDisableTiming)) != cudaSuccess) break;
+            // the staging buffer was allocated in stream order on `stream`: the copy stream may only touch it from here on
+            if ((err = cudaEventRecord(fed, stream)) != cudaSuccess) break;
+            if ((err = cudaStreamWaitEvent(feed->copy_stream, fed, 0)) != cudaSuccess) break;
         }
-        tm.mark();
-        if (p.folded) {
-            uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
-            k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, stream>>>((const uint32_t *)digits, p.stride, log2_span, cursor, sorted);
-        } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, stream>>>(digits, n, p.nb, cursor, sorted);
-        tm.mark();
-        {
-            const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
-            const uint32_t blocks = (uint32_t)((threads + ACC_THREADS - 1) / ACC_THREADS);
-            k_accumulate<C><<<blocks, ACC_THREADS, 0, stream>>>((const uint8_t *)points, sorted, offsets, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots);
+        for (uint32_t q = 0; q < p.chunks && err == cudaSuccess; q++) {
+            const uint32_t point0 = q * p.chunk_n, nq = std::min<uint32_t>(p.chunk_n, n - point0);
+            const size_t set0 = (size_t)q * p.sets;                           // first physical set of this chunk
+            const uint32_t *sc = (const uint32_t *)scalars + (size_t)point0 * 8;
+            if (feed) {
+                if ((err = cudaMemcpyAsync((uint8_t *)feed->dev_scalars + (size_t)point0 * 32, (const uint8_t *)feed->host_scalars + (size_t)point0 * 32,
+                                           (size_t)nq * 32, cudaMemcpyHostToDevice, feed->copy_stream)) != cudaSuccess) break;
+                if ((err = cudaEventRecord(fed, feed->copy_stream)) != cudaSuccess) break;
+                if ((err = cudaStreamWaitEvent(stream, fed, 0)) != cudaSuccess) break;
+            }
+            uint32_t *counts_q = counts + set0 * p.nb, *offsets_q = offsets + set0 * (p.nb + 1), *cursor_q = cursor + set0 * p.nb;
+            uint32_t *big_count_q = big_counts + q, *big_list_q = big_list + set0 * p.nb, *tiles_q = tile_sums + set0 * tiles_ps;
+            uint8_t *codes_q = digits + (size_t)q * p.stride * 4;            // folded: 32-bit codes of this chunk (chunks == 1 otherwise)
+            uint32_t *sorted_q = sorted + set0 * p.stride;
+            uint8_t *slots_q = slots + set0 * slot_stride;
+            tm.mark();
+            const uint32_t sblocks = std::min<uint32_t>((nq + 255) / 256, 148 * 8);
+            if (p.folded) k_digits<C, true><<<sblocks, 256, 0, stream>>>(sc, nq, p.c, p.windows, p.nb, codes_q, counts_q);
+            else k_digits<C, false><<<sblocks, 256, 0, stream>>>(sc, nq, p.c, p.windows, p.nb, codes_q, counts_q);
+            tm.mark();
+            k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, stream>>>(counts_q, p.nb, tiles_ps, tiles_q);
+            k_scan_tops<<<p.sets, 1024, 0, stream>>>(tiles_q, tiles_ps, p.nb, offsets_q);
+            k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, stream>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q, big_count_q, big_list_q);
+            tm.mark();
+            if (p.folded) {
+                uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
+                k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, stream>>>((const uint32_t *)codes_q, nq, p.windows, n, point0, log2_span, cursor_q, sorted_q);
+            } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, stream>>>((const uint16_t *)codes_q, nq, p.nb, cursor_q, sorted_q);
+            tm.mark();
+            {
+                const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
+                const uint32_t blocks = (uint32_t)((threads + ACC_THREADS - 1) / ACC_THREADS);
+                k_accumulate<C><<<blocks, ACC_THREADS, 0, stream>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+            }
+            k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, stream>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
+            tm.mark();
+            err = cudaGetLastError();
         }
-        k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, stream>>>(slots, offsets, big_count, big_list, p.nb, p.seg_len, p.segs_ps);
-        tm.mark();
+        if (err != cudaSuccess) break;
         uint32_t log2m = 0; while ((1u << log2m) < p.chunk) log2m++;
         {
             const uint32_t threads = p.sets * p.chunks_ps;
             k_bucket_reduce<C><<<(threads + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, stream>>>(slots, offsets, p.nb, p.seg_len, p.segs_ps,
-                                                                                                   p.sets, p.chunk, p.chunks_ps, chunks);
+                                                                                                   p.sets, p.chunks, p.chunk, p.chunks_ps, chunks);
         }
         tm.mark();
         const uint32_t cpg = p.chunks_ps / p.groups;
@@ -677,6 +715,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         tm.mark();
         err = cudaGetLastError();
     } while (0);
+    if (fed) cudaEventDestroy(fed);
     cudaError_t ferr = cudaFreeAsync(ws, stream);
     if (err == cudaSuccess) err = ferr;
     if (err != cudaSuccess) {
@@ -685,10 +724,11 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
     }
     if (timings) {
         PB_CUDA(cudaStreamSynchronize(stream));
-        timings->digits = tm.ms(0); timings->scan = tm.ms(1); timings->scatter = tm.ms(2); timings->accumulate = tm.ms(3);
-        timings->bucket_reduce = tm.ms(4); timings->window_reduce = tm.ms(5); timings->final = tm.ms(6);
+        if (tm.on) {
+            timings->digits = tm.ms(0); timings->scan = tm.ms(1); timings->scatter = tm.ms(2); timings->accumulate = tm.ms(3);
+            timings->bucket_reduce = tm.ms(4); timings->window_reduce = tm.ms(5); timings->final = tm.ms(6);
+        }
     }
-    (void)sizeof(Pt);
     return cudaSuccess;
 }
 

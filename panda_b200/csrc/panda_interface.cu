@@ -123,6 +123,15 @@ static panda_error msm_execute_host(pb::CurveId curve, const panda_msm_configura
     return perr(e != cudaSuccess ? e : f);
 }
 
+static panda_error msm_execute_host_scalars(pb::CurveId curve, const panda_msm_configuration &cfg, size_t n) {
+    if (!cfg.results || (n && (!cfg.bases || !cfg.scalars))) return perr(cudaErrorInvalidValue);
+    if (n > (size_t)1 << 30) return perr(cudaErrorInvalidValue);
+    pb::CoordType coord = cfg.msm_result_coordinate_type == PROJECTIVE ? pb::COORD_PROJECTIVE : pb::COORD_JACOBIAN;
+    return perr(pb::msm_run_streamed(curve, cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, coord, cu(cfg.mem_pool), cu(cfg.stream)));
+}
+panda_error panda_msm_execute_bn254_host_scalars(const panda_msm_configuration cfg, size_t n) { return msm_execute_host_scalars(pb::CURVE_BN254, cfg, n); }
+panda_error panda_msm_execute_bls12_377_host_scalars(const panda_msm_configuration cfg, size_t n) { return msm_execute_host_scalars(pb::CURVE_BLS12_377, cfg, n); }
+
 panda_error panda_msm_setup_bn254(void) { return panda_success; }          // nothing to prepare: msm_cuda.cuh:786-795 is empty too
 panda_error panda_msm_setup_bls12_377(void) { return panda_success; }
 panda_error panda_msm_tear_down(void) { return perr(pb::msm_release_tables()); }   // idempotent (wrapper.rs:297-312 calls it once per base set); drops cached tables
@@ -226,6 +235,12 @@ panda_error panda_debug_msm_timed(int curve, const panda_msm_configuration cfg, 
     }
     if (info) { info[0] = (unsigned)t.folded; info[1] = t.c; info[2] = t.windows; }
     return perr(e);
+}
+
+panda_error panda_debug_msm_streamed(int curve, const panda_msm_configuration cfg, size_t n, int table_mode, unsigned chunks) {
+    pb::CoordType coord = cfg.msm_result_coordinate_type == PROJECTIVE ? pb::COORD_PROJECTIVE : pb::COORD_JACOBIAN;
+    return perr(pb::msm_run_streamed(curve == 1 ? pb::CURVE_BLS12_377 : pb::CURVE_BN254, cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, coord,
+                                     cu(cfg.mem_pool), cu(cfg.stream), table_mode, chunks));
 }
 
 }  // extern "C"

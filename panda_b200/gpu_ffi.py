@@ -244,6 +244,8 @@ SIGNATURES: dict[str, list] = {
     "panda_msm_execute_bls12_377": [MSMConfiguration],
     "panda_msm_execute_bn254_n": [MSMConfiguration, SizeT],
     "panda_msm_execute_bls12_377_n": [MSMConfiguration, SizeT],
+    "panda_msm_execute_bn254_host_scalars": [MSMConfiguration, SizeT],
+    "panda_msm_execute_bls12_377_host_scalars": [MSMConfiguration, SizeT],
     "panda_msm_combine_bn254": [_vp, _uint, _vp, _int, PandaStream],
     "panda_msm_combine_bls12_377": [_vp, _uint, _vp, _int, PandaStream],
     "panda_intt_execute_bn254_v1": [NttconfigurationV1],
@@ -254,6 +256,7 @@ SIGNATURES: dict[str, list] = {
     "panda_debug_curve_op": [_int, _int, _vp, _vp, _vp, SizeT, PandaStream],
     "panda_debug_msm_plan": [_int, SizeT, _int, _uint, _uint, C.POINTER(MsmPlanInfo)],
     "panda_debug_msm_timed": [_int, MSMConfiguration, SizeT, _uint, _uint, _int, C.POINTER(C.c_float), C.POINTER(_uint)],
+    "panda_debug_msm_streamed": [_int, MSMConfiguration, SizeT, _int, _uint],
     "panda_debug_int_peak": [_int, _uint, C.POINTER(C.c_float), C.POINTER(C.c_ulonglong)],
 }
 

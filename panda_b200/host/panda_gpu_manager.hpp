@@ -244,7 +244,7 @@ namespace detail {
 
 // steps 3-7 of unit.rs:31-100, shared by the four device MSM variants
 inline std::vector<uint8_t> msm_execute_and_fetch(const PandaGpuManager &gm, void *d_scalars, void *d_bases, size_t scalars_len,
-                                                  bool free_scalars, bool free_bases) {
+                                                  bool free_scalars, bool free_bases, bool scalars_on_host = false) {
     const uint32_t log_scalars_count = log_2(scalars_len / FIELD_ELEMENT_LEN);
     const size_t result_buf_len = FIELD_ELEMENT_LEN * 3;
     void *d_result = nullptr;
@@ -257,7 +257,8 @@ inline std::vector<uint8_t> msm_execute_and_fetch(const PandaGpuManager &gm, voi
     cfg.results = d_result;
     cfg.log_scalars_count = log_scalars_count;
     cfg.msm_result_coordinate_type = static_cast<panda_msm_result_coordinate_type>(gm.get_msm_result_coordinate_type());
-    check(panda_msm_execute_bn254(cfg), PandaGpuError::SchedulingErr);
+    if (scalars_on_host) check(panda_msm_execute_bn254_host_scalars(cfg, (size_t)1 << log_scalars_count), PandaGpuError::SchedulingErr);
+    else check(panda_msm_execute_bn254(cfg), PandaGpuError::SchedulingErr);
     std::vector<uint8_t> out(result_buf_len);
     void *h = nullptr;
     check(panda_malloc_host(&h, result_buf_len), PandaGpuError::CreateContextError);
@@ -285,9 +286,9 @@ inline std::vector<uint8_t> panda_msm_bn254_gpu(const PandaGpuManager &gm, const
 inline std::vector<uint8_t> panda_msm_bn254_gpu_with_cached_bases(const PandaGpuManager &gm, const ByteSlice &scalars, size_t bases_index) {
     void *d_bases = gm.get_params_bases_ptr_mut(bases_index);
     if (!d_bases) throw PandaGpuException(PandaGpuError::BasesIndexErr);
-    void *d_scalars = memory_alloc_and_copy(gm, scalars, gm.get_h2d_stream());
-    gm.wait_h2d();
-    return detail::msm_execute_and_fetch(gm, d_scalars, d_bases, scalars.len, true, false);
+    // fix: unit.rs:113-131 uploads every scalar before the MSM starts; panda_msm_execute_bn254_host_scalars streams them in chunks
+    // on the library's copy stream and overlaps the upload with the sort / accumulation of the chunks already on the device
+    return detail::msm_execute_and_fetch(gm, const_cast<uint8_t *>(scalars.data), d_bases, scalars.len, false, false, true);
 }
 // unit.rs:190-275
 inline std::vector<uint8_t> panda_msm_bn254_gpu_with_cached_scalars(const PandaGpuManager &gm, size_t scalars_index, const ByteSlice &bases) {

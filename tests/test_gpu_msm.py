@@ -278,3 +278,60 @@ def test_table_cache_follows_the_bases_not_the_pointer(oracle, dev):
     assert ffi.lib.panda_msm_tear_down() == 0                        # drops the tables; idempotent
     assert ffi.lib.panda_msm_tear_down() == 0
     assert ffi.lib.panda_debug_msm_timed(0, cfg, n, 0, 0, 1, None, info) == 0 and info[0] == 0
+
+
+@pytest.mark.parametrize("n,chunks,mode", [(1 << 13, 0, 0), (1 << 13, 1, 2), (1 << 14, 2, 2), (20000, 3, 2), (1 << 15, 4, 2), (40001, 7, 2),
+                                           (1 << 16, 0, 2)])
+def test_host_scalars_streamed(oracle, dev, n, chunks, mode):
+    """panda_msm_execute_bn254_host_scalars: scalars in HOST memory (pageable and pinned), uploaded chunk by chunk while earlier
+    chunks are sorted and accumulated; the chunks share the bucket reduction.  Same point as the device-resident path."""
+    ffi, gu = dev
+    bases = oracle.gen_bases(0, 300 + chunks, n)
+    scal = oracle.gen_scalars(1, 301 + chunks, n)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, 300 + chunks, scal, n))
+    d_b, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf(96)
+    stream, pool = ffi.PandaStream.new(), ffi.PandaMemPool.new(0)
+    pinned = C.c_void_p()
+    assert ffi.lib.panda_malloc_host(C.byref(pinned), scal.size) == 0
+    scal_pinned = np.ctypeslib.as_array((C.c_uint8 * scal.size).from_address(pinned.value))
+    scal_pinned[:] = scal
+    try:
+        for host in (scal, scal_pinned):
+            for coord in (0, 1):
+                cfg = ffi.MSMConfiguration(pool, stream, d_b.ptr, host.ctypes.data, d_r.ptr, 0, coord)
+                assert ffi.lib.panda_debug_msm_streamed(0, cfg, n, mode, chunks) == 0
+                stream.sync()
+                assert (affine(oracle, 0, d_r.to_numpy(), coord) == exp).all(), (coord,)
+        assert (scal_pinned == scal).all()
+        cfg = ffi.MSMConfiguration(pool, stream, d_b.ptr, scal_pinned.ctypes.data, d_r.ptr, 0, 0)
+        for _ in range(3):      # the product entry point: table after the second sighting of the bases, automatic chunking
+            assert ffi.lib.panda_msm_execute_bn254_host_scalars(cfg, n) == 0
+            stream.sync()
+            assert (oracle.jac_to_affine(0, d_r.to_numpy()) == exp).all()
+    finally:
+        ffi.lib.panda_free_host(pinned)
+        assert ffi.lib.panda_msm_tear_down() == 0
+
+
+def test_host_scalars_streamed_skew_and_bls(oracle, dev):
+    """chunked path with oversized buckets in every chunk (all scalars equal) and on the second curve"""
+    ffi, gu = dev
+    n = 1 << 14
+    bases = oracle.gen_bases(0, 310, n)
+    scal = np.tile(oracle.gen_scalars(1, 311, 1), n)
+    exp = oracle.jac_to_affine(0, oracle.msm(0, bases, scal, n, c=10))
+    d_b, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf(96)
+    s = ffi.PandaStream.new()
+    cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, scal.ctypes.data, d_r.ptr, 0, 0)
+    assert ffi.lib.panda_debug_msm_streamed(0, cfg, n, 2, 4) == 0
+    s.sync()
+    assert (oracle.jac_to_affine(0, d_r.to_numpy()) == exp).all()
+    bases = oracle.gen_bases(1, 312, n)
+    scal = oracle.gen_scalars(3, 313, n)
+    exp = oracle.jac_to_affine(1, oracle.expected_progression_msm(1, 312, scal, n))
+    d_b, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf(144)
+    cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, scal.ctypes.data, d_r.ptr, 0, 0)
+    assert ffi.lib.panda_debug_msm_streamed(1, cfg, n, 2, 3) == 0
+    s.sync()
+    assert (oracle.jac_to_affine(1, d_r.to_numpy()) == exp).all()
+    assert ffi.lib.panda_msm_tear_down() == 0
