@@ -143,6 +143,15 @@ panda_error panda_msm_execute_bls12_377(const panda_msm_configuration exec_cfg);
 panda_error panda_msm_execute_bn254_n(const panda_msm_configuration exec_cfg, size_t n);
 panda_error panda_msm_execute_bls12_377_n(const panda_msm_configuration exec_cfg, size_t n);
 
+/* init_msm for cached bases (wrapper.rs:122-152 keeps the device pointer and reuses it across calls): announces that the n
+ * affine points at d_bases stay unchanged until panda_msm_unregister_bases / panda_msm_tear_down.  The library builds its
+ * table of 2^(c*j) * P multiples right away (asynchronous on `stream`; W * n * 64 bytes of HBM) and every later MSM on d_bases
+ * -- or on a prefix of it -- runs the one-bucket-set pipeline without the content fingerprint (and its host synchronisation)
+ * that unannounced pointers get.  Re-registering a pointer replaces the old entry. */
+panda_error panda_msm_register_bases_bn254(const void *d_bases, size_t n, panda_stream stream);
+panda_error panda_msm_register_bases_bls12_377(const void *d_bases, size_t n, panda_stream stream);
+panda_error panda_msm_unregister_bases(const void *d_bases);
+
 /* MSM whose scalars are still in HOST memory (cfg.scalars: host pointer, pinned for full overlap; cfg.bases / cfg.results:
  * device pointers as in panda_msm_execute_bn254).  Replaces the copy-then-execute sequence of unit.rs:103-188
  * (panda_msm_bn254_gpu_with_cached_bases): the library uploads the scalars in chunks on its own copy stream and sorts /

@@ -46,6 +46,7 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
     MsmPlan p{};
     p.n = n;
+    p.table_n = n;
     p.folded = folded ? 1 : 0;
     const uint32_t c_lo = 8, c_hi = folded ? 23 : 16;          // windowed digit codes are 16 bit
     uint32_t best_c = 0;
@@ -127,6 +128,7 @@ struct TableEntry {
     uint32_t n;
     unsigned long long fingerprint;
     unsigned sightings;
+    bool registered;        // announced by msm_register_bases: immutable until unregistered, no fingerprint needed
     void *table;            // nullptr until built
     uint32_t c, windows;
     size_t bytes;
@@ -144,13 +146,14 @@ static void drop_table(TableEntry &e) {
     if (e.ready) { cudaEventDestroy(e.ready); e.ready = nullptr; }
 }
 
-cudaError_t msm_release_tables() {
+cudaError_t msm_release_tables() {     // the current device's tables (panda_msm_tear_down: one MSM unit per device)
     std::lock_guard<std::mutex> lock(g_table_mutex);
     int cur = 0;
     cudaGetDevice(&cur);
-    for (auto &e : g_tables) { cudaSetDevice(e.device); drop_table(e); }
-    g_tables.clear();
-    cudaSetDevice(cur);
+    for (size_t i = 0; i < g_tables.size();) {
+        if (g_tables[i].device == cur) { drop_table(g_tables[i]); g_tables.erase(g_tables.begin() + i); }
+        else i++;
+    }
     return cudaSuccess;
 }
 
@@ -175,14 +178,88 @@ static cudaError_t run_pipeline(CurveId curve, const MsmPlan &p, const void *poi
 
 // Looks `bases` up in the table cache (building the table when the mode asks for it).  On return *table is the table to use
 // (with its window width in *tc and `stream` already waiting for the build) or nullptr: stay on the windowed path.
+static cudaError_t build_table_locked(TableEntry *hit, CurveId curve, const void *bases, uint32_t n, uint32_t c_override, cudaStream_t stream) {
+    size_t free_b = 0, total_b = 0;
+    PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = free_b > ((size_t)6 << 30) ? (free_b - ((size_t)4 << 30)) / 2 : 0;   // leave room for workspaces
+    MsmPlan fp_plan = msm_make_plan(curve, n, true, c_override > 16 ? c_override : 0, 0, budget);
+    if (!fp_plan.c) return cudaSuccess;                // no table fits: stay on the windowed path
+    void *tab = nullptr;
+    if (cudaMalloc(&tab, fp_plan.table_bytes) != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
+    cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, tab, stream)
+                                              : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, tab, stream);
+    cudaEvent_t ev = nullptr;
+    if (be == cudaSuccess) be = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (be == cudaSuccess) be = cudaEventRecord(ev, stream);
+    if (be != cudaSuccess) { cudaFree(tab); if (ev) cudaEventDestroy(ev); return be; }
+    hit->table = tab; hit->c = fp_plan.c; hit->windows = fp_plan.windows; hit->bytes = fp_plan.table_bytes; hit->ready = ev;
+    return cudaSuccess;
+}
+
+static void evict_if_full_locked() {
+    if (g_tables.size() < MAX_TABLES) return;
+    size_t victim = g_tables.size();                   // least recently used entry that is not registered
+    for (size_t i = 0; i < g_tables.size(); i++)
+        if (!g_tables[i].registered && (victim == g_tables.size() || g_tables[i].last_use < g_tables[victim].last_use)) victim = i;
+    if (victim == g_tables.size()) return;             // only registered sets: let the vector grow (the caller owns their lifetime)
+    int cur = 0; cudaGetDevice(&cur); cudaSetDevice(g_tables[victim].device);
+    drop_table(g_tables[victim]);
+    cudaSetDevice(cur);
+    g_tables.erase(g_tables.begin() + victim);
+}
+
+cudaError_t msm_register_bases(CurveId curve, const void *bases, uint32_t n, cudaStream_t stream) {
+    if (!bases || n == 0) return cudaErrorInvalidValue;
+    int dev = 0;
+    PB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    TableEntry *hit = nullptr;
+    for (auto &t : g_tables) if (t.device == dev && t.bases == bases) { hit = &t; break; }
+    if (hit) { drop_table(*hit); *hit = TableEntry{dev, curve, bases, n, 0, 0, true, nullptr, 0, 0, 0, nullptr, ++g_use_clock}; }
+    else {
+        evict_if_full_locked();
+        g_tables.push_back(TableEntry{dev, curve, bases, n, 0, 0, true, nullptr, 0, 0, 0, nullptr, ++g_use_clock});
+        hit = &g_tables.back();
+    }
+    if (default_table_mode() == MSM_TABLE_OFF || n < 1024) return cudaSuccess;
+    return build_table_locked(hit, curve, bases, n, 0, stream);
+}
+
+cudaError_t msm_unregister_bases(const void *bases) {
+    int dev = 0;
+    PB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    for (size_t i = 0; i < g_tables.size(); i++)
+        if (g_tables[i].device == dev && g_tables[i].bases == bases) {
+            drop_table(g_tables[i]);
+            g_tables.erase(g_tables.begin() + i);
+            return cudaSuccess;
+        }
+    return cudaSuccess;                                // unknown pointer: nothing to do (idempotent)
+}
+
 static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, cudaStream_t stream, int table_mode, uint32_t c_override,
-                                 const void **table, uint32_t *tc) {
+                                 const void **table, uint32_t *tc, uint32_t *table_n) {
     *table = nullptr;
+    *table_n = n;
     const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
     if (table_mode == MSM_TABLE_DEFAULT) table_mode = default_table_mode();
     if (table_mode == MSM_TABLE_OFF || n < 1024) return cudaSuccess;
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
+    {   // registered base sets (init_msm): no fingerprint, no host synchronisation; a prefix of the set may be used
+        std::unique_lock<std::mutex> lock(g_table_mutex);
+        for (auto &t : g_tables)
+            if (t.registered && t.device == dev && t.curve == curve && t.bases == bases && n <= t.n) {
+                t.last_use = ++g_use_clock;
+                if (!t.table) return cudaSuccess;
+                *table = t.table; *tc = t.c; *table_n = t.n;
+                cudaEvent_t ready = t.ready;
+                lock.unlock();
+                PB_CUDA(cudaStreamWaitEvent(stream, ready, 0));
+                return cudaSuccess;
+            }
+    }
     // 1. content fingerprint of the bases (one pass over n * 64 bytes at HBM speed, 8 bytes read back)
     unsigned long long *d_fp = nullptr, fp = 0;
     PB_CUDA(cudaMallocAsync((void **)&d_fp, 8, stream));
@@ -202,40 +279,14 @@ static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, c
         hit->fingerprint = fp; hit->sightings = 0;
     }
     if (!hit) {
-        if (g_tables.size() >= MAX_TABLES) {  // evict the least recently used entry
-            size_t victim = 0;
-            for (size_t i = 1; i < g_tables.size(); i++) if (g_tables[i].last_use < g_tables[victim].last_use) victim = i;
-            int cur = 0; cudaGetDevice(&cur); cudaSetDevice(g_tables[victim].device);
-            drop_table(g_tables[victim]);
-            cudaSetDevice(cur);
-            g_tables.erase(g_tables.begin() + victim);
-        }
-        g_tables.push_back(TableEntry{dev, curve, bases, n, fp, 0, nullptr, 0, 0, 0, nullptr, 0});
+        evict_if_full_locked();
+        g_tables.push_back(TableEntry{dev, curve, bases, n, fp, 0, false, nullptr, 0, 0, 0, nullptr, 0});
         hit = &g_tables.back();
     }
     hit->sightings++;
     hit->last_use = ++g_use_clock;
     const bool want = table_mode == MSM_TABLE_EAGER || hit->sightings >= 2;
-    if (!hit->table && want) {
-        size_t free_b = 0, total_b = 0;
-        PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const size_t budget = free_b > ((size_t)6 << 30) ? (free_b - ((size_t)4 << 30)) / 2 : 0;   // leave room for workspaces
-        MsmPlan fp_plan = msm_make_plan(curve, n, true, c_override > 16 ? c_override : 0, 0, budget);
-        if (fp_plan.c) {
-            void *tab = nullptr;
-            if (cudaMalloc(&tab, fp_plan.table_bytes) == cudaSuccess) {
-                cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, tab, stream)
-                                                          : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, tab, stream);
-                cudaEvent_t ev = nullptr;
-                if (be == cudaSuccess) be = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-                if (be == cudaSuccess) be = cudaEventRecord(ev, stream);
-                if (be != cudaSuccess) { cudaFree(tab); if (ev) cudaEventDestroy(ev); return be; }
-                hit->table = tab; hit->c = fp_plan.c; hit->windows = fp_plan.windows; hit->bytes = fp_plan.table_bytes; hit->ready = ev;
-            } else {
-                cudaGetLastError();            // out of memory: stay on the windowed path
-            }
-        }
-    }
+    if (!hit->table && want) PB_CUDA(build_table_locked(hit, curve, bases, n, c_override, stream));
     if (hit->table) {
         *table = hit->table;
         *tc = hit->c;
@@ -255,9 +306,11 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
     }
     const void *table = nullptr;
     uint32_t tc = 0;
-    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, c_override, &table, &tc));
+    uint32_t table_n = n;
+    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, c_override, &table, &tc, &table_n));
     if (table) {
         MsmPlan p = msm_make_plan(curve, n, true, tc, seg_override);
+        p.table_n = table_n;
         return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings);
     }
     MsmPlan p = msm_make_plan(curve, n, false, c_override <= 16 ? c_override : 0, seg_override);
@@ -286,7 +339,8 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
     }
     const void *table = nullptr;
     uint32_t tc = 0;
-    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, 0, &table, &tc));
+    uint32_t table_n = n;
+    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, 0, &table, &tc, &table_n));
     uint8_t *d_scal = nullptr;
     if (pool) PB_CUDA(cudaMallocFromPoolAsync((void **)&d_scal, (size_t)n * 32, pool, stream));
     else PB_CUDA(cudaMallocAsync((void **)&d_scal, (size_t)n * 32, stream));
@@ -295,6 +349,7 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
         static const uint32_t forced = [] { const char *v = getenv("PANDA_MSM_CHUNKS"); return v ? (uint32_t)atoi(v) : 0u; }();
         uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 19) ? 2 : 1);
         MsmPlan p = msm_make_plan(curve, n, true, tc, 0, ~(size_t)0, chunks);
+        p.table_n = table_n;
         MsmFeed feed{host_scalars, d_scal, nullptr};
         e = copy_stream_for_current_device(&feed.copy_stream);
         if (e == cudaSuccess) e = run_pipeline(curve, p, table, d_scal, result, coord, pool, stream, nullptr, &feed);

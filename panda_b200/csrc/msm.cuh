@@ -16,6 +16,7 @@ enum CoordType { COORD_JACOBIAN = 0, COORD_PROJECTIVE = 1 };   // curve.cuh:23-2
 
 struct MsmPlan {
     uint32_t n;            // points
+    uint32_t table_n;      // folded: row length of the table (>= n: an MSM may use a prefix of a registered base set)
     uint32_t c;            // window width in bits (signed digits)
     uint32_t windows;      // W digit windows per scalar
     uint32_t nb;           // buckets per bucket set = 2^(c-1)
@@ -71,7 +72,12 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
 // result = sum of `count` Jacobian partials (the per-GPU results of a sharded MSM), then coordinate conversion.
 cudaError_t msm_combine(CurveId curve, const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream);
 
-// drops every cached table (all devices); synchronises
+// init_msm for a base set that stays put until it is unregistered: builds its table right away (asynchronous on `stream`) and
+// lets every later MSM on `bases` (or a prefix of it) skip the content fingerprint and its host synchronisation.
+cudaError_t msm_register_bases(CurveId curve, const void *bases, uint32_t n, cudaStream_t stream);
+cudaError_t msm_unregister_bases(const void *bases);
+
+// drops every table of the current device (registered or not); synchronises
 cudaError_t msm_release_tables();
 
 }  // namespace pb

@@ -680,7 +680,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             tm.mark();
             if (p.folded) {
                 uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
-                k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, stream>>>((const uint32_t *)codes_q, nq, p.windows, n, point0, log2_span, cursor_q, sorted_q);
+                k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, stream>>>((const uint32_t *)codes_q, nq, p.windows, p.table_n, point0, log2_span, cursor_q, sorted_q);
             } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, stream>>>((const uint16_t *)codes_q, nq, p.nb, cursor_q, sorted_q);
             tm.mark();
             {

@@ -1,4 +1,5 @@
-// ntt.cu -- multi-pass radix-2^r NTT (r <= 8 per pass) with shared-memory butterflies and precomputed twiddles.
+// ntt.cu -- multi-pass radix-2^r NTT (r <= 8 per pass): register-resident radix-8 butterfly units, shared memory only
+// for the exchanges between them, precomputed twiddles.
 //
 // n = 2^k is split into P = ceil(k/8) digits N_1..N_P (balanced).  With i = (i_1,..,i_P) (i_1 most significant)
 // and j = j_1 + N_1 j_2 + N_1 N_2 j_3 + ..:
@@ -8,9 +9,16 @@
 //   pass P     : N_P-point DFTs over contiguous runs (C runs per CTA, adjacent in j_1), written to the digit-
 //                reversed positions, which are C*32-byte runs again.
 // Each pass reads one buffer and writes the other, so the result lands in d_dst iff P is odd (fft.cu:193-211).
+//
+// Inside a pass the r radix-2 DIF stages are done in groups of up to three: a thread holds the 8 elements of a
+// radix-8 unit in registers (12 butterflies = 12 Montgomery products), the first group loads straight from global
+// memory and the last one stores straight to it, so an 8-stage pass crosses shared memory twice instead of 8 times.
+// IMAD-bound: (n/2) log2 n butterfly products + 1 (direct table) or 2 (two-level table) products per element and
+// pass boundary; HBM traffic 64 B per element and pass.
 #include "ntt.cuh"
 #include "field.cuh"
 
+#include <algorithm>
 #include <array>
 #include <cstdio>
 #include <cstring>
@@ -22,6 +30,7 @@ namespace pb {
 static constexpr int NTT_THREADS = 256;
 static constexpr unsigned NTT_MAX_RADIX_LOG = 8;      // fft.cu:10 MAX_LOG2_RADIX
 static constexpr unsigned NTT_MAX_PARTS = 16;         // destination buffers of the exchange step (GPUs of one box)
+static constexpr unsigned NTT_DIRECT_LOG = 20;        // pass boundaries with at most 2^20 distinct twiddles get a direct table
 
 struct NttShape {
     unsigned log_n, passes;
@@ -37,11 +46,19 @@ static NttShape ntt_shape(unsigned log_n) {
 }
 
 // ---- twiddle tables --------------------------------------------------------------------------------
-// words: [omega 8][scale 8][t_lo 8<<lo_bits][t_hi 8<<(k-lo_bits)][stage table of r_max][stage table of r_min]
+// One device array per (device, log n, omega, direction):
+//   [omega][scale = 2^-log_n][t_lo: omega^e, e < 2^lo_bits][t_hi: omega^(e << lo_bits)]      two-level table, any exponent < n
+//   [stage table of r_a: omega^(e << (k - r_a)), e < 2^(r_a-1)][stage table of r_b]           butterfly twiddles of a pass
+//   [direct table of boundary p: omega^(e << log_O_p), e < n >> log_O_p]                      where that is <= 2^20 entries
+
+struct NttSegment { size_t off; uint32_t count; unsigned shift; };
 
 struct NttTableLayout {
     unsigned lo_bits, hi_bits, r_a, r_b;
     size_t off_omega, off_scale, off_lo, off_hi, off_sa, off_sb, words;
+    size_t off_direct[4];           // per pass boundary p (twiddle applied at the end of pass p); 0 = none
+    unsigned nseg;
+    NttSegment seg[8];
 };
 
 static NttTableLayout ntt_table_layout(const NttShape &s) {
@@ -51,12 +68,24 @@ static NttTableLayout ntt_table_layout(const NttShape &s) {
     t.r_a = s.passes ? s.r[0] : 0;
     t.r_b = s.passes ? s.r[s.passes - 1] : 0;
     size_t off = 0;
+    auto add = [&](uint32_t count, unsigned shift) {
+        const size_t at = off;
+        t.seg[t.nseg++] = NttSegment{at, count, shift};
+        off += (size_t)8 * count;
+        return at;
+    };
     t.off_omega = off; off += 8;
     t.off_scale = off; off += 8;
-    t.off_lo = off; off += (size_t)8 << t.lo_bits;
-    t.off_hi = off; off += (size_t)8 << t.hi_bits;
-    t.off_sa = off; off += t.r_a ? (size_t)8 << (t.r_a - 1) : 8;
-    t.off_sb = off; off += t.r_b ? (size_t)8 << (t.r_b - 1) : 8;
+    t.off_lo = add(1u << t.lo_bits, 0);
+    t.off_hi = add(1u << t.hi_bits, t.lo_bits);
+    t.off_sa = add(t.r_a ? 1u << (t.r_a - 1) : 1, t.r_a ? s.log_n - t.r_a : 0);
+    t.off_sb = add(t.r_b ? 1u << (t.r_b - 1) : 1, t.r_b ? s.log_n - t.r_b : 0);
+    unsigned log_O = 0;
+    for (unsigned p = 0; p + 1 < s.passes; p++) {
+        const unsigned size_log = s.log_n - log_O;
+        if (size_log <= NTT_DIRECT_LOG) t.off_direct[p] = add(1u << size_log, log_O);
+        log_O += s.r[p];
+    }
     t.words = off;
     return t;
 }
@@ -73,26 +102,20 @@ PB_DEV F fe_pow_u32(const F &base, uint32_t e) {
     return acc;
 }
 
+struct NttTableArgs { unsigned log_n, nseg; NttSegment seg[8]; size_t off_scale; int inverse; };
+
 template <class P>
-__global__ void k_ntt_tables(uint32_t *tab, unsigned log_n, unsigned lo_bits, unsigned hi_bits, unsigned r_a, unsigned r_b,
-                             size_t off_lo, size_t off_hi, size_t off_sa, size_t off_sb, size_t off_scale, int inverse) {
+__global__ void k_ntt_tables(uint32_t *tab, const NttTableArgs a) {
     using F = Fe<P>;
-    const uint32_t n_lo = 1u << lo_bits, n_hi = 1u << hi_bits;
-    const uint32_t n_sa = r_a ? 1u << (r_a - 1) : 1, n_sb = r_b ? 1u << (r_b - 1) : 1;
-    const uint32_t total = n_lo + n_hi + n_sa + n_sb + 1;
-    const uint32_t nmask = log_n >= 32 ? 0xffffffffu : ((1u << log_n) - 1);
+    uint32_t total = 0;
+    for (unsigned s = 0; s < a.nseg; s++) total += a.seg[s].count;
+    const uint32_t nmask = a.log_n >= 32 ? 0xffffffffu : ((1u << a.log_n) - 1);
     const F omega = F::load_plain(tab);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        uint32_t e;
-        uint32_t *out;
-        if (i < n_lo) { e = i; out = tab + off_lo + (size_t)i * 8; }
-        else if (i < n_lo + n_hi) { uint32_t t = i - n_lo; e = t << lo_bits; out = tab + off_hi + (size_t)t * 8; }
-        else if (i < n_lo + n_hi + n_sa) { uint32_t t = i - n_lo - n_hi; e = t << (log_n - r_a); out = tab + off_sa + (size_t)t * 8; }
-        else if (i < n_lo + n_hi + n_sa + n_sb) { uint32_t t = i - n_lo - n_hi - n_sa; e = t << (log_n - r_b); out = tab + off_sb + (size_t)t * 8; }
-        else {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= total; i += gridDim.x * blockDim.x) {
+        if (i == total) {
             // scale = 2^-log_n (Montgomery): halve ONE log_n times
             F x = F::one().canon();
-            for (unsigned k = 0; k < log_n; k++) {
+            for (unsigned k = 0; k < a.log_n; k++) {
                 uint32_t odd = x.l[0] & 1, carry = 0;
                 if (odd) {   // x += p (may carry out of the top limb)
                     x.l[0] = ptx::add_cc(x.l[0], P::mod(0));
@@ -104,11 +127,15 @@ __global__ void k_ntt_tables(uint32_t *tab, unsigned log_n, unsigned lo_bits, un
                 for (int q = 0; q < F::N - 1; q++) x.l[q] = __funnelshift_r(x.l[q], x.l[q + 1], 1);
                 x.l[F::N - 1] = (x.l[F::N - 1] >> 1) | (carry << 31);
             }
-            x.store(tab + off_scale);
+            x.store(tab + a.off_scale);
             continue;
         }
-        if (inverse) e = (0u - e) & nmask;
-        fe_pow_u32(omega, e).canon().store(out);
+        uint32_t t = i;
+        unsigned s = 0;
+        while (t >= a.seg[s].count) { t -= a.seg[s].count; s++; }
+        uint32_t e = (t << a.seg[s].shift) & nmask;
+        if (a.inverse) e = (0u - e) & nmask;
+        fe_pow_u32(omega, e).canon().store(tab + a.seg[s].off + (size_t)t * 8);
     }
 }
 
@@ -128,29 +155,80 @@ PB_DEV void sm_store(uint32_t *sm, uint32_t LS, uint32_t idx, const F &x) {
     for (int l = 0; l < F::N; l++) sm[l * LS + idx] = x.l[l];
 }
 
-// in-place radix-2 DIF over the N = 2^r rows of an N x C tile; output row pos holds X[bitrev_r(pos)]
-template <class F>
-PB_DEV void tile_dft(uint32_t *sm, uint32_t LS, uint32_t CP, unsigned r, unsigned logC, const uint32_t *__restrict__ stage_tw) {
-    const uint32_t C = 1u << logC;
-    const uint32_t bflies = (1u << (r - 1)) << logC;
-#pragma unroll 1
-    for (unsigned s = 0; s < r; s++) {
-        const uint32_t half = 1u << (r - 1 - s);
-#pragma unroll 1
-        for (uint32_t q = threadIdx.x; q < bflies; q += blockDim.x) {
-            const uint32_t col = q & (C - 1), bf = q >> logC;
-            const uint32_t j = bf & (half - 1), grp = bf >> (r - 1 - s);
-            const uint32_t i0 = ((grp << (r - s)) + j) * CP + col, i1 = i0 + half * CP;
-            F u = sm_load<F>(sm, LS, i0), v = sm_load<F>(sm, LS, i1);
-            F sum = u + v, diff = u - v;
-            if (s + 1 < r) {
-                F w = F::load(stage_tw + (size_t)(j << s) * F::N);
-                diff = diff * w;
-            }
-            sm_store(sm, LS, i0, sum);
-            sm_store(sm, LS, i1, diff);
+// DIF stages s .. s+G-1 of an N = 2^r point transform on the 2^G elements a thread holds:
+// x[k] is row hi * 2^(r-s) + k * 2^(r-G-s) + low.  Butterfly (u, v) -> (u + v, (u - v) * w^(j << stage)), j = lower row mod half.
+template <class F, int G>
+PB_DEV void radix_unit(F (&x)[8], unsigned s, unsigned r, uint32_t low, const uint32_t *__restrict__ stage_tw) {
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+        constexpr int size = 1 << G;
+        const int dist = size >> (t + 1);
+#pragma unroll
+        for (int k0 = 0; k0 < size; k0++) {
+            if (k0 & dist) continue;
+            const uint32_t j = ((uint32_t)(k0 & (dist - 1)) << (r - G - s)) + low;
+            const uint32_t e = j << (s + t);
+            const F u = x[k0], v = x[k0 + dist];
+            x[k0] = u + v;
+            F d = u - v;
+            if (e) d = d * F::load(stage_tw + (size_t)e * F::N);
+            x[k0 + dist] = d;
         }
-        __syncthreads();
+    }
+}
+
+// stage groups of a pass: ceil(r / 3) groups, as even as possible
+struct NttGroups { unsigned n, g[3]; };
+PB_DEV NttGroups ntt_groups(unsigned r) {
+    NttGroups q{};
+    q.n = (r + 2) / 3;
+    for (unsigned i = 0; i < q.n; i++) q.g[i] = r / q.n + (i < r % q.n ? 1 : 0);
+    return q;
+}
+
+// One group of stages over the whole N x C tile.  ld(row, col) / st(row, col, x) reach global memory for the first / last
+// group and shared memory otherwise (decided by the caller's functors).  row_fastest: consecutive threads take consecutive rows
+// (contiguous runs of the last pass), otherwise consecutive columns.
+template <class F, int G, class Ld, class St>
+PB_DEV void run_group(unsigned s, unsigned r, unsigned logC, bool row_fastest, const uint32_t *__restrict__ stage_tw, Ld &&ld, St &&st) {
+    const uint32_t units = (1u << (r - G)) << logC;
+    const unsigned lowbits = r - G - s;
+#pragma unroll 1
+    for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) {
+        uint32_t col, rest;
+        if (row_fastest) { rest = u & ((1u << (r - G)) - 1); col = u >> (r - G); }
+        else { col = u & ((1u << logC) - 1); rest = u >> logC; }
+        const uint32_t low = rest & ((1u << lowbits) - 1), hi = rest >> lowbits;
+        const uint32_t row0 = (hi << (r - s)) + low;
+        F x[8];
+#pragma unroll
+        for (int k = 0; k < (1 << G); k++) x[k] = ld(row0 + ((uint32_t)k << lowbits), col);
+        radix_unit<F, G>(x, s, r, low, stage_tw);
+#pragma unroll
+        for (int k = 0; k < (1 << G); k++) st(row0 + ((uint32_t)k << lowbits), col, x[k]);
+    }
+}
+
+// all r stages of the tile: gl/gs are the global load / store functors, shared memory carries the exchanges in between.
+// After the r DIF stages row `pos` holds X[bitrev_r(pos)]; gs receives (pos, col, value).
+template <class F, class GLd, class GSt>
+PB_DEV void tile_transform(uint32_t *sm, uint32_t LS, uint32_t CP, unsigned r, unsigned logC, bool first_row_fastest,
+                           const uint32_t *__restrict__ stage_tw, GLd &&gl, GSt &&gs) {
+    const NttGroups q = ntt_groups(r);
+    unsigned s = 0;
+#pragma unroll 1
+    for (unsigned gi = 0; gi < q.n; gi++) {
+        const bool first = gi == 0, last = gi + 1 == q.n;
+        auto ld = [&](uint32_t row, uint32_t col) -> F { return first ? gl(row, col) : sm_load<F>(sm, LS, row * CP + col); };
+        auto st = [&](uint32_t row, uint32_t col, const F &x) { if (last) gs(row, col, x); else sm_store(sm, LS, row * CP + col, x); };
+        const bool rf = first && !last && first_row_fastest;
+        switch (q.g[gi]) {
+            case 3: run_group<F, 3>(s, r, logC, rf, stage_tw, ld, st); break;
+            case 2: run_group<F, 2>(s, r, logC, rf, stage_tw, ld, st); break;
+            default: run_group<F, 1>(s, r, logC, rf, stage_tw, ld, st); break;
+        }
+        if (!last) __syncthreads();
+        s += q.g[gi];
     }
 }
 
@@ -158,43 +236,41 @@ struct NttPassArgs {
     unsigned log_n, r, log_M, log_O, logC, lo_bits;
     unsigned log_bpt;                 // last pass: log2(CTAs per transform); the CTA index above that is the batch row
     unsigned passes, rad[4];          // all radices (last pass: digit reversal)
-    const uint32_t *stage_tw, *t_lo, *t_hi, *scale;
+    const uint32_t *stage_tw, *t_lo, *t_hi, *t_direct, *scale;
 };
 
 // pass p < P
 template <class P>
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, NttPassArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const NttPassArgs a) {
     using F = Fe<P>;
     extern __shared__ uint32_t sm[];
     const uint32_t N = 1u << a.r, C = 1u << a.logC, CP = C > 1 ? C + 1 : 1, LS = N * CP;
     const uint32_t blocks_per_o = 1u << (a.log_M - a.logC);
-    const uint32_t o = blockIdx.x / blocks_per_o, ib = blockIdx.x % blocks_per_o;
+    const uint32_t o = blockIdx.x / blocks_per_o, ib = blockIdx.x % blocks_per_o;     // o also carries the batch row
     const uint32_t i0 = ib << a.logC;
     const size_t base = ((size_t)o << (a.r + a.log_M)) + i0;
-    for (uint32_t e = threadIdx.x; e < N * C; e += blockDim.x) {
-        const uint32_t row = e >> a.logC, col = e & (C - 1);
-        F x = F::load(src + (base + ((size_t)row << a.log_M) + col) * F::N);
-        sm_store(sm, LS, row * CP + col, x);
-    }
-    __syncthreads();
-    tile_dft<F>(sm, LS, CP, a.r, a.logC, a.stage_tw);
     const uint32_t lo_mask = (1u << a.lo_bits) - 1;
-    for (uint32_t e = threadIdx.x; e < N * C; e += blockDim.x) {
-        const uint32_t jp = e >> a.logC, col = e & (C - 1);
-        const uint32_t pos = __brev(jp) >> (32 - a.r);
-        F x = sm_load<F>(sm, LS, pos * CP + col);
-        const uint32_t ex = ((i0 + col) * jp) << a.log_O;       // < n
-        if (ex) {
-            F tw = F::load(a.t_hi + (size_t)(ex >> a.lo_bits) * F::N) * F::load(a.t_lo + (size_t)(ex & lo_mask) * F::N);
+    auto gl = [&](uint32_t row, uint32_t col) -> F { return F::load(src + (base + ((size_t)row << a.log_M) + col) * F::N); };
+    auto gs = [&](uint32_t pos, uint32_t col, F x) {
+        const uint32_t jp = __brev(pos) >> (32 - a.r);
+        const uint32_t prod = (i0 + col) * jp;                    // < n >> log_O
+        if (prod) {
+            F tw;
+            if (a.t_direct) tw = F::load(a.t_direct + (size_t)prod * F::N);
+            else {
+                const uint32_t ex = prod << a.log_O;
+                tw = F::load(a.t_hi + (size_t)(ex >> a.lo_bits) * F::N) * F::load(a.t_lo + (size_t)(ex & lo_mask) * F::N);
+            }
             x = x * tw;
         }
         x.canon().store(dst + (base + ((size_t)jp << a.log_M) + col) * F::N);
-    }
+    };
+    tile_transform<F>(sm, LS, CP, a.r, a.logC, false, a.stage_tw, gl, gs);
 }
 
 // pass P (last): contiguous runs in, digit-reversed positions out
 template <class P>
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, NttPassArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const NttPassArgs a) {
     using F = Fe<P>;
     extern __shared__ uint32_t sm[];
     const uint32_t N = 1u << a.r, C = 1u << a.logC, CP = C > 1 ? C + 1 : 1, LS = N * CP;
@@ -217,24 +293,19 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(const uint32_t *__rest
             tmp >>= a.rad[d];
         }
     }
-    for (uint32_t e = threadIdx.x; e < N * C; e += blockDim.x) {
-        const uint32_t cidx = e >> a.r, ip = e & (N - 1);
-        const size_t o = (size_t)(j1_0 + cidx) * rest_count + rest;
-        F x = F::load(src + ((o << a.r) + ip) * F::N);
-        sm_store(sm, LS, ip * CP + cidx, x);
-    }
-    __syncthreads();
-    tile_dft<F>(sm, LS, CP, a.r, a.logC, a.stage_tw);
     F scale;
     if (a.scale) scale = F::load(a.scale);
     const size_t out_base = (size_t)j1_0 + ((size_t)revp << r1);
-    for (uint32_t e = threadIdx.x; e < N * C; e += blockDim.x) {
-        const uint32_t jp = e >> a.logC, cidx = e & (C - 1);
-        const uint32_t pos = __brev(jp) >> (32 - a.r);
-        F x = sm_load<F>(sm, LS, pos * CP + cidx);
+    auto gl = [&](uint32_t ip, uint32_t cidx) -> F {
+        const size_t o = (size_t)(j1_0 + cidx) * rest_count + rest;
+        return F::load(src + ((o << a.r) + ip) * F::N);
+    };
+    auto gs = [&](uint32_t pos, uint32_t cidx, F x) {
+        const uint32_t jp = __brev(pos) >> (32 - a.r);
         if (a.scale) x = x * scale;
         x.canon().store(dst + (out_base + cidx + ((size_t)jp << log_OP)) * F::N);
-    }
+    };
+    tile_transform<F>(sm, LS, CP, a.r, a.logC, true, a.stage_tw, gl, gs);
 }
 
 // ---- exchange step of the four-step transform -----------------------------------------------------
@@ -322,8 +393,12 @@ static cudaError_t ntt_get_tables(const NttShape &shape, const void *omega_host,
     err = cudaMemcpyAsync(e->d_tab, e->omega.data(), 32, cudaMemcpyHostToDevice, stream);
     if (err == cudaSuccess) {
         const NttTableLayout &t = e->layout;
-        k_ntt_tables<Bn254Fr><<<64, 128, 0, stream>>>(e->d_tab, shape.log_n, t.lo_bits, t.hi_bits, t.r_a, t.r_b, t.off_lo, t.off_hi, t.off_sa,
-                                                    t.off_sb, t.off_scale, inverse ? 1 : 0);
+        NttTableArgs ta{};
+        ta.log_n = shape.log_n; ta.nseg = t.nseg; ta.off_scale = t.off_scale; ta.inverse = inverse ? 1 : 0;
+        uint32_t total = 0;
+        for (unsigned s = 0; s < t.nseg; s++) { ta.seg[s] = t.seg[s]; total += t.seg[s].count; }
+        const unsigned blocks = std::min<uint32_t>((total + 128) / 128, 148 * 16);
+        k_ntt_tables<Bn254Fr><<<blocks, 128, 0, stream>>>(e->d_tab, ta);
         err = cudaGetLastError();
     }
     if (err != cudaSuccess) { cudaFree(e->d_tab); delete e; return err; }
@@ -367,7 +442,7 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
     static bool attr_done[64] = {};
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
-    const size_t max_smem = (size_t)8 * (256 * 9) * 4;
+    const size_t max_smem = (size_t)8 * (256 * 9) * 4;                 // r = 8, C = 8; shorter transforms with more columns stay below it
     if (dev < 64 && !attr_done[dev]) {
         PB_CUDA(cudaFuncSetAttribute(k_ntt_cols<Bn254Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         PB_CUDA(cudaFuncSetAttribute(k_ntt_last<Bn254Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -383,20 +458,24 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
         a.log_M = log_n - log_O - a.r;
         a.stage_tw = tab->d_tab + (a.r == t.r_a ? t.off_sa : t.off_sb);
         a.t_lo = tab->d_tab + t.off_lo; a.t_hi = tab->d_tab + t.off_hi;
+        a.t_direct = nullptr;
         a.scale = nullptr;
         const bool last = p + 1 == shape.passes;
         if (!last) {
-            a.logC = a.log_M < 3 ? a.log_M : 3;
+            if (t.off_direct[p]) a.t_direct = tab->d_tab + t.off_direct[p];
+            // C adjacent columns per CTA: at least 8 (256-byte runs), more for short transforms so that a tile holds 2048 elements
+            // (one radix-8 unit per thread)
+            a.logC = std::min<unsigned>(a.log_M, std::max<unsigned>(3, 11 - std::min<unsigned>(a.r, 11)));
             const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
-            const size_t smem = (size_t)8 * ((size_t)(1u << a.r) * CP) * 4;
+            const size_t smem = a.r > 3 ? (size_t)8 * ((size_t)(1u << a.r) * CP) * 4 : 0;   // a single stage group never touches smem
             const uint32_t blocks = batch << (log_O + a.log_M - a.logC);   // batch rows extend the outer index: (t * 2^log_O + o)
             k_ntt_cols<Bn254Fr><<<blocks, NTT_THREADS, smem, stream>>>(src, dst, a);
         } else {
             const unsigned r1 = shape.passes > 1 ? shape.r[0] : 0;
-            a.logC = r1 < 3 ? r1 : 3;
+            a.logC = std::min<unsigned>(r1, std::max<unsigned>(3, 11 - std::min<unsigned>(a.r, 11)));
             if (inverse) a.scale = tab->d_tab + t.off_scale;
             const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
-            const size_t smem = (size_t)8 * ((size_t)(1u << a.r) * CP) * 4;
+            const size_t smem = a.r > 3 ? (size_t)8 * ((size_t)(1u << a.r) * CP) * 4 : 0;
             a.log_bpt = log_O - a.logC;
             const uint32_t blocks = batch << a.log_bpt;
             k_ntt_last<Bn254Fr><<<blocks, NTT_THREADS, smem, stream>>>(src, dst, a);

@@ -132,6 +132,16 @@ static panda_error msm_execute_host_scalars(pb::CurveId curve, const panda_msm_c
 panda_error panda_msm_execute_bn254_host_scalars(const panda_msm_configuration cfg, size_t n) { return msm_execute_host_scalars(pb::CURVE_BN254, cfg, n); }
 panda_error panda_msm_execute_bls12_377_host_scalars(const panda_msm_configuration cfg, size_t n) { return msm_execute_host_scalars(pb::CURVE_BLS12_377, cfg, n); }
 
+panda_error panda_msm_register_bases_bn254(const void *d_bases, size_t n, panda_stream stream) {
+    if (n > (size_t)1 << 30) return perr(cudaErrorInvalidValue);
+    return perr(pb::msm_register_bases(pb::CURVE_BN254, d_bases, (uint32_t)n, cu(stream)));
+}
+panda_error panda_msm_register_bases_bls12_377(const void *d_bases, size_t n, panda_stream stream) {
+    if (n > (size_t)1 << 30) return perr(cudaErrorInvalidValue);
+    return perr(pb::msm_register_bases(pb::CURVE_BLS12_377, d_bases, (uint32_t)n, cu(stream)));
+}
+panda_error panda_msm_unregister_bases(const void *d_bases) { return perr(pb::msm_unregister_bases(d_bases)); }
+
 panda_error panda_msm_setup_bn254(void) { return panda_success; }          // nothing to prepare: msm_cuda.cuh:786-795 is empty too
 panda_error panda_msm_setup_bls12_377(void) { return panda_success; }
 panda_error panda_msm_tear_down(void) { return perr(pb::msm_release_tables()); }   // idempotent (wrapper.rs:297-312 calls it once per base set); drops cached tables

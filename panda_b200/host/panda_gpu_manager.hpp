@@ -164,13 +164,23 @@ class PandaGpuManager {
         check(panda_memcpy(d, b.data, b.len), PandaGpuError::CreateContextError);
         return d;
     }
+    // cached bases are announced to the library (panda_msm_register_bases_bn254): it builds its table of precomputed multiples
+    // once, here, and every MSM on the cached pointer runs without a content check.  No counterpart in wrapper.rs: the
+    // reference's panda_msm_setup_bn254 is an empty hook (msm_cuda.cuh:786-795).
+    static void *upload_bases(const ByteSlice &b) {
+        void *d = upload(b);
+        panda_stream null_stream{nullptr};
+        const size_t points = b.len / (2 * FIELD_ELEMENT_LEN);
+        if (points) check(panda_msm_register_bases_bn254(d, points, null_stream), PandaGpuError::SetBasesErr);
+        return d;
+    }
     static std::vector<void *> init_msm(const std::vector<ByteSlice> &bases) {   // wrapper.rs:122-152
         std::vector<void *> out;
-        for (const auto &b : bases) out.push_back(upload(b));
+        for (const auto &b : bases) out.push_back(upload_bases(b));
         check(panda_msm_setup_bn254(), PandaGpuError::CreateContextError);
         return out;
     }
-    static void *init_msm_cached_bases(const ByteSlice &bases) { return upload(bases); }       // wrapper.rs:154-170
+    static void *init_msm_cached_bases(const ByteSlice &bases) { return upload_bases(bases); } // wrapper.rs:154-170
     static void *init_msm_cached_scalars(const ByteSlice &scalars) { return upload(scalars); }   // wrapper.rs:172-188
     static std::pair<void *, void *> init_msm_cached(const ByteSlice &scalars, const ByteSlice &bases) {   // wrapper.rs:190-197
         void *s = init_msm_cached_scalars(scalars);
@@ -209,7 +219,7 @@ class PandaGpuManager {
     size_t device_id() const { return device_id_; }
     void deinit() {   // wrapper.rs:297-312 (tear_down is idempotent here; streams are destroyed too)
         sync();
-        for (void *p : d_bases) { check(panda_free(p), PandaGpuError::DestroyContextErr); check(panda_msm_tear_down(), PandaGpuError::DestroyContextErr); }
+        for (void *p : d_bases) { check(panda_msm_unregister_bases(p), PandaGpuError::DestroyContextErr); check(panda_free(p), PandaGpuError::DestroyContextErr); check(panda_msm_tear_down(), PandaGpuError::DestroyContextErr); }
         for (void *p : d_scalars) check(panda_free(p), PandaGpuError::DestroyContextErr);
         d_bases.clear(); d_scalars.clear(); scalars_len.clear();
         check(panda_mem_pool_destroy(mem_pool_.raw), PandaGpuError::DestroyContextErr);

@@ -55,8 +55,15 @@ def msm_case(cid, k, coord, mode, label):
     cfg = ffi.MSMConfiguration(pool, stream, d_b.ptr, d_s.ptr, d_r.ptr, k, coord)
     info = (C.c_uint * 3)()
 
+    if mode == 2:       # init_msm: cached bases announced once, table built here
+        assert (ffi.lib.panda_msm_register_bases_bls12_377 if cid else ffi.lib.panda_msm_register_bases_bn254)(d_b.ptr, n, stream) == 0
+    assert ffi.lib.panda_debug_msm_timed(cid, cfg, n, 0, 0, -1 if mode == 2 else 0, None, info) == 0      # which plan runs
+
     def run():
-        assert ffi.lib.panda_debug_msm_timed(cid, cfg, n, 0, 0, mode, None, info) == 0
+        if mode == 2:
+            assert (ffi.lib.panda_msm_execute_bls12_377_n if cid else ffi.lib.panda_msm_execute_bn254_n)(cfg, n) == 0
+        else:
+            assert ffi.lib.panda_debug_msm_timed(cid, cfg, n, 0, 0, 0, None, None) == 0
 
     ms = timed(run)
     got = d_r.to_numpy()

@@ -335,3 +335,34 @@ def test_host_scalars_streamed_skew_and_bls(oracle, dev):
     s.sync()
     assert (oracle.jac_to_affine(1, d_r.to_numpy()) == exp).all()
     assert ffi.lib.panda_msm_tear_down() == 0
+
+
+def test_registered_bases(oracle, dev):
+    """panda_msm_register_bases_bn254 (init_msm): table from the first call on, prefixes of the registered set share it, no
+    fingerprint; unregister / tear_down fall back to the unannounced behaviour"""
+    ffi, gu = dev
+    n = 1 << 13
+    bases = oracle.gen_bases(0, 400, n)
+    scal = oracle.gen_scalars(1, 401, n)
+    d_b, d_s, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf.from_numpy(scal), gu.DevBuf(96)
+    s = ffi.PandaStream.new()
+    assert ffi.lib.panda_msm_register_bases_bn254(d_b.ptr, n, s) == 0
+    info = (C.c_uint * 3)()
+    cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, d_s.ptr, d_r.ptr, 13, 0)
+    for m in (n, n // 2, 3000, 1024):          # the whole set and prefixes of it
+        exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, 400, scal[:m * 32], m))
+        assert ffi.lib.panda_debug_msm_timed(0, cfg, m, 0, 0, -1, None, info) == 0
+        assert info[0] == 1                                             # folded from the first call
+        assert (oracle.jac_to_affine(0, d_r.to_numpy()) == exp).all(), m
+        assert ffi.lib.panda_msm_execute_bn254_n(cfg, m) == 0
+        s.sync()
+        assert (oracle.jac_to_affine(0, d_r.to_numpy()) == exp).all(), m
+        hs = scal[:m * 32].copy()
+        cfg_h = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, hs.ctypes.data, d_r.ptr, 0, 0)
+        assert ffi.lib.panda_msm_execute_bn254_host_scalars(cfg_h, m) == 0
+        s.sync()
+        assert (oracle.jac_to_affine(0, d_r.to_numpy()) == exp).all(), m
+    assert ffi.lib.panda_msm_unregister_bases(d_b.ptr) == 0
+    assert ffi.lib.panda_msm_unregister_bases(d_b.ptr) == 0             # idempotent
+    assert ffi.lib.panda_debug_msm_timed(0, cfg, n, 0, 0, -1, None, info) == 0 and info[0] == 0
+    assert ffi.lib.panda_msm_tear_down() == 0
