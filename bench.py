@@ -148,7 +148,7 @@ def run_reference_arm(args):
                                    f"about 1/(2 s/2^24 + per-point cost))"},
         "e2e": {"value": value, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -438,13 +438,22 @@ def run_own_arm(args):
     }
     if sharded_ntt is not None:
         line["ntt_sharded"] = sharded_ntt
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def emit(line: dict):
+    """the ONE JSON line goes to the real stdout; everything else this process (or NCCL) prints was redirected to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+
+
 def main():
+    os.dup2(2, 1)          # libraries that print to stdout (NCCL's version banner) must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -463,7 +472,7 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                    "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
                    "--warmup", str(args.warmup)]
-            return subprocess.call(cmd)
+            return subprocess.call(cmd, stdout=_REAL_STDOUT)
         log(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
     return run_own_arm(args)
 

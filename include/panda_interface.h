@@ -171,6 +171,11 @@ panda_error panda_msm_combine_bls12_377(const void *partials, unsigned count, vo
 /* Inverse transform: x = (1/n) * DFT_{omega^-1}(y); omega is the FORWARD root (host pointer), same flag contract. */
 panda_error panda_intt_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cfg);
 
+/* Coset transforms (what a PLONK / halo2 prover calls around its quotient polynomial; no reference precedent): with coset
+ * generator g (HOST pointer, 32 B Montgomery) forward computes y = NTT(x_i * g^i), inverse != 0 computes
+ * x_i = g^-i * INTT(y)_i; same omega / flag contract as panda_ntt_execute_bn254_v1. */
+panda_error panda_ntt_coset_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cfg, const void *coset_gen, int inverse);
+
 /* Batched transform: `batch` independent 2^log_n-point (I)NTTs stored back to back in d_src (d_dst: same size); same omega /
  * flag contract as panda_ntt_execute_bn254_v1 (flag tells which buffer holds all `batch` results).  inverse != 0: omega^-1 and
  * the 1/2^log_n scale.  Building block of polynomial-batch provers and of the multi-GPU four-step transform. */

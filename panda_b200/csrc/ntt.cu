@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <array>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -30,7 +31,7 @@ namespace pb {
 static constexpr int NTT_THREADS = 256;
 static constexpr unsigned NTT_MAX_RADIX_LOG = 8;      // fft.cu:10 MAX_LOG2_RADIX
 static constexpr unsigned NTT_MAX_PARTS = 16;         // destination buffers of the exchange step (GPUs of one box)
-static constexpr unsigned NTT_DIRECT_LOG = 20;        // pass boundaries with at most 2^20 distinct twiddles get a direct table
+static constexpr unsigned NTT_DIRECT_LOG = 24;        // pass boundaries with at most 2^24 distinct twiddles get a direct table (<= 512 MiB; B200: 2^24 4.55 -> 4.33 ms wall)
 
 struct NttShape {
     unsigned log_n, passes;
@@ -61,6 +62,11 @@ struct NttTableLayout {
     NttSegment seg[8];
 };
 
+static unsigned ntt_direct_log() {       // PANDA_NTT_DIRECT_LOG overrides (tuning)
+    static const unsigned v = [] { const char *e = getenv("PANDA_NTT_DIRECT_LOG"); return e ? (unsigned)atoi(e) : NTT_DIRECT_LOG; }();
+    return v;
+}
+
 static NttTableLayout ntt_table_layout(const NttShape &s) {
     NttTableLayout t{};
     t.lo_bits = (s.log_n + 1) / 2;
@@ -83,7 +89,7 @@ static NttTableLayout ntt_table_layout(const NttShape &s) {
     unsigned log_O = 0;
     for (unsigned p = 0; p + 1 < s.passes; p++) {
         const unsigned size_log = s.log_n - log_O;
-        if (size_log <= NTT_DIRECT_LOG) t.off_direct[p] = add(1u << size_log, log_O);
+        if (size_log <= ntt_direct_log()) t.off_direct[p] = add(1u << size_log, log_O);
         log_O += s.r[p];
     }
     t.words = off;
@@ -359,10 +365,32 @@ __global__ void __launch_bounds__(256) k_ntt_exchange(const NttExchangeArgs a) {
     }
 }
 
+// ---- coset transforms ---------------------------------------------------------------------------------
+template <class P>
+__global__ void k_fe_invert(uint32_t *x) {
+    using F = Fe<P>;
+    fe_inverse(F::load_plain(x)).canon().store(x);
+}
+
+// data[i] *= g^i (two-level table of the powers of g): the pre-scaling of a coset NTT / the post-scaling of its inverse.
+// HBM-bound pass (64 B per element) with 2 products per element.
+template <class P>
+__global__ void __launch_bounds__(256) k_ntt_coset_scale(uint32_t *__restrict__ data, uint32_t n, const uint32_t *__restrict__ t_lo,
+                                                         const uint32_t *__restrict__ t_hi, unsigned lo_bits) {
+    using F = Fe<P>;
+    const uint32_t lo_mask = (1u << lo_bits) - 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        F x = F::load_plain(data + (size_t)i * F::N);
+        if (i) x = x * (F::load(t_hi + (size_t)(i >> lo_bits) * F::N) * F::load(t_lo + (size_t)(i & lo_mask) * F::N));
+        x.canon().store(data + (size_t)i * F::N);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 
 struct NttCacheEntry {
     int device;
+    int kind;               // 0: powers of a root of unity (transform tables); 1: powers of a coset generator (two-level table only)
     unsigned log_n;
     bool inverse;
     std::array<uint32_t, 8> omega;
@@ -375,17 +403,21 @@ static std::vector<NttCacheEntry *> g_ntt_cache;
 
 #define PB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[panda-b200] CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); return e_; } } while (0)
 
-static cudaError_t ntt_get_tables(const NttShape &shape, const void *omega_host, bool inverse, cudaStream_t stream, NttCacheEntry **out) {
+static cudaError_t ntt_get_tables(const NttShape &shape, const void *omega_host, bool inverse, cudaStream_t stream, NttCacheEntry **out, int kind = 0) {
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
     std::array<uint32_t, 8> om;
     memcpy(om.data(), omega_host, 32);
     std::lock_guard<std::mutex> lock(g_ntt_mutex);
     for (auto *e : g_ntt_cache)
-        if (e->device == dev && e->log_n == shape.log_n && e->inverse == inverse && e->omega == om) { *out = e; return cudaSuccess; }
+        if (e->device == dev && e->kind == kind && e->log_n == shape.log_n && e->inverse == inverse && e->omega == om) { *out = e; return cudaSuccess; }
     auto *e = new NttCacheEntry();
-    e->device = dev; e->log_n = shape.log_n; e->inverse = inverse; e->omega = om;
+    e->device = dev; e->kind = kind; e->log_n = shape.log_n; e->inverse = inverse; e->omega = om;
     e->layout = ntt_table_layout(shape);
+    if (kind == 1) {           // coset generator: only the two-level table (segments 0 and 1)
+        e->layout.nseg = 2;
+        e->layout.words = e->layout.off_sa;
+    }
     e->d_tab = nullptr;
     cudaError_t err = cudaMalloc((void **)&e->d_tab, e->layout.words * 4);
     if (err != cudaSuccess) { delete e; return err; }
@@ -395,6 +427,10 @@ static cudaError_t ntt_get_tables(const NttShape &shape, const void *omega_host,
         const NttTableLayout &t = e->layout;
         NttTableArgs ta{};
         ta.log_n = shape.log_n; ta.nseg = t.nseg; ta.off_scale = t.off_scale; ta.inverse = inverse ? 1 : 0;
+        if (kind == 1) {           // g has no small order: g^-e is a power of g^-1, not g^(n-e)
+            if (inverse) k_fe_invert<Bn254Fr><<<1, 1, 0, stream>>>(e->d_tab);
+            ta.inverse = 0;
+        }
         uint32_t total = 0;
         for (unsigned s = 0; s < t.nseg; s++) { ta.seg[s] = t.seg[s]; total += t.seg[s].count; }
         const unsigned blocks = std::min<uint32_t>((total + 128) / 128, 148 * 16);
@@ -507,6 +543,17 @@ cudaError_t ntt_exchange(NttField field, const void *d_src, unsigned log_rows, u
     }
     const uint32_t tiles_r = ((1u << log_rows) + 15) / 16, tiles_c = ((1u << log_cols) + 15) / 16;
     k_ntt_exchange<Bn254Fr><<<tiles_r * tiles_c, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t ntt_coset_scale(NttField field, void *d_data, unsigned log_n, const void *gen_host, bool inverse, cudaStream_t stream) {
+    (void)field;
+    if (!d_data || !gen_host || log_n > 28) return cudaErrorInvalidValue;
+    NttCacheEntry *tab = nullptr;
+    PB_CUDA(ntt_get_tables(ntt_shape(log_n), gen_host, inverse, stream, &tab, 1));
+    const uint32_t n = 1u << log_n;
+    k_ntt_coset_scale<Bn254Fr><<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256, 0, stream>>>((uint32_t *)d_data, n, tab->d_tab + tab->layout.off_lo,
+                                                                                                tab->d_tab + tab->layout.off_hi, tab->layout.lo_bits);
     return cudaGetLastError();
 }
 

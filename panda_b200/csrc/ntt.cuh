@@ -28,6 +28,9 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
 cudaError_t ntt_exchange(NttField field, const void *d_src, unsigned log_rows, unsigned log_cols, unsigned row_offset, const void *omega_host,
                          unsigned log_n, bool inverse, unsigned parts, void *const *dst, size_t ld, size_t col_offset, cudaStream_t stream);
 
+// d_data[i] *= g^i (inverse: g^-i) for i < 2^log_n; gen_host: HOST pointer to the coset generator g (Montgomery).
+cudaError_t ntt_coset_scale(NttField field, void *d_data, unsigned log_n, const void *gen_host, bool inverse, cudaStream_t stream);
+
 // frees the cached twiddle tables of every device
 cudaError_t ntt_release_tables();
 

@@ -209,6 +209,16 @@ panda_error panda_ntt_batch_execute_bn254_v1(const panda_ntt_configuration_v1 cf
     *static_cast<unsigned *>(cfg.flag) = in_dst;
     return perr(e);
 }
+panda_error panda_ntt_coset_execute_bn254_v1(const panda_ntt_configuration_v1 cfg, const void *coset_gen, int inverse) {
+    if (!cfg.d_omega || !cfg.flag || !coset_gen || !cfg.d_src || !cfg.d_dst) return perr(cudaErrorInvalidValue);
+    cudaError_t e = cudaSuccess;
+    if (!inverse) e = pb::ntt_coset_scale(pb::NTT_BN254_FR, cfg.d_src, cfg.log_n, coset_gen, false, cu(cfg.stream));
+    unsigned in_dst = 0;
+    if (e == cudaSuccess) e = pb::ntt_run(pb::NTT_BN254_FR, cfg.d_src, cfg.d_dst, cfg.log_n, cfg.d_omega, inverse != 0, cu(cfg.stream), &in_dst);
+    *static_cast<unsigned *>(cfg.flag) = in_dst;
+    if (e == cudaSuccess && inverse) e = pb::ntt_coset_scale(pb::NTT_BN254_FR, in_dst ? cfg.d_dst : cfg.d_src, cfg.log_n, coset_gen, true, cu(cfg.stream));
+    return perr(e);
+}
 panda_error panda_ntt_exchange_bn254(const panda_ntt_exchange_configuration *cfg) {
     if (!cfg) return perr(cudaErrorInvalidValue);
     return perr(pb::ntt_exchange(pb::NTT_BN254_FR, cfg->d_src, cfg->log_rows, cfg->log_cols, cfg->row_offset, cfg->omega, cfg->log_n, cfg->inverse != 0,

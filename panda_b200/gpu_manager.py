@@ -43,6 +43,8 @@ def _load() -> C.CDLL:
         "panda_host_msm_bn254_gpu_host": [vp, vp, sz, vp, sz, vp],
         "panda_host_ntt_bn254_gpu": [vp, vp, sz, u32],
         "panda_host_ntt_bn254_gpu_v1": [vp, vp, sz, vp, u32],
+        "panda_host_intt_bn254_gpu_v1": [vp, vp, sz, vp, u32],
+        "panda_host_msm_bls12_377_gpu": [vp, vp, sz, vp, sz, vp],
     }
     for name, args in sigs.items():
         fn = getattr(h, name)
@@ -217,3 +219,19 @@ def panda_ntt_bn254_gpu(gm: PandaGpuManager, scalars: np.ndarray, log_n: int) ->
 def panda_ntt_bn254_gpu_v1(gm: PandaGpuManager, scalars: np.ndarray, omega, log_n: int) -> None:  # unit.rs:481-543
     s, om = _bytes(scalars), _bytes(omega)
     _ok(host.panda_host_ntt_bn254_gpu_v1(gm._h, s.ctypes.data, s.size, om.ctypes.data, log_n))
+
+
+# ---- additions (no counterpart in unit.rs): the inverse transform and the second curve, same calling shape -------------------------
+
+def panda_intt_bn254_gpu_v1(gm: PandaGpuManager, scalars: np.ndarray, omega, log_n: int) -> None:
+    """in place: scalars <- (1/n) DFT_{omega^-1}(scalars); omega is the FORWARD root of unity"""
+    s, om = _bytes(scalars), _bytes(omega)
+    _ok(host.panda_host_intt_bn254_gpu_v1(gm._h, s.ctypes.data, s.size, om.ctypes.data, log_n))
+
+
+def panda_msm_bls12_377_gpu(gm: PandaGpuManager, scalars, bases) -> np.ndarray:
+    """BLS12-377 G1 MSM: bases 96 B per point, scalars 32 B, 144-byte result in the manager's coordinate type"""
+    s, b = _bytes(scalars), _bytes(bases)
+    r = np.zeros(144, np.uint8)
+    _ok(host.panda_host_msm_bls12_377_gpu(gm._h, s.ctypes.data, s.size, b.ctypes.data, b.size, r.ctypes.data))
+    return r

@@ -370,4 +370,50 @@ inline void panda_ntt_bn254_gpu_v1(const PandaGpuManager &gm, uint8_t *scalars, 
     detail::ntt_fetch(gm, scalars, len, d_src, d_dst, flag);
 }
 
+// ---- additions: the entry points README.md:36 promises ("BLS12-377 ... will be easy") and the inverse transform, in the same shape as the
+// functions above (no counterpart in unit.rs) ------------------------------------------------------------------------------------------
+
+// panda_ntt_bn254_gpu_v1's inverse: scalars <- (1/n) DFT_{omega^-1}(scalars), omega = the FORWARD root
+inline void panda_intt_bn254_gpu_v1(const PandaGpuManager &gm, uint8_t *scalars, size_t len, const ByteSlice &omega, uint32_t log_n) {
+    if (len != (size_t(1) << log_n) * 32) throw std::invalid_argument("scalars.len() != (1 << log_n) * 32");
+    void *d_src = memory_alloc_and_copy(gm, ByteSlice{scalars, len}, gm.get_h2d_stream());
+    void *d_dst = nullptr;
+    malloc_from_pool_async(&d_dst, len, gm.get_mem_pool(), gm.get_h2d_stream());
+    gm.wait_h2d();
+    unsigned flag = 0;
+    panda_ntt_configuration_v1 cfg{gm.get_mem_pool().raw, gm.get_exec_stream().raw, d_src, d_dst, const_cast<uint8_t *>(omega.data), log_n, &flag};
+    check(panda_intt_execute_bn254_v1(cfg), PandaGpuError::SchedulingErr);
+    gm.get_exec_stream().sync();
+    detail::ntt_fetch(gm, scalars, len, d_src, d_dst, flag);
+}
+
+constexpr size_t BLS12_377_FQ_LEN = 48;
+
+// BLS12-377 G1 MSM: bases 96 B per point (x || y, 12 x u32 Montgomery), scalars 32 B, result 144 B (Jacobian or Projective per set_config)
+inline std::vector<uint8_t> panda_msm_bls12_377_gpu(const PandaGpuManager &gm, const ByteSlice &scalars, const ByteSlice &bases) {
+    const uint32_t log_scalars_count = log_2(scalars.len / FIELD_ELEMENT_LEN);
+    if (bases.len / (2 * BLS12_377_FQ_LEN) < (size_t(1) << log_scalars_count)) throw PandaGpuException(PandaGpuError::MSMBasesAddrError);
+    void *d_scalars = memory_alloc_and_copy(gm, scalars, gm.get_h2d_stream());
+    void *d_bases = memory_alloc_and_copy(gm, bases, gm.get_h2d_stream());
+    gm.wait_h2d();
+    const size_t result_buf_len = BLS12_377_FQ_LEN * 3;
+    void *d_result = nullptr;
+    malloc_from_pool_async(&d_result, result_buf_len, gm.get_mem_pool(), gm.get_exec_stream());
+    panda_msm_configuration cfg{};
+    cfg.mem_pool = gm.get_mem_pool().raw;
+    cfg.stream = gm.get_exec_stream().raw;
+    cfg.bases = d_bases; cfg.scalars = d_scalars; cfg.results = d_result;
+    cfg.log_scalars_count = log_scalars_count;
+    cfg.msm_result_coordinate_type = static_cast<panda_msm_result_coordinate_type>(gm.get_msm_result_coordinate_type());
+    check(panda_msm_execute_bls12_377(cfg), PandaGpuError::SchedulingErr);
+    std::vector<uint8_t> out(result_buf_len);
+    panda_error rc = panda_memcpy_async(out.data(), d_result, result_buf_len, gm.get_exec_stream().raw);
+    if (rc == panda_success) rc = panda_stream_synchronize(gm.get_exec_stream().raw);
+    free_async(d_scalars, gm.get_exec_stream());
+    free_async(d_bases, gm.get_exec_stream());
+    free_async(d_result, gm.get_exec_stream());
+    if (rc != panda_success) throw PandaGpuException(PandaGpuError::CreateContextError);
+    return out;
+}
+
 }  // namespace panda

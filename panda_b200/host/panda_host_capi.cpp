@@ -94,4 +94,11 @@ int panda_host_ntt_bn254_gpu_v1(void *gm, void *scalars, size_t len, const void 
     return guarded([&] { panda_ntt_bn254_gpu_v1(*static_cast<PandaGpuManager *>(gm), static_cast<uint8_t *>(scalars), len, bs(omega, 32), log_n); });
 }
 
+int panda_host_intt_bn254_gpu_v1(void *gm, void *scalars, size_t len, const void *omega, unsigned log_n) {
+    return guarded([&] { panda_intt_bn254_gpu_v1(*static_cast<PandaGpuManager *>(gm), static_cast<uint8_t *>(scalars), len, bs(omega, 32), log_n); });
+}
+int panda_host_msm_bls12_377_gpu(void *gm, const void *scalars, size_t scalars_len, const void *bases, size_t bases_len, void *result144) {
+    return guarded([&] { auto r = panda_msm_bls12_377_gpu(*static_cast<PandaGpuManager *>(gm), bs(scalars, scalars_len), bs(bases, bases_len)); memcpy(result144, r.data(), r.size()); });
+}
+
 }  // extern "C"

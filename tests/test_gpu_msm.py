@@ -366,3 +366,24 @@ def test_registered_bases(oracle, dev):
     assert ffi.lib.panda_msm_unregister_bases(d_b.ptr) == 0             # idempotent
     assert ffi.lib.panda_debug_msm_timed(0, cfg, n, 0, 0, -1, None, info) == 0 and info[0] == 0
     assert ffi.lib.panda_msm_tear_down() == 0
+
+
+def test_host_api_additions(oracle, dev):
+    """panda_msm_bls12_377_gpu and panda_intt_bn254_gpu_v1: the second curve and the inverse transform in the host API's shape"""
+    from panda_b200 import gpu_manager as gm
+
+    k, n = 11, 1 << 11
+    bases = oracle.gen_bases(1, 500, n); scal = oracle.gen_scalars(3, 501, n)
+    exp = oracle.jac_to_affine(1, oracle.expected_progression_msm(1, 500, scal, n))
+    m = gm.PandaGpuManager.new(0)
+    try:
+        assert (oracle.jac_to_affine(1, gm.panda_msm_bls12_377_gpu(m, scal, bases)) == exp).all()
+        m.set_config(gm.PandaMSMResultCoordinateType.Projective)
+        assert (oracle.proj_to_affine(1, gm.panda_msm_bls12_377_gpu(m, scal, bases)) == exp).all()
+        x = oracle.gen_scalars(1, 502, n)
+        w = oracle.omega_bn254(k)
+        y = x.copy(); gm.panda_ntt_bn254_gpu_v1(m, y, w, k)
+        gm.panda_intt_bn254_gpu_v1(m, y, w, k)
+        assert (y == x).all()
+    finally:
+        m.deinit()

@@ -111,3 +111,35 @@ def test_host_api_ntt(oracle, dev):
         assert (b == exp).all()
     finally:
         m.deinit()
+
+
+@pytest.mark.parametrize("k", [1, 6, 13, 17])
+def test_coset_transforms(oracle, dev, k):
+    """panda_ntt_coset_execute_bn254_v1: y = NTT(x_i * g^i) against the oracle (powers of g by repeated multiplication), and the
+    inverse brings x back"""
+    ffi, gu = dev
+    n = 1 << k
+    x = oracle.gen_scalars(1, 6000 + k, n)
+    w = oracle.omega_bn254(k)
+    g = oracle.gen_scalars(1, 77, 1)                                   # some field element as coset generator
+    pw = np.empty((n, 32), np.uint8)
+    pw[0] = oracle.field_const(1, 1)
+    cur = 1
+    while cur < n:                                                     # doubling: pw[cur:2cur] = pw[:cur] * g^cur
+        gp = oracle.f_pow2k(1, g, cur.bit_length() - 1)
+        pw[cur:2 * cur] = oracle.f_mul(1, pw[:cur].reshape(-1), np.tile(gp, cur)).reshape(cur, 32)
+        cur *= 2
+    exp = oracle.ntt(1, oracle.f_mul(1, x, pw.reshape(-1)), k, w)
+    om, gg = w.copy(), g.copy()
+    s = ffi.PandaStream.null()
+    flag = C.c_uint(9)
+    a, b = gu.DevBuf.from_numpy(x), gu.DevBuf(x.size)
+    cfg = ffi.NttconfigurationV1(ffi.PandaMemPool.null(), s, a.ptr, b.ptr, om.ctypes.data, k, C.pointer(flag))
+    assert ffi.lib.panda_ntt_coset_execute_bn254_v1(cfg, gg.ctypes.data, 0) == 0
+    y = (b if flag.value else a).to_numpy(x.size)
+    assert (y == exp).all()
+    a2, b2 = gu.DevBuf.from_numpy(y), gu.DevBuf(x.size)
+    cfg = ffi.NttconfigurationV1(ffi.PandaMemPool.null(), s, a2.ptr, b2.ptr, om.ctypes.data, k, C.pointer(flag))
+    assert ffi.lib.panda_ntt_coset_execute_bn254_v1(cfg, gg.ctypes.data, 1) == 0
+    assert ((b2 if flag.value else a2).to_numpy(x.size) == x).all()
+    assert ffi.lib.panda_ntt_coset_execute_bn254_v1(cfg, None, 0) != 0
