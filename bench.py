@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 LOG_N = 24
 MODMUL_MACS = 136            # 2*8^2 + 8 32x32->64 multiply-adds per BN254 Montgomery product
 MADD_MODMULS = 10            # XYZZ mixed addition: 8M + 2S
+NCU_ACCUMULATE_TRAFFIC_BYTES = 27.50e9   # k_accumulate at 2^24 (table plan), dram__bytes_read.sum + dram__bytes_write.sum per launch
 
 
 def kernels_per_msm(plan) -> int:
@@ -419,10 +420,14 @@ def run_own_arm(args):
                 "d2h_bytes_per_step": 96 * world, "api": "panda_msm_bn254_gpu_with_cached_bases (host scalars pinned, cached bases) -> panda_msm_execute_bn254_host_scalars: chunked upload overlapped with the sort / accumulation"},
         "gpu_launches": args.steps * world * (kernels_per_msm(plan) + (1 if world > 1 else 0)),
         "roofline": {"kernel": "k_accumulate (bucket accumulation, XYZZ mixed additions)", "bound": "int32-imad", "achieved": achieved_macs / 1e12,
-                     "peak": wide_peak / 1e12, "unit": "T(32x32+64 MAC)/s", "frac": achieved_macs / wide_peak, "traffic": None,
+                     "peak": wide_peak / 1e12, "unit": "T(32x32+64 MAC)/s", "frac": achieved_macs / wide_peak,
+                     "traffic": NCU_ACCUMULATE_TRAFFIC_BYTES if (plan.folded and n_local == 1 << 24) else None,
+                     "traffic_source": "ncu --set full, profiles/r1_msm_kernels_full.md: dram read 26.83 GB + write 0.67 GB per launch (algorithmic 13.7 GB: the 64-byte "
+                                       "table gathers are fetched as 128-byte lines); the kernel is integer-bound, 13 % of HBM peak",
                      "peak_source": "IMAD.WIDE issue rate measured live by panda_debug_int_peak (32-bit IMAD rate: %.2f T/s; BN254 modmul microbench: %.2f G modmul/s)"
                                     % (imad_peak / 1e12, modmul_peak / 1e9),
-                     "algorithmic": f"{entries} mixed additions x {MADD_MODMULS} modmul x {MODMUL_MACS} MAC", "ms": acc_ms,
+                     "algorithmic": f"{entries} mixed additions x {MADD_MODMULS} modmul x {MODMUL_MACS} MAC (SURVEY 8d counts a squaring as a product; the 2 squarings of "
+                                    f"a mixed addition execute 108 MACs each, so frac can read slightly above 1)", "ms": acc_ms,
                      "share_of_step": acc_ms / float(stages.sum())},
         "roofline_hbm": {"bound": "hbm", "kernel": "k_accumulate", "achieved": acc_bytes / (acc_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": acc_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",

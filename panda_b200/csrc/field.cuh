@@ -238,7 +238,29 @@ struct Fe {
         r.l[N - 1] = ptx::addc(A[N - 1], 0);
         return r;
     }
-    PB_DEV Fe sqr() const { return *this * *this; }
+    // Montgomery square: the rows of the product above with the symmetric terms folded -- row i multiplies a_i into
+    // (a_i, 2a_{i+1}, (2a)_{i+2}, ..) and skips the columns below i, whose products the earlier rows already added twice.
+    // N(N+1)/2 + N^2 + N multiply-adds instead of 2N^2 + N (108 vs 136 for N = 8); the skipped columns become carry-only adds.
+    // Needs the top bit of the top limb clear (2a must fit N limbs): true for every value < 2p here.
+    PB_DEV Fe sqr() const {
+        uint32_t A[N], B[N], a2[N];
+        a2[0] = 0;
+        _Pragma("unroll") for (int j = 1; j < N; j++) a2[j] = __funnelshift_l(l[j - 1], l[j], 1);
+        {   // row 0: every column is live
+            const uint32_t bi = l[0];
+            _Pragma("unroll") for (int j = 0; j < N; j += 2) {
+                ptx::mul_wide(A[j], A[j + 1], j == 0 ? l[0] : a2[j], bi);
+                ptx::mul_wide(B[j], B[j + 1], j == 0 ? (l[1] << 1) : a2[j + 1], bi);
+            }
+            reduce_row(A, B);
+        }
+        sqr_rows<1>(A, B, l, a2);
+        Fe r;
+        r.l[0] = ptx::add_cc(A[0], B[1]);
+        _Pragma("unroll") for (int k = 1; k < N - 1; k++) r.l[k] = ptx::addc_cc(A[k], B[k + 1]);
+        r.l[N - 1] = ptx::addc(A[N - 1], 0);
+        return r;
+    }
 
     // Montgomery -> canonical integer (multiply by 1): reduction rows only.  Output canonical.
     PB_DEV Fe from_mont() const {
@@ -248,6 +270,34 @@ struct Fe {
     PB_DEV Fe to_mont() const { return *this * r2(); }
 
 private:
+    template <int I>
+    PB_DEV static void sqr_rows(uint32_t *A, uint32_t *B, const uint32_t *al, const uint32_t *a2) {
+        if constexpr (I < N) {
+            uint32_t c[N];
+            _Pragma("unroll") for (int j = 0; j < N; j++) c[j] = j == I ? al[I] : (j == I + 1 ? (al[j] << 1) : a2[j]);   // c[j], j < I: unused
+            if (I & 1) { sqr_row<I>(B, A, c, al[I]); reduce_row(B, A); }
+            else       { sqr_row<I>(A, B, c, al[I]); reduce_row(A, B); }
+            sqr_rows<I + 1>(A, B, al, a2);
+        }
+    }
+    // mul_row with the columns below FIRST reduced to carry propagation (same shift of the frame, no product)
+    template <int FIRST>
+    PB_DEV static void sqr_row(uint32_t *Y, uint32_t *Z, const uint32_t *a, uint32_t bi) {
+        Y[0] = ptx::add_cc(Y[0], Z[1]);
+        _Pragma("unroll") for (int j = 0; j < N - 2; j += 2) {
+            if (j + 1 >= FIRST) { Z[j] = ptx::madc_lo_cc(a[j + 1], bi, Z[j + 2]); Z[j + 1] = ptx::madc_hi_cc(a[j + 1], bi, Z[j + 3]); }
+            else                { Z[j] = ptx::addc_cc(Z[j + 2], 0); Z[j + 1] = ptx::addc_cc(Z[j + 3], 0); }
+        }
+        Z[N - 2] = ptx::madc_lo_cc(a[N - 1], bi, 0);       // column N-1 is live in every row (FIRST <= N-1)
+        Z[N - 1] = ptx::madc_hi(a[N - 1], bi, 0);
+        Y[0] = ptx::add_cc(Y[0], 0);                       // FIRST >= 1: column 0 is never live here; clears the carry
+        Y[1] = ptx::addc_cc(Y[1], 0);
+        _Pragma("unroll") for (int j = 2; j < N; j += 2) {
+            if (j >= FIRST) { Y[j] = ptx::madc_lo_cc(a[j], bi, Y[j]); Y[j + 1] = ptx::madc_hi_cc(a[j], bi, Y[j + 1]); }
+            else            { Y[j] = ptx::addc_cc(Y[j], 0); Y[j + 1] = ptx::addc_cc(Y[j + 1], 0); }
+        }
+        Z[N - 1] = ptx::addc(Z[N - 1], 0);
+    }
     // E: even-aligned accumulator (positions 0..N-1), O: odd-aligned (positions 1..N).
     // Adds m*p with m chosen so that E[0] becomes 0.
     PB_DEV static void reduce_row(uint32_t *E, uint32_t *O) {

@@ -61,7 +61,11 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
         }
         // modmul counts: mixed add 10; bucket combine + running sums ~3.5 full adds of 14 per bucket (the reduction kernels
         // run at about half the accumulate kernel's rate, hence the factor 2); folded mode has a single bucket set
-        const double cost = (double)n * W * 10.0 + (folded ? 1.0 : W) * nb * 3.5 * 14.0 * 2.0;
+        // A narrow top window (t bits) sends n digits to 2^t buckets: their counters are hot L2-atomic addresses in the histogram and
+        // scatter kernels (measured at n = 2^21, t = 7: +0.6 ms, i.e. ~20 modmul-equivalents per scalar), ~2500 / 2^t per scalar.
+        const int t = (int)bits - (int)(W - 1) * (int)c;
+        const double hot = t > 0 && t < 20 ? (double)n * 2500.0 / (double)(1u << t) : 0.0;
+        const double cost = (double)n * W * 10.0 + (folded ? 1.0 : W) * nb * 3.5 * 14.0 * 2.0 + hot;
         if (cost < best) { best = cost; best_c = c; }
     }
     if (!best_c) { p.c = 0; return p; }                         // no feasible plan (folded table would not fit)
@@ -72,9 +76,15 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     // chunks (folded only): every chunk is a physical bucket set of its own (counts, sorted list, partial slots); the bucket
     // reduction merges the chunks of a logical set
     p.chunks = folded ? std::max<uint32_t>(1, std::min<uint32_t>(chunks, std::max<uint32_t>(1, n / 4096))) : 1;
-    p.chunk_n = p.chunks > 1 ? ((n + p.chunks - 1) / p.chunks + 3) & ~3u : n;
-    p.chunks = (n + p.chunk_n - 1) / p.chunk_n;
-    p.stride = folded ? p.chunk_n * p.windows : n;
+    // the first chunk is short (its upload is exposed), the others are four times as long (their upload hides behind the chunk before)
+    if (p.chunks > 1) {
+        p.chunk_first = std::max<uint32_t>(4, (n / (1 + 4 * (p.chunks - 1)) + 3) & ~3u);
+        p.chunk_n = ((n - p.chunk_first + (p.chunks - 1) - 1) / (p.chunks - 1) + 3) & ~3u;
+        p.chunks = 1 + (n - p.chunk_first + p.chunk_n - 1) / p.chunk_n;
+    } else {
+        p.chunk_first = p.chunk_n = n;
+    }
+    p.stride = folded ? std::max(p.chunk_first, p.chunk_n) * p.windows : n;
     p.table_bytes = folded ? (size_t)n * p.windows * 2 * fq_bytes : 0;
     // segment length: about one average bucket, so that most buckets end up with one or two partial sums, but
     // never so long that the accumulation kernel has fewer than ~4 waves of threads (148 SMs x 384 threads)
@@ -89,6 +99,9 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     // then CTAs of 256 threads stitch 1024 chunk sums each; more than 32 such groups get one more stitch level
     uint32_t m = pow2_floor(std::max<uint64_t>(1, ((uint64_t)p.sets * p.nb) / 262144));
     m = std::min<uint32_t>(std::min<uint32_t>(m, 32), p.nb);
+    // small bucket sets: the stitching is a chain of ~60 dependent point additions per level (0.55 ms), so folding up to 8 buckets per
+    // thread is worth it when it brings a set down to 32 groups of 1024 chunk sums (one stitch level instead of two)
+    if (p.nb / 8 <= 32768) m = std::max<uint32_t>(m, std::max<uint32_t>(1, p.nb / 32768));
     p.chunk = m;
     p.chunks_ps = p.nb / m;
     p.groups = std::min<uint32_t>(256, std::max<uint32_t>(1, p.chunks_ps / 1024));
@@ -101,6 +114,15 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
         if (forced) p.phases = std::min<uint32_t>(pow2_floor(forced), p.nb);
     }
 
+    // batched-affine bucket accumulation (table plan, one chunk): opt-in while it is being tuned (PANDA_MSM_AFFINE=1)
+    static const int affine_env = [] { const char *e = getenv("PANDA_MSM_AFFINE"); return e ? atoi(e) : 0; }();
+    p.affine = (folded && p.chunks == 1 && affine_env > 0 && n >= 4096) ? 1 : 0;
+    if (p.affine) {
+        const uint64_t avg = std::max<uint64_t>(1, entries / p.nb);
+        uint32_t r = 1; while ((1ull << r) < 2 * avg) r++;          // buckets up to twice the average size end as one point
+        p.rounds = std::min<uint32_t>(std::max<uint32_t>(r + 1, 2), 24);
+        if (affine_env > 1) p.rounds = std::min<uint32_t>(affine_env, 24);
+    }
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     const size_t phys = (size_t)p.sets * p.chunks;                              // physical bucket sets
@@ -114,6 +136,20 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.off_slots = off;   off = align(off + phys * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);
     p.off_chunks = off;  off = align(off + (size_t)p.sets * p.chunks_ps * 2 * 4 * fq_bytes);
     p.off_gsums = off;   off = align(off + (size_t)p.sets * (p.groups + 1) * 2 * 4 * fq_bytes);   // + the second stitch level
+    if (p.affine) {
+        // outputs of round r: at most in/2 + nb (every bucket may carry one odd entry over)
+        const uint64_t out0 = std::min<uint64_t>(p.stride, (uint64_t)p.stride / 2 + p.nb);
+        const uint64_t out1 = std::min<uint64_t>(out0, out0 / 2 + p.nb);
+        const uint64_t per_cta = 256 * 32;
+        p.aff_ctas = (uint32_t)((out0 + per_cta - 1) / per_cta);
+        p.off_aff_a = off;    off = align(off + out0 * 2 * fq_bytes);
+        p.off_aff_b = off;    off = align(off + out1 * 2 * fq_bytes);
+        p.off_aff_pre = off;  off = align(off + (uint64_t)p.aff_ctas * per_cta * fq_bytes);
+        p.off_aff_tot = off;  off = align(off + (uint64_t)p.aff_ctas * 256 * fq_bytes);
+        p.off_aff_cta = off;  off = align(off + (uint64_t)p.aff_ctas * 3 * fq_bytes + 256);
+        p.off_aff_offs = off; off = align(off + (size_t)p.rounds * (p.nb + 1) * 4);
+        p.off_slots = p.off_aff_a;      // no partial-sum slots in this plan: the region is not used
+    }
     p.bytes = off;
     return p;
 }

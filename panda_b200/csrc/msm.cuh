@@ -30,10 +30,15 @@ struct MsmPlan {
     uint32_t groups;       // CTAs per set in the group-reduce stage (<= 256, divides chunks_ps)
     uint32_t chunks;       // Q: point-range chunks that are sorted and accumulated separately and share the bucket reduction
                            //    (Q > 1 only for streamed scalars: chunk q computes while chunk q+1 is still being uploaded)
-    uint32_t chunk_n;      // points per chunk (the last chunk may be shorter)
+    uint32_t chunk_first;  // points in chunk 0
+    uint32_t chunk_n;      // points in every later chunk (the last one may be shorter)
     uint32_t phases;       // folded scatter: passes over the codes, one bucket range each (L2-resident output slice)
+    uint32_t affine;       // 1: buckets are reduced by rounds of batched affine additions (msm_affine.cuh) instead of k_accumulate
+    uint32_t rounds;       // affine: tree rounds (a bucket of up to 2^rounds entries ends as one point; leftovers are folded serially)
     // workspace layout (byte offsets into one arena)
     size_t off_counts, off_offsets, off_cursor, off_biglist, off_tiles, off_digits, off_sorted, off_slots, off_chunks, off_gsums, bytes;
+    size_t off_aff_a, off_aff_b, off_aff_pre, off_aff_tot, off_aff_cta, off_aff_offs;   // affine: ping-pong points, prefix products, thread / CTA products, per-round offsets
+    uint32_t aff_ctas;     // CTAs of the first (largest) round
     size_t table_bytes;    // folded: size of the precomputed table (W * n affine points)
 };
 

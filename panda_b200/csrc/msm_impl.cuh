@@ -3,6 +3,7 @@
 #pragma once
 #include "msm.cuh"
 #include "ec.cuh"
+#include "msm_affine.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -151,8 +152,9 @@ static __global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *__re
     for (int k = 0; k < 4; k++) {
         const uint32_t idx = base + k;
         if (idx < nb) {
-            ow[idx] = excl; kw[idx] = excl;
-            if (c4[k] && (excl + c4[k] - 1) / L - excl / L + 1 > BIG_SPAN) big_list[atomicAdd(big_count, 1u)] = set * nb + idx;
+            ow[idx] = excl;
+            if (cursor) kw[idx] = excl;
+            if (big_count && c4[k] && (excl + c4[k] - 1) / L - excl / L + 1 > BIG_SPAN) big_list[atomicAdd(big_count, 1u)] = set * nb + idx;
         }
         excl += c4[k];
     }
@@ -296,6 +298,35 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const uint8_t *__
         tri.add(run);
     }
     uint8_t *out = chunks + (size_t)gid * 2 * Pt::BYTES;
+    tri.store(out);
+    run.store(out + Pt::BYTES);
+}
+
+// K5 (affine plan): after the tree rounds bucket j holds off[j+1] - off[j] affine points (one, unless the bucket was larger than
+// 2^rounds): fold them with mixed additions, then the same running sums as k_bucket_reduce.
+template <class C>
+__global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce_affine(const uint8_t *__restrict__ pts, const uint32_t *__restrict__ off,
+                                                                     uint32_t m, uint32_t chunks_ps, uint8_t *__restrict__ chunks) {
+    using Fq = typename C::Fq;
+    using Pt = Xyzz<Fq>;
+    using Af = Affine<Fq>;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks_ps) return;
+    Pt run = Pt::identity(), tri = Pt::identity();
+#pragma unroll 1
+    for (uint32_t i = m; i-- > 0;) {
+        const uint32_t j = t * m + i;
+        const uint32_t o0 = __ldg(off + j), o1 = __ldg(off + j + 1);
+#pragma unroll 1
+        for (uint32_t e = o0; e < o1; e++) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(pts + (size_t)e * Af::BYTES);
+            Af a;
+            a.x = Fq::load_plain(q); a.y = Fq::load_plain(q + Fq::N);
+            if (!a.is_identity()) run.madd(a.x, a.y);
+        }
+        tri.add(run);
+    }
+    uint8_t *out = chunks + (size_t)t * 2 * Pt::BYTES;
     tri.store(out);
     run.store(out + Pt::BYTES);
 }
@@ -655,7 +686,8 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             if ((err = cudaStreamWaitEvent(feed->copy_stream, fed, 0)) != cudaSuccess) break;
         }
         for (uint32_t q = 0; q < p.chunks && err == cudaSuccess; q++) {
-            const uint32_t point0 = q * p.chunk_n, nq = std::min<uint32_t>(p.chunk_n, n - point0);
+            const uint32_t point0 = q == 0 ? 0 : p.chunk_first + (q - 1) * p.chunk_n;
+            const uint32_t nq = q == 0 ? p.chunk_first : std::min<uint32_t>(p.chunk_n, n - point0);
             const size_t set0 = (size_t)q * p.sets;                           // first physical set of this chunk
             const uint32_t *sc = (const uint32_t *)scalars + (size_t)point0 * 8;
             if (feed) {
@@ -683,18 +715,51 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                 k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, stream>>>((const uint32_t *)codes_q, nq, p.windows, p.table_n, point0, log2_span, cursor_q, sorted_q);
             } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, stream>>>((const uint16_t *)codes_q, nq, p.nb, cursor_q, sorted_q);
             tm.mark();
-            {
+            if (p.affine) {
+                // tree rounds: every round halves the buckets with batched affine additions (one field inversion per round)
+                const size_t fe = sizeof(typename C::Fq);
+                uint8_t *cta_base = ws + p.off_aff_cta;
+                const uint32_t *off_in = offsets_q;
+                uint64_t in_max = p.stride;
+                for (uint32_t r = 0; r < p.rounds; r++) {
+                    uint32_t *off_out = (uint32_t *)(ws + p.off_aff_offs) + (size_t)r * (p.nb + 1);
+                    const uint64_t out_max = std::min<uint64_t>(in_max, in_max / 2 + p.nb);
+                    const uint32_t ctas = (uint32_t)((out_max + AFF_PER_CTA - 1) / AFF_PER_CTA);
+                    aff_next_counts<<<std::min<uint32_t>((p.nb + 255) / 256, 148 * 8), 256, 0, stream>>>(off_in, p.nb, counts_q);
+                    k_scan_tiles<<<dim3(tiles_ps, 1), 1024, 0, stream>>>(counts_q, p.nb, tiles_ps, tiles_q);
+                    k_scan_tops<<<1, 1024, 0, stream>>>(tiles_q, tiles_ps, p.nb, off_out);
+                    k_scan_apply<<<dim3(tiles_ps, 1), 1024, 0, stream>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, off_out, nullptr, nullptr, nullptr);
+                    AffRound ar{};
+                    ar.table = r == 0 ? (const uint8_t *)points : nullptr;
+                    ar.entries = r == 0 ? sorted_q : nullptr;
+                    ar.in = r == 0 ? nullptr : ws + ((r & 1) ? p.off_aff_a : p.off_aff_b);
+                    ar.off_in = off_in; ar.off_out = off_out;
+                    ar.out = ws + ((r & 1) ? p.off_aff_b : p.off_aff_a);
+                    ar.pre = ws + p.off_aff_pre; ar.tot = ws + p.off_aff_tot;
+                    ar.cta_prod = cta_base; ar.cta_inv = cta_base + (size_t)p.aff_ctas * fe;
+                    ar.nb = p.nb;
+                    aff_products<C><<<ctas, AFF_THREADS, 0, stream>>>(ar);
+                    aff_invert<C><<<1, 1024, 0, stream>>>(ar.cta_prod, ar.cta_inv, cta_base + (size_t)2 * p.aff_ctas * fe, ctas);
+                    aff_add<C><<<ctas, AFF_THREADS, 0, stream>>>(ar);
+                    off_in = off_out;
+                    in_max = out_max;
+                }
+            } else {
                 const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
                 const uint32_t blocks = (uint32_t)((threads + ACC_THREADS - 1) / ACC_THREADS);
                 k_accumulate<C><<<blocks, ACC_THREADS, 0, stream>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, stream>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
             }
-            k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, stream>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
             tm.mark();
             err = cudaGetLastError();
         }
         if (err != cudaSuccess) break;
         uint32_t log2m = 0; while ((1u << log2m) < p.chunk) log2m++;
-        {
+        if (p.affine) {
+            const uint32_t last = p.rounds - 1;
+            k_bucket_reduce_affine<C><<<(p.chunks_ps + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, stream>>>(
+                ws + ((last & 1) ? p.off_aff_b : p.off_aff_a), (const uint32_t *)(ws + p.off_aff_offs) + (size_t)last * (p.nb + 1), p.chunk, p.chunks_ps, chunks);
+        } else {
             const uint32_t threads = p.sets * p.chunks_ps;
             k_bucket_reduce<C><<<(threads + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, stream>>>(slots, offsets, p.nb, p.seg_len, p.segs_ps,
                                                                                                    p.sets, p.chunks, p.chunk, p.chunks_ps, chunks);

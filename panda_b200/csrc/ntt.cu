@@ -31,7 +31,8 @@ namespace pb {
 static constexpr int NTT_THREADS = 256;
 static constexpr unsigned NTT_MAX_RADIX_LOG = 8;      // fft.cu:10 MAX_LOG2_RADIX
 static constexpr unsigned NTT_MAX_PARTS = 16;         // destination buffers of the exchange step (GPUs of one box)
-static constexpr unsigned NTT_DIRECT_LOG = 24;        // pass boundaries with at most 2^24 distinct twiddles get a direct table (<= 512 MiB; B200: 2^24 4.55 -> 4.33 ms wall)
+static constexpr unsigned NTT_DIRECT_LOG = 20;        // pass boundaries with at most 2^20 distinct twiddles get a direct table (32 MiB, L2-resident);
+                                                      // 2^24 entries (512 MiB) measured no better in steady state: 4.16 vs 4.10 ms at 2^24
 
 struct NttShape {
     unsigned log_n, passes;

@@ -387,3 +387,19 @@ def test_host_api_additions(oracle, dev):
         assert (y == x).all()
     finally:
         m.deinit()
+
+
+@pytest.mark.parametrize("k", [12, 15])
+def test_batched_affine_plan_opt_in(k):
+    """PANDA_MSM_AFFINE=1 (experimental plan, read once per process): tree rounds of batched affine additions with one field
+    inversion per round give the same point (closed form); tests/run_msm.py prints the verdict"""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PANDA_MSM_AFFINE="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "run_msm.py"), str(k), "1", "0", "0", "0", "2"], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "closed-form match: True" in out.stdout, out.stdout[-2000:]
