@@ -99,9 +99,9 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     // then CTAs of 256 threads stitch 1024 chunk sums each; more than 32 such groups get one more stitch level
     uint32_t m = pow2_floor(std::max<uint64_t>(1, ((uint64_t)p.sets * p.nb) / 262144));
     m = std::min<uint32_t>(std::min<uint32_t>(m, 32), p.nb);
-    // small bucket sets: the stitching is a chain of ~60 dependent point additions per level (0.55 ms), so folding up to 16 buckets per
-    // thread is worth it when it brings a set down to 32 groups of 1024 chunk sums (one stitch level instead of two)
-    if (p.nb / 16 <= 32768) m = std::max<uint32_t>(m, std::max<uint32_t>(1, p.nb / 32768));
+    // small bucket sets: the stitching is a chain of ~60 dependent point additions per level (0.55 ms), so folding up to 8 buckets per
+    // thread is worth it when it brings a set down to 32 groups of 1024 chunk sums (one stitch level instead of two; 16 per thread measured worse: 2^22 points, 1.77 vs 1.60 ms)
+    if (p.nb / 8 <= 32768) m = std::max<uint32_t>(m, std::max<uint32_t>(1, p.nb / 32768));
     p.chunk = m;
     p.chunks_ps = p.nb / m;
     p.groups = std::min<uint32_t>(256, std::max<uint32_t>(1, p.chunks_ps / 1024));
