@@ -333,6 +333,9 @@ static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, c
     return cudaSuccess;
 }
 
+static cudaError_t aux_stream_for_current_device(cudaStream_t *out);
+static uint32_t resident_chunks(uint32_t n);
+
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
                     cudaMemPool_t pool, cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings, int table_mode) {
     const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
@@ -345,25 +348,47 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
     uint32_t table_n = n;
     PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, c_override, &table, &tc, &table_n));
     if (table) {
-        MsmPlan p = msm_make_plan(curve, n, true, tc, seg_override);
+        // per-stage timings are an attribution pass over the unsplit pipeline; the product path splits large jobs in two chunks
+        const uint32_t chunks = timings ? 1 : resident_chunks(n);
+        MsmPlan p = msm_make_plan(curve, n, true, tc, seg_override, ~(size_t)0, chunks);
         p.table_n = table_n;
+        if (p.chunks > 1) {
+            MsmFeed feed{nullptr, nullptr, nullptr, nullptr};
+            PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
+            return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, nullptr, &feed);
+        }
         return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings);
     }
     MsmPlan p = msm_make_plan(curve, n, false, c_override <= 16 ? c_override : 0, seg_override);
     return run_pipeline(curve, p, bases, scalars, result, coord, pool, stream, timings);
 }
 
-// one copy stream per device for streamed scalars (created on first use, lives as long as the process)
-static cudaError_t copy_stream_for_current_device(cudaStream_t *out) {
+// per device: one copy stream (streamed scalars) and one auxiliary compute stream (chunk overlap), created on first use
+static cudaError_t side_stream_for_current_device(int which, cudaStream_t *out) {
     static std::mutex m;
-    static cudaStream_t streams[64] = {};
+    static cudaStream_t streams[2][64] = {};
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     std::lock_guard<std::mutex> lock(m);
-    if (!streams[dev]) PB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
-    *out = streams[dev];
+    if (!streams[which][dev]) {
+        int least = 0, greatest = 0;                       // the auxiliary compute stream outranks the caller's stream, so that its
+        PB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));   // (small) sort CTAs slot in between the accumulation CTAs
+        PB_CUDA(cudaStreamCreateWithPriority(&streams[which][dev], cudaStreamNonBlocking, which == 1 ? greatest : least));
+    }
+    *out = streams[which][dev];
     return cudaSuccess;
+}
+static cudaError_t copy_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(0, out); }
+static cudaError_t aux_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(1, out); }
+
+// chunks of a device-resident table-plan MSM.  Splitting in two (the second chunk's sort hides behind the first chunk's accumulation
+// on the higher-priority auxiliary stream) was measured at 2^24: the overlap wins 2 ms, the second set of partial sums costs 3
+// (40.7 vs 39.6 ms), so the default is one chunk; PANDA_MSM_SPLIT = q forces q chunks (tests, tuning).
+static uint32_t resident_chunks(uint32_t n) {
+    static const int forced = [] { const char *v = getenv("PANDA_MSM_SPLIT"); return v ? atoi(v) : 0; }();
+    (void)n;
+    return forced > 0 ? (uint32_t)forced : 1;
 }
 
 cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_scalars, uint32_t n, void *result, CoordType coord,
@@ -386,8 +411,9 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
         uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 19) ? 2 : 1);
         MsmPlan p = msm_make_plan(curve, n, true, tc, 0, ~(size_t)0, chunks);
         p.table_n = table_n;
-        MsmFeed feed{host_scalars, d_scal, nullptr};
+        MsmFeed feed{host_scalars, d_scal, nullptr, nullptr};
         e = copy_stream_for_current_device(&feed.copy_stream);
+        if (e == cudaSuccess) e = aux_stream_for_current_device(&feed.aux_stream);
         if (e == cudaSuccess) e = run_pipeline(curve, p, table, d_scal, result, coord, pool, stream, nullptr, &feed);
     } else {
         e = cudaMemcpyAsync(d_scal, host_scalars, (size_t)n * 32, cudaMemcpyHostToDevice, stream);

@@ -46,8 +46,9 @@ struct MsmPlan {
 MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget = ~(size_t)0,
                       uint32_t chunks = 1);
 
-// Scalars still in HOST memory: the pipeline uploads chunk q on copy_stream right before queueing chunk q's kernels.
-struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; };
+// How a chunked pipeline is fed: host_scalars != nullptr: chunk q is uploaded on copy_stream right before its kernels are queued;
+// aux_stream != nullptr: odd chunks run on it, so that one chunk's sort overlaps the previous chunk's accumulation.
+struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; cudaStream_t aux_stream; };
 
 // Per-stage device timings (ms) filled when msm_run is called with timings != nullptr (adds event syncs;
 // the benchmark harness uses it to attribute time to kernels -- never set on the product path).

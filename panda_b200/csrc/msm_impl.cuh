@@ -675,27 +675,39 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
     const size_t slot_stride = ((size_t)p.segs_ps + p.nb) * Pt::BYTES;       // per physical set
 
     StageTimer tm(timings != nullptr && p.chunks == 1, stream);
-    cudaEvent_t fed = nullptr;
+    // events: `fed` orders the copy stream against the compute streams; `sorted_ev` staggers the chunks (chunk q+1 starts sorting when
+    // chunk q starts accumulating, on the other stream, so that its atomics-bound sort hides behind integer-bound additions);
+    // `aux_done` joins the auxiliary stream back into `stream`
+    cudaEvent_t fed = nullptr, sorted_ev = nullptr, aux_done = nullptr;
+    const bool uploading = feed && feed->host_scalars;
+    cudaStream_t aux = (feed && p.chunks > 1) ? feed->aux_stream : nullptr;
     cudaError_t err = cudaSuccess;
     do {
         if ((err = cudaMemsetAsync(counts, 0, (phys * p.nb + p.chunks) * 4, stream)) != cudaSuccess) break;
-        if (feed) {
+        if (uploading || aux) {
             if ((err = cudaEventCreateWithFlags(&fed, cudaEventDisableTiming)) != cudaSuccess) break;
-            // the staging buffer was allocated in stream order on `stream`: the copy stream may only touch it from here on
+            // the workspace / staging buffer were allocated in stream order on `stream`: other streams may only touch them from here on
             if ((err = cudaEventRecord(fed, stream)) != cudaSuccess) break;
-            if ((err = cudaStreamWaitEvent(feed->copy_stream, fed, 0)) != cudaSuccess) break;
+            if (uploading && (err = cudaStreamWaitEvent(feed->copy_stream, fed, 0)) != cudaSuccess) break;
+            if (aux && (err = cudaStreamWaitEvent(aux, fed, 0)) != cudaSuccess) break;
+        }
+        if (aux) {
+            if ((err = cudaEventCreateWithFlags(&sorted_ev, cudaEventDisableTiming)) != cudaSuccess) break;
+            if ((err = cudaEventCreateWithFlags(&aux_done, cudaEventDisableTiming)) != cudaSuccess) break;
         }
         for (uint32_t q = 0; q < p.chunks && err == cudaSuccess; q++) {
+            cudaStream_t sq = (aux && (q & 1)) ? aux : stream;               // chunks alternate between the two streams
             const uint32_t point0 = q == 0 ? 0 : p.chunk_first + (q - 1) * p.chunk_n;
             const uint32_t nq = q == 0 ? p.chunk_first : std::min<uint32_t>(p.chunk_n, n - point0);
             const size_t set0 = (size_t)q * p.sets;                           // first physical set of this chunk
             const uint32_t *sc = (const uint32_t *)scalars + (size_t)point0 * 8;
-            if (feed) {
+            if (uploading) {
                 if ((err = cudaMemcpyAsync((uint8_t *)feed->dev_scalars + (size_t)point0 * 32, (const uint8_t *)feed->host_scalars + (size_t)point0 * 32,
                                            (size_t)nq * 32, cudaMemcpyHostToDevice, feed->copy_stream)) != cudaSuccess) break;
                 if ((err = cudaEventRecord(fed, feed->copy_stream)) != cudaSuccess) break;
-                if ((err = cudaStreamWaitEvent(stream, fed, 0)) != cudaSuccess) break;
+                if ((err = cudaStreamWaitEvent(sq, fed, 0)) != cudaSuccess) break;
             }
+            if (aux && q > 0 && (err = cudaStreamWaitEvent(sq, sorted_ev, 0)) != cudaSuccess) break;   // previous chunk is sorted
             uint32_t *counts_q = counts + set0 * p.nb, *offsets_q = offsets + set0 * (p.nb + 1), *cursor_q = cursor + set0 * p.nb;
             uint32_t *big_count_q = big_counts + q, *big_list_q = big_list + set0 * p.nb, *tiles_q = tile_sums + set0 * tiles_ps;
             uint8_t *codes_q = digits + (size_t)q * p.stride * 4;            // folded: 32-bit codes of this chunk (chunks == 1 otherwise)
@@ -703,17 +715,18 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             uint8_t *slots_q = slots + set0 * slot_stride;
             tm.mark();
             const uint32_t sblocks = std::min<uint32_t>((nq + 255) / 256, 148 * 8);
-            if (p.folded) k_digits<C, true><<<sblocks, 256, 0, stream>>>(sc, nq, p.c, p.windows, p.nb, codes_q, counts_q);
-            else k_digits<C, false><<<sblocks, 256, 0, stream>>>(sc, nq, p.c, p.windows, p.nb, codes_q, counts_q);
+            if (p.folded) k_digits<C, true><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.nb, codes_q, counts_q);
+            else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.nb, codes_q, counts_q);
             tm.mark();
-            k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, stream>>>(counts_q, p.nb, tiles_ps, tiles_q);
-            k_scan_tops<<<p.sets, 1024, 0, stream>>>(tiles_q, tiles_ps, p.nb, offsets_q);
-            k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, stream>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q, big_count_q, big_list_q);
+            k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, p.nb, tiles_ps, tiles_q);
+            k_scan_tops<<<p.sets, 1024, 0, sq>>>(tiles_q, tiles_ps, p.nb, offsets_q);
+            k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q, big_count_q, big_list_q);
             tm.mark();
             if (p.folded) {
                 uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
-                k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, stream>>>((const uint32_t *)codes_q, nq, p.windows, p.table_n, point0, log2_span, cursor_q, sorted_q);
-            } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, stream>>>((const uint16_t *)codes_q, nq, p.nb, cursor_q, sorted_q);
+                k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, sq>>>((const uint32_t *)codes_q, nq, p.windows, p.table_n, point0, log2_span, cursor_q, sorted_q);
+            } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, sq>>>((const uint16_t *)codes_q, nq, p.nb, cursor_q, sorted_q);
+            if (aux && (err = cudaEventRecord(sorted_ev, sq)) != cudaSuccess) break;
             tm.mark();
             if (p.affine) {
                 // tree rounds: every round halves the buckets with batched affine additions (one field inversion per round)
@@ -725,10 +738,10 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                     uint32_t *off_out = (uint32_t *)(ws + p.off_aff_offs) + (size_t)r * (p.nb + 1);
                     const uint64_t out_max = std::min<uint64_t>(in_max, in_max / 2 + p.nb);
                     const uint32_t ctas = (uint32_t)((out_max + AFF_PER_CTA - 1) / AFF_PER_CTA);
-                    aff_next_counts<<<std::min<uint32_t>((p.nb + 255) / 256, 148 * 8), 256, 0, stream>>>(off_in, p.nb, counts_q);
-                    k_scan_tiles<<<dim3(tiles_ps, 1), 1024, 0, stream>>>(counts_q, p.nb, tiles_ps, tiles_q);
-                    k_scan_tops<<<1, 1024, 0, stream>>>(tiles_q, tiles_ps, p.nb, off_out);
-                    k_scan_apply<<<dim3(tiles_ps, 1), 1024, 0, stream>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, off_out, nullptr, nullptr, nullptr);
+                    aff_next_counts<<<std::min<uint32_t>((p.nb + 255) / 256, 148 * 8), 256, 0, sq>>>(off_in, p.nb, counts_q);
+                    k_scan_tiles<<<dim3(tiles_ps, 1), 1024, 0, sq>>>(counts_q, p.nb, tiles_ps, tiles_q);
+                    k_scan_tops<<<1, 1024, 0, sq>>>(tiles_q, tiles_ps, p.nb, off_out);
+                    k_scan_apply<<<dim3(tiles_ps, 1), 1024, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, off_out, nullptr, nullptr, nullptr);
                     AffRound ar{};
                     ar.table = r == 0 ? (const uint8_t *)points : nullptr;
                     ar.entries = r == 0 ? sorted_q : nullptr;
@@ -738,22 +751,26 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                     ar.pre = ws + p.off_aff_pre; ar.tot = ws + p.off_aff_tot;
                     ar.cta_prod = cta_base; ar.cta_inv = cta_base + (size_t)p.aff_ctas * fe;
                     ar.nb = p.nb;
-                    aff_products<C><<<ctas, AFF_THREADS, 0, stream>>>(ar);
-                    aff_invert<C><<<1, 1024, 0, stream>>>(ar.cta_prod, ar.cta_inv, cta_base + (size_t)2 * p.aff_ctas * fe, ctas);
-                    aff_add<C><<<ctas, AFF_THREADS, 0, stream>>>(ar);
+                    aff_products<C><<<ctas, AFF_THREADS, 0, sq>>>(ar);
+                    aff_invert<C><<<1, 1024, 0, sq>>>(ar.cta_prod, ar.cta_inv, cta_base + (size_t)2 * p.aff_ctas * fe, ctas);
+                    aff_add<C><<<ctas, AFF_THREADS, 0, sq>>>(ar);
                     off_in = off_out;
                     in_max = out_max;
                 }
             } else {
                 const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
                 const uint32_t blocks = (uint32_t)((threads + ACC_THREADS - 1) / ACC_THREADS);
-                k_accumulate<C><<<blocks, ACC_THREADS, 0, stream>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
-                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, stream>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
+                k_accumulate<C><<<blocks, ACC_THREADS, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
             }
             tm.mark();
             err = cudaGetLastError();
         }
         if (err != cudaSuccess) break;
+        if (aux) {
+            if ((err = cudaEventRecord(aux_done, aux)) != cudaSuccess) break;
+            if ((err = cudaStreamWaitEvent(stream, aux_done, 0)) != cudaSuccess) break;
+        }
         uint32_t log2m = 0; while ((1u << log2m) < p.chunk) log2m++;
         if (p.affine) {
             const uint32_t last = p.rounds - 1;
@@ -781,6 +798,8 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         err = cudaGetLastError();
     } while (0);
     if (fed) cudaEventDestroy(fed);
+    if (sorted_ev) cudaEventDestroy(sorted_ev);
+    if (aux_done) cudaEventDestroy(aux_done);
     cudaError_t ferr = cudaFreeAsync(ws, stream);
     if (err == cudaSuccess) err = ferr;
     if (err != cudaSuccess) {

@@ -48,3 +48,12 @@ fn = ffi.lib.panda_msm_execute_bn254 if cid == 0 else ffi.lib.panda_msm_execute_
 for r in range(reps):
     e0.record(stream); rc = fn(cfg); e1.record(stream); e1.sync()
     assert rc == 0
+got_api = d_r.to_numpy()
+print("product path (panda_msm_execute_*) closed-form match:", bool((O.jac_to_affine(cid, got_api) == exp).all()))
+cu = C.CDLL("libcudart.so.12"); cu.cudaEventElapsedTime.argtypes = [C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+ms = C.c_float()
+ts = []
+for r in range(max(reps, 5)):
+    e0.record(stream); rc = fn(cfg); e1.record(stream); e1.sync()
+    cu.cudaEventElapsedTime(C.byref(ms), e0.handle, e1.handle); ts.append(round(ms.value, 3))
+print("product path device ms per call:", ts)

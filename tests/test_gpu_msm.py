@@ -403,3 +403,19 @@ def test_batched_affine_plan_opt_in(k):
                          text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "closed-form match: True" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("split", [2, 3])
+def test_split_pipeline_small(split):
+    """PANDA_MSM_SPLIT forces the two-stream chunked pipeline of large jobs (one chunk's sort overlapping the previous chunk's
+    accumulation) onto a small one; the product entry point must return the closed-form point"""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PANDA_MSM_SPLIT=str(split))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "run_msm.py"), "15", "1", "0", "0", "0", "2"], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "product path (panda_msm_execute_*) closed-form match: True" in out.stdout, out.stdout[-2000:]
