@@ -209,8 +209,20 @@ struct Fe {
     // -a in [0,2p):  2p - a  (a == 0 gives 2p ... folded back to 0 by the compare below)
     PB_DEV Fe neg() const { return zero() - *this; }
 
-    // Montgomery product, inputs < 2p, output < 2p.
+    // Montgomery product, inputs < 2p, output < 2p.  12-limb fields call it out of line: ten inlined 300-multiply products per point
+    // addition overflow the instruction cache (ncu on the BLS12-377 accumulation kernel: 1.0 stall cycles per issue waiting for
+    // instructions against 0.05 with 8 limbs), and a call costs far less than that.
     PB_DEV friend Fe operator*(const Fe &a, const Fe &b) {
+        if constexpr (N > 8) return mul_call(a, b);
+        else return mul_inline(a, b);
+    }
+    __device__ __noinline__ static Fe mul_call(Fe a, Fe b) { return mul_inline(a, b); }
+    __device__ __noinline__ static Fe sqr_call(Fe a) { return a.sqr_inline(); }
+    PB_DEV Fe sqr() const {
+        if constexpr (N > 8) return sqr_call(*this);
+        else return sqr_inline();
+    }
+    PB_DEV static Fe mul_inline(const Fe &a, const Fe &b) {
         // Two accumulators.  In the frame of the current row, A holds limb positions 0..N-1 as pairs
         // (0,1),(2,3),..  and B holds positions 1..N as pairs (1,2),(3,4),..   After the reduction step
         // A[0] == 0; dividing by 2^32 turns B into the even-aligned accumulator and A (shifted by two
@@ -242,7 +254,7 @@ struct Fe {
     // (a_i, 2a_{i+1}, (2a)_{i+2}, ..) and skips the columns below i, whose products the earlier rows already added twice.
     // N(N+1)/2 + N^2 + N multiply-adds instead of 2N^2 + N (108 vs 136 for N = 8); the skipped columns become carry-only adds.
     // Needs the top bit of the top limb clear (2a must fit N limbs): true for every value < 2p here.
-    PB_DEV Fe sqr() const {
+    PB_DEV Fe sqr_inline() const {
         uint32_t A[N], B[N], a2[N];
         a2[0] = 0;
         _Pragma("unroll") for (int j = 1; j < N; j++) a2[j] = __funnelshift_l(l[j - 1], l[j], 1);

@@ -758,9 +758,11 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                     in_max = out_max;
                 }
             } else {
+                // 12-limb fields (186 registers per thread): 64-thread CTAs fit 5 per SM (10 warps) where 128-thread ones fit 2 (8 warps)
+                const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
                 const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
-                const uint32_t blocks = (uint32_t)((threads + ACC_THREADS - 1) / ACC_THREADS);
-                k_accumulate<C><<<blocks, ACC_THREADS, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                const uint32_t blocks = (uint32_t)((threads + acc_threads - 1) / acc_threads);
+                k_accumulate<C><<<blocks, acc_threads, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
                 k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
             }
             tm.mark();
