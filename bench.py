@@ -32,6 +32,10 @@ MADD_MODMULS = 10            # XYZZ mixed addition: 8M + 2S
 NCU_ACCUMULATE_TRAFFIC_BYTES = 27.50e9   # k_accumulate at 2^24 (table plan), dram__bytes_read.sum + dram__bytes_write.sum per launch
 
 
+def ntt_passes_count(k: int) -> int:
+    return (k + 7) // 8
+
+
 def kernels_per_msm(plan) -> int:
     """our launches in one device-resident MSM: [fingerprint] digits, scan x3, scatter, accumulate, reduce_big, bucket_reduce,
     group_reduce (x2 when there are more than 32 groups), final"""
@@ -403,6 +407,9 @@ def run_own_arm(args):
     # butterflies + pass-boundary twiddles: boundary 1 (2^24 distinct exponents) composes two table entries (2 products),
     # boundary 2 (2^16 distinct) reads a direct table (1 product)
     ntt_modmuls = (1 << k) // 2 * k + (2 + 1) * (1 << k)
+    ntt_alg_modmuls = (1 << k) // 2 * k                      # (n/2) log2 n products
+    # executed: the last stage of every pass has unit twiddles (no product): 3 passes x 7 stages x n/2 + 3n boundary products
+    ntt_exec_modmuls = ntt_passes_count(k) * 0 + ((k - ntt_passes_count(k)) * ((1 << k) // 2)) + 3 * (1 << k)
     ntt_passes = (k + 7) // 8
 
     cpu = cpu_baseline_leg(O, np)
@@ -438,7 +445,13 @@ def run_own_arm(args):
         "step_ms_rank0": [round(x, 3) for x in per_step],
         "ntt": {"metric": "bn254_fr_ntt_2^24_latency", "ms": ntt_ms, "passes": ntt_passes, "modmul_per_s": ntt_modmuls / (ntt_ms * 1e-3),
                 "frac_of_modmul_peak": ntt_modmuls / (ntt_ms * 1e-3) / modmul_peak, "hbm_GBps": ntt_passes * 64 * (1 << k) / (ntt_ms * 1e-3) / 1e9,
-                "frac_of_hbm_peak": ntt_passes * 64 * (1 << k) / (ntt_ms * 1e-3) / 1e9 / hbm_peak},
+                "frac_of_hbm_peak": ntt_passes * 64 * (1 << k) / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
+                "roofline": {"bound": "int32-imad", "unit": "G modmul/s", "peak": modmul_peak / 1e9,
+                             "achieved": ntt_alg_modmuls / (ntt_ms * 1e-3) / 1e9, "frac": ntt_alg_modmuls / (ntt_ms * 1e-3) / modmul_peak,
+                             "algorithmic": "(n/2) log2 n Montgomery products (SURVEY 8d)",
+                             "executed_modmul_per_s": ntt_exec_modmuls / (ntt_ms * 1e-3),
+                             "executed_frac": ntt_exec_modmuls / (ntt_ms * 1e-3) / modmul_peak,
+                             "peak_source": "BN254 Montgomery-product microbenchmark, measured live (panda_debug_int_peak kind 2)"}},
         "cpu_baseline": cpu,
     }
     if sharded_ntt is not None:
