@@ -120,6 +120,23 @@ def test_reference_host_path_random_k10(oracle):
         assert (mine == oracle.msm_reference(0, bases, scal, k, 0)).all()
 
 
+def test_reference_host_path_config1_k16(oracle):
+    """BASELINE.json config 1: BN254 G1 MSM n = 2^16, random scalars, through the reference's own host (CPU debug) path -- the top of the
+    range its test sweeps (tests/test.rs:116-117).  arkworks is not buildable here; its role is played by the closed form of the
+    synthetic bases and by the restatement's fast MSM (both pinned to arkworks through the golden k13 vector).  About 30 s, one core."""
+    if oracle.build_ref() is None:
+        pytest.skip("oracle/_ref not built and /root/reference not available")
+    k, n = 16, 1 << 16
+    bases = oracle.gen_bases(0, oracle.seed_for(k), n)
+    scal = oracle.gen_scalars(1, oracle.seed_for(k) + 1, n)
+    keep = scal.copy()
+    ref, _ms = oracle.ref_host_msm(bases, scal, k)
+    assert (scal == keep).all()                                         # our driver hands the reference a copy (it converts in place)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, oracle.seed_for(k), scal, n))
+    assert (oracle.jac_to_affine(0, ref) == exp).all()
+    assert (oracle.jac_to_affine(0, oracle.msm(0, bases, scal, n, c=13)) == exp).all()
+
+
 @pytest.mark.parametrize("cid,k,c", [(0, 8, 7), (0, 12, 11), (0, 14, 13), (1, 10, 9), (1, 12, 16)])
 def test_fast_msm_equals_closed_form(oracle, cid, k, c):
     """po_msm with any window width equals the O(n) closed form for progression bases, on both curves."""
