@@ -176,6 +176,10 @@ panda_error panda_intt_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cf
  * x_i = g^-i * INTT(y)_i; same omega / flag contract as panda_ntt_execute_bn254_v1. */
 panda_error panda_ntt_coset_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cfg, const void *coset_gen, int inverse);
 
+/* Bit-reversal permutation of 2^log_n Fr elements, out of place: d_dst[bitrev(i)] = d_src[i].  Together with the natural-order
+ * transforms it gives the natural-in / reversed-out (and reversed-in / natural-out) variants provers ask for. */
+panda_error panda_ntt_bit_reverse_bn254(const void *d_src, void *d_dst, unsigned log_n, panda_stream stream);
+
 /* Batched transform: `batch` independent 2^log_n-point (I)NTTs stored back to back in d_src (d_dst: same size); same omega /
  * flag contract as panda_ntt_execute_bn254_v1 (flag tells which buffer holds all `batch` results).  inverse != 0: omega^-1 and
  * the 1/2^log_n scale.  Building block of polynomial-batch provers and of the multi-GPU four-step transform. */

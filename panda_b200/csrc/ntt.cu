@@ -387,6 +387,39 @@ __global__ void __launch_bounds__(256) k_ntt_coset_scale(uint32_t *__restrict__ 
     }
 }
 
+// ---- bit-reversal permutation (natural <-> bit-reversed order variants of the transforms) ------------------------
+// dst[bitrev_k(i)] = src[i].  Tiles of 32 x 32 elements: i = (a, m, b) with a and b the top and bottom 5 bits; a tile fixes m, reads rows
+// (a fixed, b running: 1 KiB runs) and writes rows of the reversed index (rev(b) fixed, rev(a) running: 1 KiB runs) through
+// shared memory.  HBM-bound: 32 B read + 32 B written per element.
+template <class P>
+__global__ void __launch_bounds__(256) k_ntt_bit_reverse(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, unsigned log_n) {
+    using F = Fe<P>;
+    __shared__ uint32_t sm[F::N * 32 * 33];
+    if (log_n < 10) {                                        // small sizes: one element per thread, no tiling
+        const uint32_t n = 1u << log_n;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const uint32_t j = log_n ? __brev(i) >> (32 - log_n) : 0;
+            F::load(src + (size_t)i * F::N).store(dst + (size_t)j * F::N);
+        }
+        return;
+    }
+    const unsigned mid_bits = log_n - 10;
+    const uint32_t m = blockIdx.x;                           // middle bits
+    const uint32_t rm = mid_bits ? __brev(m) >> (32 - mid_bits) : 0;
+    for (uint32_t e = threadIdx.x; e < 1024; e += blockDim.x) {
+        const uint32_t a = e >> 5, b = e & 31;
+        const size_t i = ((size_t)a << (log_n - 5)) | ((size_t)m << 5) | b;
+        sm_store(sm, 32 * 33, a * 33 + b, F::load(src + i * F::N));
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < 1024; e += blockDim.x) {
+        const uint32_t rb = e >> 5, ra = e & 31;              // output row = rev(b), column = rev(a)
+        const uint32_t a = __brev(ra) >> 27, b = __brev(rb) >> 27;
+        const size_t j = ((size_t)rb << (log_n - 5)) | ((size_t)rm << 5) | ra;
+        sm_load<F>(sm, 32 * 33, a * 33 + b).store(dst + j * F::N);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 
 struct NttCacheEntry {
@@ -555,6 +588,14 @@ cudaError_t ntt_coset_scale(NttField field, void *d_data, unsigned log_n, const 
     const uint32_t n = 1u << log_n;
     k_ntt_coset_scale<Bn254Fr><<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256, 0, stream>>>((uint32_t *)d_data, n, tab->d_tab + tab->layout.off_lo,
                                                                                                 tab->d_tab + tab->layout.off_hi, tab->layout.lo_bits);
+    return cudaGetLastError();
+}
+
+cudaError_t ntt_bit_reverse(NttField field, const void *d_src, void *d_dst, unsigned log_n, cudaStream_t stream) {
+    (void)field;
+    if (!d_src || !d_dst || d_src == d_dst || log_n > 30) return cudaErrorInvalidValue;
+    const uint32_t blocks = log_n < 10 ? std::max<uint32_t>(1, (1u << log_n) / 256) : (1u << (log_n - 10));
+    k_ntt_bit_reverse<Bn254Fr><<<blocks, 256, 0, stream>>>((const uint32_t *)d_src, (uint32_t *)d_dst, log_n);
     return cudaGetLastError();
 }
 

@@ -31,6 +31,9 @@ cudaError_t ntt_exchange(NttField field, const void *d_src, unsigned log_rows, u
 // d_data[i] *= g^i (inverse: g^-i) for i < 2^log_n; gen_host: HOST pointer to the coset generator g (Montgomery).
 cudaError_t ntt_coset_scale(NttField field, void *d_data, unsigned log_n, const void *gen_host, bool inverse, cudaStream_t stream);
 
+// d_dst[bitrev(i)] = d_src[i] (out of place): turns natural-order data into bit-reversed order and back
+cudaError_t ntt_bit_reverse(NttField field, const void *d_src, void *d_dst, unsigned log_n, cudaStream_t stream);
+
 // frees the cached twiddle tables of every device
 cudaError_t ntt_release_tables();
 

@@ -219,6 +219,9 @@ panda_error panda_ntt_coset_execute_bn254_v1(const panda_ntt_configuration_v1 cf
     if (e == cudaSuccess && inverse) e = pb::ntt_coset_scale(pb::NTT_BN254_FR, in_dst ? cfg.d_dst : cfg.d_src, cfg.log_n, coset_gen, true, cu(cfg.stream));
     return perr(e);
 }
+panda_error panda_ntt_bit_reverse_bn254(const void *d_src, void *d_dst, unsigned log_n, panda_stream stream) {
+    return perr(pb::ntt_bit_reverse(pb::NTT_BN254_FR, d_src, d_dst, log_n, cu(stream)));
+}
 panda_error panda_ntt_exchange_bn254(const panda_ntt_exchange_configuration *cfg) {
     if (!cfg) return perr(cudaErrorInvalidValue);
     return perr(pb::ntt_exchange(pb::NTT_BN254_FR, cfg->d_src, cfg->log_rows, cfg->log_cols, cfg->row_offset, cfg->omega, cfg->log_n, cfg->inverse != 0,

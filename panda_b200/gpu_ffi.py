@@ -252,6 +252,7 @@ SIGNATURES: dict[str, list] = {
     "panda_msm_combine_bn254": [_vp, _uint, _vp, _int, PandaStream],
     "panda_msm_combine_bls12_377": [_vp, _uint, _vp, _int, PandaStream],
     "panda_intt_execute_bn254_v1": [NttconfigurationV1],
+    "panda_ntt_bit_reverse_bn254": [_vp, _vp, _uint, PandaStream],
     "panda_ntt_coset_execute_bn254_v1": [NttconfigurationV1, _vp, _int],
     "panda_ntt_batch_execute_bn254_v1": [NttconfigurationV1, _uint, _int],
     "panda_ntt_exchange_bn254": [C.POINTER(NttExchangeConfiguration)],

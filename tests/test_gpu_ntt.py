@@ -143,3 +143,28 @@ def test_coset_transforms(oracle, dev, k):
     assert ffi.lib.panda_ntt_coset_execute_bn254_v1(cfg, gg.ctypes.data, 1) == 0
     assert ((b2 if flag.value else a2).to_numpy(x.size) == x).all()
     assert ffi.lib.panda_ntt_coset_execute_bn254_v1(cfg, None, 0) != 0
+
+
+@pytest.mark.parametrize("k", [0, 1, 5, 9, 10, 11, 16, 21])
+def test_bit_reverse_permutation(oracle, dev, k):
+    """panda_ntt_bit_reverse_bn254: dst[bitrev(i)] = src[i]; applying it twice is the identity"""
+    ffi, gu = dev
+    n = 1 << k
+    x = oracle.gen_scalars(1, 8800 + k, n)
+    rev = np.array([int(format(i, f"0{k}b")[::-1], 2) if k else 0 for i in range(n)], dtype=np.int64) if k <= 16 else None
+    a, b, c = gu.DevBuf.from_numpy(x), gu.DevBuf(x.size), gu.DevBuf(x.size)
+    s = ffi.PandaStream.null()
+    assert ffi.lib.panda_ntt_bit_reverse_bn254(a.ptr, b.ptr, k, s) == 0
+    assert ffi.lib.panda_ntt_bit_reverse_bn254(b.ptr, c.ptr, k, s) == 0
+    assert ffi.lib.panda_stream_synchronize(s) == 0
+    y = b.to_numpy(x.size).reshape(n, 32)
+    if rev is not None:
+        exp = np.empty((n, 32), np.uint8)
+        exp[rev] = x.reshape(n, 32)
+        assert (y == exp).all()
+    else:                                                     # spot checks
+        for i in (0, 1, 2, n // 2, n - 1, 0x12345):
+            j = int(format(i, f"0{k}b")[::-1], 2)
+            assert (y[j] == x.reshape(n, 32)[i]).all()
+    assert (c.to_numpy(x.size) == x).all()
+    assert ffi.lib.panda_ntt_bit_reverse_bn254(a.ptr, a.ptr, k, s) != 0          # in place is refused
