@@ -8,7 +8,7 @@
 //   src/gpu_manager/unit.rs:10-543  panda_msm_bn254_gpu{,_with_cached_bases,_with_cached_scalars,_with_cached_input,_host},
 //                                   panda_ntt_bn254_gpu{,_v1}
 // Same argument meaning and error behaviour (a Rust Err(PandaGpuError::X) is a thrown PandaGpuException{X}).  Deliberate
-// fixes, each marked "fix:" below: the result staging buffer is freed (unit.rs:67-74 leaks it), the result buffer is
+// fixes, each marked "fix:" below: no pinned result staging buffer per call (unit.rs:67-74 allocates and leaks one), the result buffer is
 // allocated on the stream that writes it (unit.rs:33-40 allocates on h2d_stream), the NTT waits for
 // its upload before executing (unit.rs:426-453 does not).
 #pragma once
@@ -270,12 +270,9 @@ inline std::vector<uint8_t> msm_execute_and_fetch(const PandaGpuManager &gm, voi
     if (scalars_on_host) check(panda_msm_execute_bn254_host_scalars(cfg, (size_t)1 << log_scalars_count), PandaGpuError::SchedulingErr);
     else check(panda_msm_execute_bn254(cfg), PandaGpuError::SchedulingErr);
     std::vector<uint8_t> out(result_buf_len);
-    void *h = nullptr;
-    check(panda_malloc_host(&h, result_buf_len), PandaGpuError::CreateContextError);
-    panda_error rc = panda_memcpy_async(h, d_result, result_buf_len, gm.get_exec_stream().raw);
+    // fix: unit.rs:67-74 allocates (and leaks) a pinned staging buffer per call; 96 bytes go straight into the result vector
+    panda_error rc = panda_memcpy_async(out.data(), d_result, result_buf_len, gm.get_exec_stream().raw);
     if (rc == panda_success) rc = panda_stream_synchronize(gm.get_exec_stream().raw);               // unit.rs:60-62 + :76
-    if (rc == panda_success) memcpy(out.data(), h, result_buf_len);
-    panda_free_host(h);                                                                            // fix: unit.rs:67-74 leaks this buffer
     if (rc != panda_success) throw PandaGpuException(PandaGpuError::CreateContextError);
     if (free_scalars) free_async(d_scalars, gm.get_exec_stream());
     if (free_bases) free_async(d_bases, gm.get_exec_stream());
