@@ -419,3 +419,48 @@ def test_split_pipeline_small(split):
                          text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "product path (panda_msm_execute_*) closed-form match: True" in out.stdout, out.stdout[-2000:]
+
+
+def test_randomised_differential(oracle, dev):
+    """40 seeded random cases against the oracle: ragged sizes, scalars mixing 0 / 1 / r-1 / small / random, bases with identities,
+    duplicates and negated pairs, windowed and table plans, both output coordinates, device-resident and host (streamed) scalars"""
+    import random
+
+    ffi, gu = dev
+    rng = random.Random(20261018)
+    one = oracle.field_const(1, 1)
+    minus_one = oracle.f_neg(1, one)
+    s = ffi.PandaStream.new()
+    for case in range(40):
+        n = rng.choice([1, 2, 3, 31, 32, 33, 255, 1000, 1023, 1024, 1025, 2047, 4097, 6000])
+        bases = oracle.gen_bases(0, 700 + case, n).reshape(n, 64).copy()
+        scal = oracle.gen_scalars(1, 800 + case, n).reshape(n, 32).copy()
+        for i in range(n):
+            r = rng.random()
+            if r < 0.05: scal[i] = 0
+            elif r < 0.10: scal[i] = one
+            elif r < 0.15: scal[i] = minus_one
+            elif r < 0.25:
+                small = np.zeros(32, np.uint8); small[0] = rng.randrange(256); small[1] = rng.randrange(4)
+                scal[i] = oracle.f_to_mont(1, small)
+            r = rng.random()
+            if r < 0.03: bases[i] = 0
+            elif r < 0.08 and i: bases[i] = bases[rng.randrange(i)]
+            elif r < 0.12 and i:
+                j = rng.randrange(i)
+                bases[i] = bases[j]; bases[i, 32:] = oracle.f_neg(0, bases[j, 32:].copy())
+        exp = oracle.jac_to_affine(0, oracle.msm(0, bases.reshape(-1), scal.reshape(-1), n, c=rng.choice([4, 7, 10])))
+        coord = rng.randrange(2)
+        mode = rng.choice([0, 2])
+        d_b, d_r = gu.DevBuf.from_numpy(bases.reshape(-1)), gu.DevBuf(96)
+        if rng.random() < 0.5:
+            d_s = gu.DevBuf.from_numpy(scal.reshape(-1))
+            cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, d_s.ptr, d_r.ptr, 0, coord)
+            assert ffi.lib.panda_debug_msm_timed(0, cfg, n, 0, 0, mode, None, None) == 0
+        else:
+            hs = np.ascontiguousarray(scal.reshape(-1))
+            cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, hs.ctypes.data, d_r.ptr, 0, coord)
+            assert ffi.lib.panda_debug_msm_streamed(0, cfg, n, mode, rng.choice([0, 1, 2, 3])) == 0
+        s.sync()
+        assert (affine(oracle, 0, d_r.to_numpy(), coord) == exp).all(), (case, n, coord, mode)
+    assert ffi.lib.panda_msm_tear_down() == 0
