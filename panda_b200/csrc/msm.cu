@@ -22,8 +22,8 @@ cudaError_t msm_pipeline_bn254(const MsmPlan &p, const void *points, const void 
                                cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed);
 cudaError_t msm_pipeline_bls12_377(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
                                    cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed);
-cudaError_t msm_build_table_bn254(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream);
-cudaError_t msm_build_table_bls12_377(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream);
+cudaError_t msm_build_table_bn254(const void *bases, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, void *table, cudaStream_t stream);
+cudaError_t msm_build_table_bls12_377(const void *bases, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, void *table, cudaStream_t stream);
 cudaError_t msm_fingerprint_launch(const void *data, size_t bytes, unsigned long long *d_out, cudaStream_t stream);
 cudaError_t msm_combine_bn254(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream);
 cudaError_t msm_combine_bls12_377(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream);
@@ -37,6 +37,18 @@ static uint32_t windows_for(uint32_t bits, uint32_t c) {
     int t = (int)bits - (int)(W - 1) * (int)c;
     if (t > (int)c - 1) W++;
     return W;
+}
+
+// Table plan: W = ceil((bits + 1) / c) windows whose widths add up to exactly bits + 1 (one spare bit for the recoding carry): the low
+// `wide` windows are c bits, the others c - 1.  No window is short, so no bucket range collects a whole window's digits.
+// Returns false when c - 1 would do (wide <= 0): that plan is the one of c - 1.
+static bool balanced_windows(uint32_t bits, uint32_t c, uint32_t *W, uint32_t *wide) {
+    const uint32_t total = bits + 1;
+    *W = (total + c - 1) / c;
+    const int w = (int)total - (int)(*W) * (int)(c - 1);
+    if (w <= 0) return false;
+    *wide = (uint32_t)w;
+    return true;
 }
 
 static uint32_t pow2_floor(uint64_t v) { uint32_t r = 1; while ((uint64_t)r * 2 <= v) r *= 2; return r; }
@@ -53,7 +65,9 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     double best = 1e300;
     for (uint32_t c = c_lo; c <= c_hi; c++) {
         if (c_override && c != c_override) continue;
-        const double W = windows_for(bits, c), nb = (double)(1u << (c - 1));
+        uint32_t Wi = windows_for(bits, c), widei = Wi;
+        if (folded && !balanced_windows(bits, c, &Wi, &widei)) continue;
+        const double W = Wi, nb = (double)(1u << (c - 1));
         if (W > 32) continue;
         if (folded) {
             if ((double)n * W >= 2147483648.0) continue;                            // table index + sign must fit 32 bits
@@ -64,13 +78,15 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
         // A narrow top window (t bits) sends n digits to 2^t buckets: their counters are hot L2-atomic addresses in the histogram and
         // scatter kernels (measured at n = 2^21, t = 7: +0.6 ms, i.e. ~20 modmul-equivalents per scalar), ~2500 / 2^t per scalar.
         const int t = (int)bits - (int)(W - 1) * (int)c;
-        const double hot = t > 0 && t < 20 ? (double)n * 2500.0 / (double)(1u << t) : 0.0;
+        const double hot = !folded && t > 0 && t < 20 ? (double)n * 2500.0 / (double)(1u << t) : 0.0;   // the table plan has no short window
         const double cost = (double)n * W * 10.0 + (folded ? 1.0 : W) * nb * 3.5 * 14.0 * 2.0 + hot;
         if (cost < best) { best = cost; best_c = c; }
     }
     if (!best_c) { p.c = 0; return p; }                         // no feasible plan (folded table would not fit)
     p.c = best_c;
     p.windows = windows_for(bits, p.c);
+    p.wide = p.windows;
+    if (folded) balanced_windows(bits, p.c, &p.windows, &p.wide);
     p.nb = 1u << (p.c - 1);
     p.sets = folded ? 1 : p.windows;
     // chunks (folded only): every chunk is a physical bucket set of its own (counts, sorted list, partial slots); the bucket
@@ -222,8 +238,8 @@ static cudaError_t build_table_locked(TableEntry *hit, CurveId curve, const void
     if (!fp_plan.c) return cudaSuccess;                // no table fits: stay on the windowed path
     void *tab = nullptr;
     if (cudaMalloc(&tab, fp_plan.table_bytes) != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
-    cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, tab, stream)
-                                              : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, tab, stream);
+    cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, tab, stream)
+                                              : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, tab, stream);
     cudaEvent_t ev = nullptr;
     if (be == cudaSuccess) be = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (be == cudaSuccess) be = cudaEventRecord(ev, stream);

@@ -19,6 +19,7 @@ struct MsmPlan {
     uint32_t table_n;      // folded: row length of the table (>= n: an MSM may use a prefix of a registered base set)
     uint32_t c;            // window width in bits (signed digits)
     uint32_t windows;      // W digit windows per scalar
+    uint32_t wide;         // windows 0 .. wide-1 are c bits wide, the others c-1 (table plan: balanced windows); W for uniform windows
     uint32_t nb;           // buckets per bucket set = 2^(c-1)
     uint32_t folded;       // 1: precomputed 2^(c*j)*P table, every window feeds ONE bucket set; 0: one bucket set per window
     uint32_t sets;         // bucket sets: 1 (folded) or W

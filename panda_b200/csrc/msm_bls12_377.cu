@@ -7,8 +7,8 @@ cudaError_t msm_pipeline_bls12_377(const MsmPlan &p, const void *points, const v
                             cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed) {
     return msm_pipeline_t<Bls377>(p, points, scalars, result, coord, pool, stream, timings, feed);
 }
-cudaError_t msm_build_table_bls12_377(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream) {
-    return msm_build_table_t<Bls377>(bases, n, c, W, table, stream);
+cudaError_t msm_build_table_bls12_377(const void *bases, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, void *table, cudaStream_t stream) {
+    return msm_build_table_t<Bls377>(bases, n, c, W, wide, table, stream);
 }
 cudaError_t msm_combine_bls12_377(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream) {
     return msm_combine_t<Bls377>(partials, count, result, coord, stream);

@@ -7,8 +7,8 @@ cudaError_t msm_pipeline_bn254(const MsmPlan &p, const void *points, const void 
                             cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed) {
     return msm_pipeline_t<Bn254>(p, points, scalars, result, coord, pool, stream, timings, feed);
 }
-cudaError_t msm_build_table_bn254(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream) {
-    return msm_build_table_t<Bn254>(bases, n, c, W, table, stream);
+cudaError_t msm_build_table_bn254(const void *bases, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, void *table, cudaStream_t stream) {
+    return msm_build_table_t<Bn254>(bases, n, c, W, wide, table, stream);
 }
 cudaError_t msm_combine_bn254(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream) {
     return msm_combine_t<Bn254>(partials, count, result, coord, stream);

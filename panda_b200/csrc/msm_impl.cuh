@@ -31,19 +31,20 @@ static constexpr uint32_t BIG_SPAN = 8;             // buckets with more partial
 
 // ----------------------------------------------------------------------------------------------------
 // Signed-digit recoding of one canonical scalar, shared by the histogram and the scatter kernels.
-// Calls f(window, magnitude (1 .. 2^(c-1)), negative) for every non-zero digit.
+// Windows 0 .. wide-1 are c bits wide, the others c-1 (the table plan balances its windows this way so that no window is short;
+// wide = W gives uniform windows).  Calls f(window, magnitude (1 .. 2^(width-1)), negative) for every non-zero digit.
 template <class Fr, class F>
-PB_DEV void for_each_digit(Fr s, uint32_t c, uint32_t W, uint32_t nb, F &&f) {
+PB_DEV void for_each_digit(Fr s, uint32_t c, uint32_t W, uint32_t wide, F &&f) {
     uint32_t carry = 0;
-    const uint32_t mask = (1u << c) - 1;
     for (uint32_t w = 0; w < W; w++) {
-        uint32_t v = (s.l[0] & mask) + carry;
+        const uint32_t cw = w < wide ? c : c - 1;
+        const uint32_t v = (s.l[0] & ((1u << cw) - 1)) + carry;
 #pragma unroll
-        for (int k = 0; k < Fr::N - 1; k++) s.l[k] = __funnelshift_r(s.l[k], s.l[k + 1], c);
-        s.l[Fr::N - 1] >>= c;
+        for (int k = 0; k < Fr::N - 1; k++) s.l[k] = __funnelshift_r(s.l[k], s.l[k + 1], cw);
+        s.l[Fr::N - 1] >>= cw;
         uint32_t mag = v, neg = 0;
         carry = 0;
-        if (w + 1 < W && v > nb) { mag = (1u << c) - v; neg = 1; carry = 1; }   // the top window is never recoded
+        if (w + 1 < W && v > (1u << (cw - 1))) { mag = (1u << cw) - v; neg = 1; carry = 1; }   // the top window is never recoded
         if (mag) f(w, mag, neg);
     }
 }
@@ -54,7 +55,7 @@ PB_DEV void for_each_digit(Fr s, uint32_t c, uint32_t W, uint32_t nb, F &&f) {
 // HBM / L2-atomic bound: 32 B read + 2W (4W) B written per scalar, W reductions into an L2-resident histogram.
 static constexpr uint32_t CODE_SKIP32 = 0xFFFFFFFFu;
 template <class C, bool FOLDED>
-__global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb,
+__global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, uint32_t nb,
                                                 void *__restrict__ codes_out, uint32_t *__restrict__ counts) {
     using Fr = typename C::Fr;
     using Code = typename std::conditional<FOLDED, uint32_t, uint16_t>::type;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; the input is left untouched
         uint32_t next_w = 0;
-        for_each_digit(s, c, W, nb, [&](uint32_t w, uint32_t mag, uint32_t neg) {
+        for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t mag, uint32_t neg) {
             for (; next_w < w; next_w++) codes[(size_t)next_w * n + i] = SKIP;
             codes[(size_t)w * n + i] = (Code)((mag - 1) | (neg << SIGN_BIT));
             next_w = w + 1;
@@ -556,11 +557,12 @@ __global__ void __launch_bounds__(32) k_final(const uint8_t *__restrict__ gsums,
 }
 
 // ---- precomputed tables for reused bases ------------------------------------------------------------------------
-// table[j*n + i] = 2^(c*j) * P_i (affine), j < W: every window then feeds ONE bucket set and the final Horner disappears.
+// table[j*n + i] = 2^(o_j) * P_i (affine), j < W, o_j = total width of windows 0 .. j-1 (c*j for uniform windows): every window then feeds ONE bucket set and the final Horner disappears.
 // One thread per point: (W-1)*c Jacobian doublings, the W-1 intermediate points kept in local memory, one shared inversion
 // (Montgomery's trick) to normalise them.  Run once per cached base set (~10 MSMs worth of arithmetic).
 template <class C>
-__global__ void __launch_bounds__(128) k_build_table(const uint8_t *__restrict__ bases, uint32_t n, uint32_t c, uint32_t W, uint8_t *__restrict__ table) {
+__global__ void __launch_bounds__(128) k_build_table(const uint8_t *__restrict__ bases, uint32_t n, uint32_t c, uint32_t W, uint32_t wide,
+                                                     uint8_t *__restrict__ table) {
     using Fq = typename C::Fq;
     using Af = Affine<Fq>;
     constexpr int MAXW = 32;
@@ -582,8 +584,9 @@ __global__ void __launch_bounds__(128) k_build_table(const uint8_t *__restrict__
     Fq run = Fq::one();
 #pragma unroll 1
     for (uint32_t j = 1; j < W; j++) {
+        const uint32_t cw = j - 1 < wide ? c : c - 1;          // width of window j-1: row j = 2^(width of the windows below) * P
 #pragma unroll 1
-        for (uint32_t k = 0; k < c; k++) q = q.dbl();
+        for (uint32_t k = 0; k < cw; k++) q = q.dbl();
         pts[j] = q;
         prefix[j] = run;                   // product of z_1 .. z_{j-1}
         run = run * q.z;
@@ -715,8 +718,8 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             uint8_t *slots_q = slots + set0 * slot_stride;
             tm.mark();
             const uint32_t sblocks = std::min<uint32_t>((nq + 255) / 256, 148 * 8);
-            if (p.folded) k_digits<C, true><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.nb, codes_q, counts_q);
-            else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.nb, codes_q, counts_q);
+            if (p.folded) k_digits<C, true><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, codes_q, counts_q);
+            else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, codes_q, counts_q);
             tm.mark();
             k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, p.nb, tiles_ps, tiles_q);
             k_scan_tops<<<p.sets, 1024, 0, sq>>>(tiles_q, tiles_ps, p.nb, offsets_q);
@@ -819,8 +822,8 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
 }
 
 template <class C>
-cudaError_t msm_build_table_t(const void *bases, uint32_t n, uint32_t c, uint32_t W, void *table, cudaStream_t stream) {
-    k_build_table<C><<<(n + 127) / 128, 128, 0, stream>>>((const uint8_t *)bases, n, c, W, (uint8_t *)table);
+cudaError_t msm_build_table_t(const void *bases, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, void *table, cudaStream_t stream) {
+    k_build_table<C><<<(n + 127) / 128, 128, 0, stream>>>((const uint8_t *)bases, n, c, W, wide, (uint8_t *)table);
     return cudaGetLastError();
 }
 
