@@ -443,19 +443,21 @@ PB_DEV Xyzz<F> mul_pow2(Xyzz<F> p, uint32_t log2k) {
 //   lane 0 returns  sumP = sum_l P_l,  sumR = sum_l R_l,  wR = sum_l l * R_l
 // (suffix running sums by shuffle: sum_l l*R_l = sum_{l>=1} sum_{j>=l} R_j).
 template <class F>
-PB_DEV void warp_running_sums(Xyzz<F> &P, Xyzz<F> &R, Xyzz<F> &wR, uint32_t lane) {
+PB_DEV void warp_running_sums(Xyzz<F> &P, Xyzz<F> &R, Xyzz<F> &wR, uint32_t lane, uint32_t active = 32) {
+    // `active` (a power of two): lanes at and above it hold the identity, so the scans and trees can stop early -- each step is a
+    // dependent point addition, the unit these latency-bound kernels are made of
 #pragma unroll 1
-    for (int o = 1; o < 32; o <<= 1) {                 // inclusive suffix scan of R
-        Xyzz<F> t = shfl_down_pt(R, o);
-        if (lane + o < 32) add_cold(R, t);
+    for (uint32_t o = 1; o < active; o <<= 1) {         // inclusive suffix scan of R
+        Xyzz<F> t = shfl_down_pt(R, (int)o);
+        if (lane + o < active) add_cold(R, t);
     }
     wR = lane ? R : Xyzz<F>::identity();
 #pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) {                 // tree sums
-        Xyzz<F> t = shfl_down_pt(wR, o);
-        if (lane + o < 32) add_cold(wR, t);
-        Xyzz<F> u = shfl_down_pt(P, o);
-        if (lane + o < 32) add_cold(P, u);
+    for (uint32_t o = active >> 1; o > 0; o >>= 1) {    // tree sums
+        Xyzz<F> t = shfl_down_pt(wR, (int)o);
+        if (lane + o < active) add_cold(wR, t);
+        Xyzz<F> u = shfl_down_pt(P, (int)o);
+        if (lane + o < active) add_cold(P, u);
     }
 }
 
@@ -507,7 +509,7 @@ __global__ void __launch_bounds__(WIN_THREADS) k_group_reduce(const uint8_t *__r
             R2 = Pt::load(sh + (size_t)lane * 2 * Pt::BYTES + Pt::BYTES);
         }
         Pt wR2;
-        warp_running_sums(P2, R2, wR2, lane);
+        warp_running_sums(P2, R2, wR2, lane, WIN_THREADS / 32);
         if (lane == 0) {
             add_cold(P2, mul_pow2(wR2, log2m + log2q + 5));
             uint8_t *out = gsums + ((size_t)set * groups + g) * 2 * Pt::BYTES;
@@ -536,7 +538,8 @@ __global__ void __launch_bounds__(32) k_final(const uint8_t *__restrict__ gsums,
             R = Pt::load(in + Pt::BYTES);
         }
         if (groups > 1) {
-            warp_running_sums(P, R, wR, lane);
+            uint32_t active = 1; while (active < groups) active <<= 1;
+            warp_running_sums(P, R, wR, lane, active);
             if (lane == 0) add_cold(P, mul_pow2(wR, log2_group_unit));
         }
         if (lane == 0) {
