@@ -795,7 +795,10 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         k_group_reduce<C><<<dim3(p.groups, p.sets), WIN_THREADS, 0, stream>>>(chunks, p.chunks_ps, cpg, log2m, gsums);
         const uint8_t *final_in = gsums;
         uint32_t final_groups = p.groups, final_unit = log2m + log2cpg;
-        if (p.groups > 32) {       // second stitch level: the group sums of a set are the items of ONE more CTA (unit = m * cpg)
+        // second stitch level: the group sums of a set are the items of ONE more CTA (unit = m * cpg).  Needed beyond 32 groups, and worth it
+        // whenever there are several bucket sets (windowed plan): the sets are stitched side by side instead of one after the other by
+        // the single warp of k_final
+        if (p.groups > 32 || (p.sets > 1 && p.groups > 1)) {
             uint8_t *gsums2 = gsums + (size_t)p.sets * p.groups * 2 * Pt::BYTES;
             k_group_reduce<C><<<dim3(1, p.sets), WIN_THREADS, 0, stream>>>(gsums, p.groups, p.groups, final_unit, gsums2);
             final_in = gsums2; final_groups = 1;
