@@ -120,7 +120,9 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     if (p.nb / 8 <= 32768) m = std::max<uint32_t>(m, std::max<uint32_t>(1, p.nb / 32768));
     p.chunk = m;
     p.chunks_ps = p.nb / m;
-    p.groups = std::min<uint32_t>(256, std::max<uint32_t>(1, p.chunks_ps / 1024));
+    // at most one stitching CTA per SM over all sets (128 for one set): with 256 two of them share an SM and the latency-bound chains slow each other down
+    // (measured at 2^24: 0.84 ms for 256 CTAs of 1024 chunk sums, against 0.42 ms for the single CTA of the next level)
+    p.groups = std::min<uint32_t>(pow2_floor(std::max<uint32_t>(1, 148 / p.sets)), std::max<uint32_t>(1, p.chunks_ps / 1024));
     // folded scatter passes: the slice of the sorted list written by one pass should stay in L2 (126 MB); measured on B200 at
     // 2^24 (768 MiB list): 8 passes 4.1 ms, 16 passes 5.5 ms, 32 passes 8.3 ms, 1 pass 7.1 ms -- each pass re-reads the codes
     p.phases = 1;
