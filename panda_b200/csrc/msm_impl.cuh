@@ -212,7 +212,7 @@ static __global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *_
 // K4: bucket accumulation.  Thread (w, s) owns sorted entries [s*L, (s+1)*L) of bucket set w -- a fixed amount
 // of work whatever the bucket sizes are -- and emits one partial sum per bucket it touches into slot
 // (s + bucket), which is unique and makes a bucket's partials contiguous.
-// IMAD-bound: 10 modmul = 1370 IMAD per entry; 4 B index + 64 B (96 B) gathered point read per entry.
+// IMAD-bound: 8 products + 2 squares = 1314 IMAD-class instructions per entry (8 limbs); 4 B index + 64 B (96 B) gathered point per entry.
 template <class C>
 __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                            const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
@@ -354,7 +354,7 @@ PB_DEV Xyzz<F> shfl_down_pt(const Xyzz<F> &p, int delta) {
     return r;
 }
 
-// K4b: oversized buckets (more than BIG_SPAN partial slots: the top window's buckets in table mode, skewed scalars) are folded
+// K4b: oversized buckets (more than BIG_SPAN partial slots: skewed scalars, or a short top window of the windowed plan) are folded
 // into their first slot before the bucket reduction.  One warp per bucket (lanes stride over the slots, shuffle tree);
 // buckets with more than BIG_WARP_SPAN slots get the whole CTA (strided serial sums, a shuffle tree per warp, one across warps).
 static constexpr uint32_t BIG_WARP_SPAN = 2048;
@@ -519,7 +519,8 @@ __global__ void __launch_bounds__(WIN_THREADS) k_group_reduce(const uint8_t *__r
     }
 }
 
-// K7: one warp.  Per bucket set: S_set = sum_g S_g + (m * cpg) * sum_g g * Rtot_g (one more shuffle stitch over <= 32 groups);
+// K7: one warp.  Per bucket set: S_set = sum_g S_g + (m * cpg) * sum_g g * Rtot_g (one more shuffle stitch over <= 32 groups; with
+// several sets or more groups a second k_group_reduce level has done this already and groups == 1 here);
 // then Horner over the sets (windowed mode: (W-1)*c dependent Jacobian doublings, inherent to the window method; folded
 // mode: a single set, no doublings), conversion to the reference's result coordinates, canonical store.
 template <class C>
@@ -560,7 +561,8 @@ __global__ void __launch_bounds__(32) k_final(const uint8_t *__restrict__ gsums,
 }
 
 // ---- precomputed tables for reused bases ------------------------------------------------------------------------
-// table[j*n + i] = 2^(o_j) * P_i (affine), j < W, o_j = total width of windows 0 .. j-1 (c*j for uniform windows): every window then feeds ONE bucket set and the final Horner disappears.
+// table[j*n + i] = 2^(o_j) * P_i (affine), j < W, o_j = total width of windows 0 .. j-1 (c*j for uniform windows): every window then
+// feeds ONE bucket set and the final Horner disappears.
 // One thread per point: (W-1)*c Jacobian doublings, the W-1 intermediate points kept in local memory, one shared inversion
 // (Montgomery's trick) to normalise them.  Run once per cached base set (~10 MSMs worth of arithmetic).
 template <class C>
@@ -660,8 +662,9 @@ struct StageTimer {
 };
 
 // Runs the pipeline described by `p`.  `points` is the caller's bases (windowed) or the precomputed table (folded).
-// feed != nullptr: the scalars are still in host memory; chunk q is uploaded on feed->copy_stream right before chunk q's kernels
-// are queued, so the upload of chunk q+1 overlaps the sort / accumulation of chunk q.
+// feed != nullptr: chunked run.  With feed->host_scalars the scalars are still in host memory and chunk q is uploaded on
+// feed->copy_stream right before chunk q's kernels are queued (the upload of chunk q+1 overlaps the work on chunk q); with
+// feed->aux_stream odd chunks run on that stream, staggered so that a chunk sorts while the previous one accumulates.
 template <class C>
 cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
                            cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed) {
