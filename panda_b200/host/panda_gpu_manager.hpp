@@ -95,7 +95,11 @@ inline void memcpy_async(void *dst, const void *src, size_t size, const PandaStr
 }
 inline void free_async(void *ptr, const PandaStream &stream) { check(panda_free_async(ptr, stream.raw), PandaGpuError::AsyncMemcopyErr); }
 
-enum class PandaGpuManagerInitUnitType { None, MSM, NTT, ALL };   // wrapper.rs:23-29
+enum class PandaGpuManagerInitUnitType {   // wrapper.rs:23-29 (the long spellings are the Rust variant names)
+    None, MSM, NTT, ALL,
+    PandaGpuManagerInitUnitTypeNone = None, PandaGpuManagerInitUnitTypeMSM = MSM, PandaGpuManagerInitUnitTypeNTT = NTT,
+    PandaGpuManagerInitUnitTypeALL = ALL
+};
 
 struct ByteSlice { const uint8_t *data = nullptr; size_t len = 0; };
 
