@@ -199,7 +199,19 @@ static __global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *_
         };
         if ((nq & 3u) == 0) {
             const uint4 *c4 = reinterpret_cast<const uint4 *>(cw);
-            for (uint32_t q = tid; q < nq / 4; q += nthreads) {
+            const uint32_t nv = nq / 4;
+            uint32_t q = tid;
+            // four independent 16-byte loads in flight per thread: a pass is a stream of the codes with a returning atomic and a
+            // dependent store on one code in `phases`, so it is bound by memory latency, not by bandwidth
+            for (; q + 3 * nthreads < nv; q += 4 * nthreads) {
+                const uint4 v0 = __ldg(c4 + q), v1 = __ldg(c4 + q + nthreads), v2 = __ldg(c4 + q + 2 * nthreads), v3 = __ldg(c4 + q + 3 * nthreads);
+                place(v0.x, 4 * q); place(v0.y, 4 * q + 1); place(v0.z, 4 * q + 2); place(v0.w, 4 * q + 3);
+                const uint32_t q1 = q + nthreads, q2 = q + 2 * nthreads, q3 = q + 3 * nthreads;
+                place(v1.x, 4 * q1); place(v1.y, 4 * q1 + 1); place(v1.z, 4 * q1 + 2); place(v1.w, 4 * q1 + 3);
+                place(v2.x, 4 * q2); place(v2.y, 4 * q2 + 1); place(v2.z, 4 * q2 + 2); place(v2.w, 4 * q2 + 3);
+                place(v3.x, 4 * q3); place(v3.y, 4 * q3 + 1); place(v3.z, 4 * q3 + 2); place(v3.w, 4 * q3 + 3);
+            }
+            for (; q < nv; q += nthreads) {
                 const uint4 v = __ldg(c4 + q);
                 place(v.x, 4 * q); place(v.y, 4 * q + 1); place(v.z, 4 * q + 2); place(v.w, 4 * q + 3);
             }
