@@ -253,12 +253,17 @@ def run_own_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-timed K steps
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # clocks / throttle reasons are sampled from before the warm-up to the end of the timed region (nvidia-smi needs a few hundred
+    # milliseconds to deliver its first line, longer than a short timed region); idle samples are dropped by ClockSampler.stop()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        t_wait = time.time()
+        while sampler.proc is not None and not sampler.rows and time.time() - t_wait < 2.0:
+            time.sleep(0.02)
+    for _ in range(args.warmup):
+        step()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
