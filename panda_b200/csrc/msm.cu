@@ -230,8 +230,7 @@ static cudaError_t run_pipeline(CurveId curve, const MsmPlan &p, const void *poi
     return msm_pipeline_bn254(p, points, scalars, result, coord, pool, stream, timings, feed);
 }
 
-// Looks `bases` up in the table cache (building the table when the mode asks for it).  On return *table is the table to use
-// (with its window width in *tc and `stream` already waiting for the build) or nullptr: stay on the windowed path.
+// Builds the table of `hit` on `stream` (caller holds g_table_mutex).  Not fitting in memory is not an error: the entry stays table-less.
 static cudaError_t build_table_locked(TableEntry *hit, CurveId curve, const void *bases, uint32_t n, uint32_t c_override, cudaStream_t stream) {
     size_t free_b = 0, total_b = 0;
     PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -292,6 +291,8 @@ cudaError_t msm_unregister_bases(const void *bases) {
     return cudaSuccess;                                // unknown pointer: nothing to do (idempotent)
 }
 
+// Looks `bases` up in the table cache (building the table when the mode asks for it).  On return *table is the table to use
+// (with its window width in *tc, its row length in *table_n and `stream` already waiting for the build) or nullptr: stay on the windowed path.
 static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, cudaStream_t stream, int table_mode, uint32_t c_override,
                                  const void **table, uint32_t *tc, uint32_t *table_n) {
     *table = nullptr;
