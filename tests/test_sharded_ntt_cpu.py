@@ -103,7 +103,7 @@ def _worker(rank, world, port, k, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,k", [(1, 5), (2, 6), (2, 9), (4, 8)])
+@pytest.mark.parametrize("world,k", [(1, 5), (2, 6), (2, 9), (4, 8), (8, 8)])
 def test_sharded_ntt_gloo(world, k):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
