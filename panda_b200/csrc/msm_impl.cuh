@@ -226,9 +226,9 @@ static __global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *_
 // (s + bucket), which is unique and makes a bucket's partials contiguous.
 // IMAD-bound: 8 products + 2 squares = 1314 IMAD-class instructions per entry (8 limbs); 4 B index + 64 B (96 B) gathered point per entry.
 template <class C>
-__global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
-                                                           const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
-                                                           uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
+PB_DEV void accumulate_body(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                            const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
+                            uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
     using Fq = typename C::Fq;
     using Pt = Xyzz<Fq>;
     using Af = Affine<Fq>;
@@ -272,6 +272,20 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint8_t *__res
         acc.madd(p.x, p.y);
     }
     acc.store(slot_w + (size_t)b * Pt::BYTES);
+}
+
+template <class C>
+__global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                                                           const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
+                                                           uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
+    accumulate_body<C>(bases, sorted, offsets, stride, nb, L, segs_pw, W, slots);
+}
+// 12-limb fields: 64-thread CTAs, five per SM (204 registers) -- ten warps per SM instead of the eight that 222 registers allow
+template <class C>
+__global__ void __launch_bounds__(64, 5) k_accumulate_wide(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                                                          const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
+                                                          uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
+    accumulate_body<C>(bases, sorted, offsets, stride, nb, L, segs_pw, W, slots);
 }
 
 // K5: bucket combine + first level of the running-sum reduction.  Thread (w, t) folds buckets
@@ -783,7 +797,8 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                 const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
                 const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
                 const uint32_t blocks = (uint32_t)((threads + acc_threads - 1) / acc_threads);
-                k_accumulate<C><<<blocks, acc_threads, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                else k_accumulate<C><<<blocks, acc_threads, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
                 k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
             }
             tm.mark();
