@@ -288,6 +288,9 @@ __global__ void __launch_bounds__(64, 5) k_accumulate_wide(const uint8_t *__rest
     accumulate_body<C>(bases, sorted, offsets, stride, nb, L, segs_pw, W, slots);
 }
 
+template <class F>
+__device__ __noinline__ void add_cold(Xyzz<F> &a, const Xyzz<F> &b);      // defined with the stitching kernels below
+
 // K5: bucket combine + first level of the running-sum reduction.  Thread (w, t) folds buckets
 // [t*m, (t+1)*m) of logical set w from the top: B_j = sum of its partial slots over all `merge` chunks (physical set
 // q * W + w holds chunk q's partials), run += B_j, tri += run.
@@ -318,11 +321,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const uint8_t *__
 #pragma unroll 1
                 for (uint32_t sg = s0; sg <= s1; sg++) {
                     Pt part = Pt::load(slot_w + ((size_t)sg + j) * Pt::BYTES);
-                    run.add(part);
+                    if constexpr (Fq::N > 8) add_cold(run, part); else run.add(part);   // 12 limbs: out of line (255 registers + spills otherwise)
                 }
             }
         }
-        tri.add(run);
+        if constexpr (Fq::N > 8) add_cold(tri, run); else tri.add(run);
     }
     uint8_t *out = chunks + (size_t)gid * 2 * Pt::BYTES;
     tri.store(out);
