@@ -1,4 +1,4 @@
-"""world_size-2 gloo test (CPU) of the sharded-MSM host logic: contiguous point ranges, one all-gather of the 96-byte
+"""gloo tests (CPU, world size 2 / 4 / 8) of the sharded-MSM host logic: contiguous point ranges, one all-gather of the 96-byte
 partials, combine.  The per-rank MSM and the combine are host stand-ins (the oracle) injected into ShardedMsm, so this
 exercises exactly the partition / gather plumbing the GPU path uses, without a device."""
 import os
@@ -55,12 +55,12 @@ def _worker(rank, world, port, n, k, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [1 << 9, 777])
-def test_sharded_msm_world2_gloo(n):
-    world, k = 2, 9
+@pytest.mark.parametrize("world,n", [(2, 1 << 9), (2, 777), (4, 1000), (8, 1 << 9)])
+def test_sharded_msm_gloo(world, n):
+    k = 9
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    port = 29500 + (os.getpid() % 2000) + world
     procs = [ctx.Process(target=_worker, args=(r, world, port, n, k, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -69,4 +69,4 @@ def test_sharded_msm_world2_gloo(n):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok and okp for _r, ok, okp, _b in results)
-    assert results[0][3] == results[1][3]       # every rank holds the same combined bytes
+    assert all(r[3] == results[0][3] for r in results)       # every rank holds the same combined bytes
