@@ -40,8 +40,8 @@ typedef struct panda_debug_msm_plan_info {
 panda_error panda_debug_msm_plan(int curve_id, size_t n, int folded, unsigned c_override, unsigned seg_override, panda_debug_msm_plan_info *out);
 
 /* MSM with explicit window width / segment length / table mode and per-stage device times.
- * table_mode: -1 default (env PANDA_MSM_PRECOMPUTE, else auto), 0 never use tables, 1 auto (table after the second sighting of the
- * same bases), 2 eager (table at first sight).
+ * table_mode: -1 default (env PANDA_MSM_PRECOMPUTE, else 3), 0 never use tables, 1 auto (unannounced bases get a table after their second
+ * sighting with the same fingerprint), 2 eager (table at first sight), 3 tables only for registered base sets.
  * stage_ms (HOST float[7], may be NULL): digits, scan, scatter, accumulate, bucket_reduce, window_reduce, final.
  * info (HOST unsigned[3], may be NULL): folded, window bits, windows actually used.
  * Synchronises the stream when stage_ms or info is given. */
@@ -56,6 +56,10 @@ panda_error panda_debug_msm_streamed(int curve_id, const panda_msm_configuration
  * 4 independent chains per thread.  Fills *ms (device time of the timed launch) and *ops (instructions of that kind /
  * modular products executed). */
 panda_error panda_debug_int_peak(int kind, unsigned iters, float *ms, unsigned long long *ops);
+
+/* out = omega^(2^k) for a BN254 Fr element, HOST pointers, Montgomery in / out: the host-side helper the multi-GPU NTT derives its
+ * sub-roots with (no device involved) */
+panda_error panda_debug_fr_pow2k_host(const void *omega, unsigned k, void *out);
 
 #ifdef __cplusplus
 }

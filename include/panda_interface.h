@@ -6,11 +6,13 @@
  * Plain pointers and sizes only; every function returns panda_error: 0 on success, otherwise the raw
  * cudaError_t value (reference convention, panda_interface.cu:11-191; Rust only tests `!= 0`).
  *
- * Device pointers are owned by the caller.  Inputs (bases, scalars, d_src when the result lands in d_dst)
- * are never written: the reference converts scalars in place (msm_cuda.cuh:155, msm_host.cuh:293-296) and
- * thereby corrupts cached scalars on their second use -- this implementation does not.
+ * Device pointers are owned by the caller.  MSM inputs (bases, scalars) are never written: the reference converts
+ * scalars in place (msm_cuda.cuh:155, msm_host.cuh:293-296) and thereby corrupts cached scalars on their second
+ * use -- this implementation does not.  The NTT entry points use d_src and d_dst as ping-pong storage exactly like the
+ * reference's pass loop (fft.cu:193-211): after the call the buffer *flag names holds the result and the other one is
+ * scratch (d_src keeps its contents only for single-pass sizes, log_n <= 8).
  * MSM execution is asynchronous on cfg.stream (the Rust caller records + syncs an event on it afterwards,
- * gpu_manager/unit.rs:60-62); temporaries are allocated stream-ordered from cfg.mem_pool.
+ * gpu_manager/unit.rs:60-62) and never blocks the host; temporaries are allocated stream-ordered from cfg.mem_pool.
  * All calls act on the calling thread's current device (the reference hard-codes device 0,
  * msm_cuda.cuh:554-555).
  */
@@ -137,6 +139,7 @@ panda_error panda_ntt_tear_down(void);
 /* BLS12-377 G1: bases 96 B (x||y, 12 x u32 each), scalars 32 B (Fr, 253 bit), result 144 B. */
 panda_error panda_msm_setup_bls12_377(void);
 panda_error panda_msm_execute_bls12_377(const panda_msm_configuration exec_cfg);
+panda_error panda_msm_execute_bls12_377_host(const panda_msm_configuration exec_cfg);   /* HOST pointers, 144-byte Jacobian result; see panda_msm_execute_bn254_host */
 
 /* MSM over an arbitrary point count (a shard of a larger MSM): like panda_msm_execute_* but n need not be a
  * power of two; cfg.log_scalars_count is ignored. */
@@ -145,9 +148,11 @@ panda_error panda_msm_execute_bls12_377_n(const panda_msm_configuration exec_cfg
 
 /* init_msm for cached bases (wrapper.rs:122-152 keeps the device pointer and reuses it across calls): announces that the n
  * affine points at d_bases stay unchanged until panda_msm_unregister_bases / panda_msm_tear_down.  The library builds its
- * table of 2^(c*j) * P multiples right away (asynchronous on `stream`; W * n * 64 bytes of HBM) and every later MSM on d_bases
- * -- or on a prefix of it -- runs the one-bucket-set pipeline without the content fingerprint (and its host synchronisation)
- * that unannounced pointers get.  Re-registering a pointer replaces the old entry. */
+ * table of 2^(c*j) * P multiples right away (asynchronous on `stream`; W * n * 64 bytes of HBM, capped by PANDA_MSM_TABLE_BUDGET
+ * [GiB], default half of the free memory beyond a 4 GiB reserve) and every later MSM on d_bases -- or on a prefix of it -- runs the
+ * one-bucket-set pipeline.  Pointers that were never announced run the windowed pipeline: an execute call never allocates a
+ * table or synchronises the host on its own (PANDA_MSM_PRECOMPUTE=1 opts unannounced pointers into automatic tables at the price
+ * of a content fingerprint + 8-byte read-back per call).  Re-registering a pointer replaces the old entry. */
 panda_error panda_msm_register_bases_bn254(const void *d_bases, size_t n, panda_stream stream);
 panda_error panda_msm_register_bases_bls12_377(const void *d_bases, size_t n, panda_stream stream);
 panda_error panda_msm_unregister_bases(const void *d_bases);
@@ -173,7 +178,8 @@ panda_error panda_intt_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cf
 
 /* Coset transforms (what a PLONK / halo2 prover calls around its quotient polynomial; no reference precedent): with coset
  * generator g (HOST pointer, 32 B Montgomery) forward computes y = NTT(x_i * g^i), inverse != 0 computes
- * x_i = g^-i * INTT(y)_i; same omega / flag contract as panda_ntt_execute_bn254_v1. */
+ * x_i = g^-i * INTT(y)_i; same omega / flag contract as panda_ntt_execute_bn254_v1.  The forward pre-scaling is done in place
+ * in d_src (both buffers are work storage, see the note at the top). */
 panda_error panda_ntt_coset_execute_bn254_v1(const panda_ntt_configuration_v1 exec_cfg, const void *coset_gen, int inverse);
 
 /* Bit-reversal permutation of 2^log_n Fr elements, out of place: d_dst[bitrev(i)] = d_src[i].  Together with the natural-order
@@ -206,6 +212,42 @@ typedef struct panda_ntt_exchange_configuration {
     size_t col_offset;
 } panda_ntt_exchange_configuration;
 panda_error panda_ntt_exchange_bn254(const panda_ntt_exchange_configuration *cfg);
+
+/* ---- multi-GPU entry points: ONE process drives several GPUs of one box (the reference is
+ * single-device -- cudaSetDevice(0) in msm_cuda.cuh:554-555, "Supports one GPU by default" wrapper.rs:38 -- but its bindings
+ * already declare the peer-access calls such a caller needs, binding.rs:54-56).  The device of each shard is taken from its
+ * pointers; the calls are asynchronous on the per-device streams, ordered across devices by events, and leave the caller's current
+ * device unchanged. ---- */
+
+/* MSM sharded by contiguous point range: per_device[d] describes shard d exactly like panda_msm_execute_bn254 (bases / scalars /
+ * results on GPU d, a stream and a pool of that GPU, 2^log_scalars_count points; the _n variants take the point counts instead).
+ * Every GPU runs the whole pipeline on its shard (one host thread per GPU queues the work); the 96-byte Jacobian partials are copied
+ * peer-to-peer to the first shard's GPU and summed there.  On completion per_device[0].results holds the total in
+ * per_device[0].msm_result_coordinate_type; per_device[d > 0].results hold shard d's Jacobian partial.  Completion is ordered on
+ * per_device[0].stream. */
+panda_error panda_msm_execute_bn254_multi(const panda_msm_configuration *per_device, int n_dev);
+panda_error panda_msm_execute_bn254_multi_n(const panda_msm_configuration *per_device, const size_t *counts, int n_dev);
+panda_error panda_msm_execute_bls12_377_multi(const panda_msm_configuration *per_device, int n_dev);
+panda_error panda_msm_execute_bls12_377_multi_n(const panda_msm_configuration *per_device, const size_t *counts, int n_dev);
+
+/* Four-step NTT n = n1 * n2 (n1 = 2^floor(log_n / 2)) sharded over n_dev GPUs (a power of two <= 16, n_dev <= n1) with ONE exchange:
+ * local transpose, batched n1-point transforms, panda_ntt_exchange_bn254 storing over NVLink straight into the peers' d_dst
+ * (peer access is enabled by the call), batched n2-point transforms.
+ *   forward: d_src[g] = column block g of the natural-order n1 x n2 matrix x[i1 * n2 + i2] (columns g * n2/G ..), row-major, not written;
+ *            d_dst[g] = row block g of the result: element [j1l][j2] = X[(g * n1/G + j1l) + n1 * j2].
+ *   inverse (inverse != 0): takes that row-block layout in d_src and returns the column blocks of (1/n) * DFT_{omega^-1} in d_dst,
+ *            so forward -> pointwise work -> inverse needs no re-shuffle.
+ * omega: HOST pointer, primitive 2^log_n-th root.  Each shard is n / n_dev elements; scratch (2 x shard) comes from each GPU's default pool. */
+typedef struct panda_ntt_multi_configuration {
+    unsigned n_dev;
+    const panda_stream *streams;    /* HOST array: one stream per GPU */
+    void *const *d_src;             /* HOST array of n_dev DEVICE pointers */
+    void *const *d_dst;             /* HOST array of n_dev DEVICE pointers (plain cudaMalloc / panda_malloc memory: written by the peers) */
+    const void *omega;
+    unsigned log_n;
+    int inverse;
+} panda_ntt_multi_configuration;
+panda_error panda_ntt_execute_bn254_multi(const panda_ntt_multi_configuration *cfg);
 
 /* Library identification: "panda-b200 <version> sm_100a". */
 const char *panda_version(void);

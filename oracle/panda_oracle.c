@@ -717,20 +717,40 @@ int po_ntt(int fid, void *data, unsigned log_n, const void *omega_mont) {
     return 0;
 }
 /* one output of the DFT by its definition: out = sum_i x[i] * omega^(i*j)  (O(n)) */
+/* y[j] = sum_i x[i] * omega^(i*j) straight from the definition; the index range is cut into 256 blocks (each starts its
+ * running power at omega^(j*lo)), the blocks are spread over the host threads and their partial sums added in order */
+typedef struct { const fctx *f; const uint8_t *data; u64 wj[MAXL]; size_t n; u64 part[256][MAXL]; } dft_ctx;
+static void f_pow_u64(const fctx *f, u64 *out, const u64 *base, u64 e) {
+    u64 b[MAXL], r[MAXL]; memcpy(b, base, sizeof b); memcpy(r, f->one, sizeof r);
+    for (; e; e >>= 1) { if (e & 1) f_mul(f, r, r, b); f_sqr(f, b, b); }
+    memcpy(out, r, sizeof r);
+}
+static void dft_body(long lo, long hi, void *vctx) {
+    dft_ctx *c = (dft_ctx *)vctx; const fctx *f = c->f; const int nl = f->nl;
+    for (long blk = lo; blk < hi; blk++) {
+        const size_t i0 = c->n * (size_t)blk / 256, i1 = c->n * (size_t)(blk + 1) / 256;
+        u64 cur[MAXL], acc[MAXL] = {0};
+        f_pow_u64(f, cur, c->wj, (u64)i0);
+        for (size_t i = i0; i < i1; i++) {
+            u64 x[MAXL], t[MAXL]; ld_f(f, x, c->data + i * 8 * (size_t)nl);
+            f_mul(f, t, x, cur); f_add(f, acc, acc, t);
+            f_mul(f, cur, cur, c->wj);
+        }
+        memcpy(c->part[blk], acc, sizeof acc);
+    }
+}
 void po_dft_at(int fid, const void *data, unsigned log_n, const void *omega_mont, size_t j, void *out) {
     ensure_fields(); const fctx *f = &FIELDS[fid];
-    const int nl = f->nl; const size_t n = (size_t)1 << log_n;
-    u64 w[MAXL], wj[MAXL], cur[MAXL], acc[MAXL] = {0};
+    const size_t n = (size_t)1 << log_n;
+    dft_ctx *c = (dft_ctx *)calloc(1, sizeof(dft_ctx));
+    u64 w[MAXL], acc[MAXL] = {0};
     ld_f(f, w, (const uint8_t *)omega_mont);
-    memcpy(wj, f->one, sizeof wj);                                 /* wj = omega^j */
-    { u64 b[MAXL]; memcpy(b, w, sizeof b); for (size_t e = j; e; e >>= 1) { if (e & 1) f_mul(f, wj, wj, b); f_sqr(f, b, b); } }
-    memcpy(cur, f->one, sizeof cur);
-    for (size_t i = 0; i < n; i++) {
-        u64 x[MAXL], t[MAXL]; ld_f(f, x, (const uint8_t *)data + i * 8 * (size_t)nl);
-        f_mul(f, t, x, cur); f_add(f, acc, acc, t);
-        f_mul(f, cur, cur, wj);
-    }
+    c->f = f; c->data = (const uint8_t *)data; c->n = n;
+    f_pow_u64(f, c->wj, w, (u64)j);                                /* wj = omega^j */
+    parallel_for(256, n < 65536 ? 1 : 0, dft_body, c);
+    for (int b = 0; b < 256; b++) f_add(f, acc, acc, c->part[b]);
     st_f(f, (uint8_t *)out, acc);
+    free(c);
 }
 /* base^(2^k) by k squarings (Montgomery) -- omega for size 2^log_n from the 2^28-th root */
 void po_f_pow2k(int fid, const void *base, unsigned k, void *out) {

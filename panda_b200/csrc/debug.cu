@@ -1,6 +1,6 @@
 // debug.cu -- diagnostic kernels behind include/panda_debug.h: single-operation field / curve checks for the parity
 // tests and integer-pipe microbenchmarks for the roofline denominators.
-#include "../../include/panda_debug.h"
+#include "panda_debug.h"
 #include "ec.cuh"
 
 #include <cuda_runtime.h>

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -175,6 +176,22 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
 // ----------------------------------------------------------------------------------------------------
 // table cache for reused bases
 
+// The table itself is reference counted: an MSM holds a reference from the lookup until its kernels are queued, so that a concurrent
+// unregister / tear_down / eviction on another thread cannot free it in between (cudaFree waits for work that is already queued).
+struct TableBuf {
+    int device = 0;
+    void *ptr = nullptr;
+    cudaEvent_t ready = nullptr;    // recorded after the build; other streams wait on it
+    ~TableBuf() {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
+        if (ptr) cudaFree(ptr);     // synchronises with outstanding work on the buffer
+        if (ready) cudaEventDestroy(ready);
+        if (cur != device) cudaSetDevice(cur);
+    }
+};
+
 struct TableEntry {
     int device;
     CurveId curve;
@@ -183,10 +200,9 @@ struct TableEntry {
     unsigned long long fingerprint;
     unsigned sightings;
     bool registered;        // announced by msm_register_bases: immutable until unregistered, no fingerprint needed
-    void *table;            // nullptr until built
+    std::shared_ptr<TableBuf> table;     // empty until built
     uint32_t c, windows;
     size_t bytes;
-    cudaEvent_t ready;      // recorded after the build; other streams wait on it
     unsigned long long last_use;
 };
 
@@ -195,10 +211,7 @@ static std::vector<TableEntry> g_tables;
 static unsigned long long g_use_clock = 0;
 static constexpr size_t MAX_TABLES = 4;
 
-static void drop_table(TableEntry &e) {
-    if (e.table) { cudaFree(e.table); e.table = nullptr; }      // cudaFree waits for outstanding work on the buffer
-    if (e.ready) { cudaEventDestroy(e.ready); e.ready = nullptr; }
-}
+static void drop_table(TableEntry &e) { e.table.reset(); }
 
 cudaError_t msm_release_tables() {     // the current device's tables (panda_msm_tear_down: one MSM unit per device)
     std::lock_guard<std::mutex> lock(g_table_mutex);
@@ -211,14 +224,28 @@ cudaError_t msm_release_tables() {     // the current device's tables (panda_msm
     return cudaSuccess;
 }
 
+// PANDA_MSM_PRECOMPUTE: 0 = never build tables (not even for registered sets); 1 = also for UNANNOUNCED pointers, at their second
+// sighting with an identical content fingerprint (costs a fingerprint pass and an 8-byte read-back, i.e. a host synchronisation, per
+// call); 2 = unannounced pointers get a table at first sight; unset / 3 = tables only for sets announced with
+// panda_msm_register_bases_* (the default: an execute call never blocks the host and never allocates a table behind the caller's back).
 static int default_table_mode() {
     static int mode = [] {
         const char *e = getenv("PANDA_MSM_PRECOMPUTE");
-        if (!e || !*e) return (int)MSM_TABLE_AUTO;
+        if (!e || !*e) return (int)MSM_TABLE_REGISTERED;
         int v = atoi(e);
-        return v < 0 || v > 2 ? (int)MSM_TABLE_AUTO : v;
+        return v < 0 || v > 3 ? (int)MSM_TABLE_REGISTERED : v;
     }();
     return mode;
+}
+
+// upper bound for ONE table in bytes: PANDA_MSM_TABLE_BUDGET (GiB, fractions allowed) or half of what is free beyond a 4 GiB reserve
+static size_t table_budget_bytes() {
+    static const double forced_gib = [] { const char *e = getenv("PANDA_MSM_TABLE_BUDGET"); return e && *e ? atof(e) : -1.0; }();
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const size_t automatic = free_b > ((size_t)6 << 30) ? (free_b - ((size_t)4 << 30)) / 2 : 0;
+    if (forced_gib >= 0) return std::min<size_t>((size_t)(forced_gib * 1073741824.0), free_b > ((size_t)1 << 30) ? free_b - ((size_t)1 << 30) : 0);
+    return automatic;
 }
 
 #define PB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[panda-b200] CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); return e_; } } while (0)
@@ -232,20 +259,18 @@ static cudaError_t run_pipeline(CurveId curve, const MsmPlan &p, const void *poi
 
 // Builds the table of `hit` on `stream` (caller holds g_table_mutex).  Not fitting in memory is not an error: the entry stays table-less.
 static cudaError_t build_table_locked(TableEntry *hit, CurveId curve, const void *bases, uint32_t n, uint32_t c_override, cudaStream_t stream) {
-    size_t free_b = 0, total_b = 0;
-    PB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = free_b > ((size_t)6 << 30) ? (free_b - ((size_t)4 << 30)) / 2 : 0;   // leave room for workspaces
+    const size_t budget = table_budget_bytes();
     MsmPlan fp_plan = msm_make_plan(curve, n, true, c_override > 16 ? c_override : 0, 0, budget);
     if (!fp_plan.c) return cudaSuccess;                // no table fits: stay on the windowed path
-    void *tab = nullptr;
-    if (cudaMalloc(&tab, fp_plan.table_bytes) != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
-    cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, tab, stream)
-                                              : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, tab, stream);
-    cudaEvent_t ev = nullptr;
-    if (be == cudaSuccess) be = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (be == cudaSuccess) be = cudaEventRecord(ev, stream);
-    if (be != cudaSuccess) { cudaFree(tab); if (ev) cudaEventDestroy(ev); return be; }
-    hit->table = tab; hit->c = fp_plan.c; hit->windows = fp_plan.windows; hit->bytes = fp_plan.table_bytes; hit->ready = ev;
+    auto buf = std::make_shared<TableBuf>();
+    PB_CUDA(cudaGetDevice(&buf->device));
+    if (cudaMalloc(&buf->ptr, fp_plan.table_bytes) != cudaSuccess) { cudaGetLastError(); buf->ptr = nullptr; return cudaSuccess; }
+    cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, buf->ptr, stream)
+                                              : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, buf->ptr, stream);
+    if (be == cudaSuccess) be = cudaEventCreateWithFlags(&buf->ready, cudaEventDisableTiming);
+    if (be == cudaSuccess) be = cudaEventRecord(buf->ready, stream);
+    if (be != cudaSuccess) return be;                  // buf's destructor frees
+    hit->table = buf; hit->c = fp_plan.c; hit->windows = fp_plan.windows; hit->bytes = fp_plan.table_bytes;
     return cudaSuccess;
 }
 
@@ -255,9 +280,7 @@ static void evict_if_full_locked() {
     for (size_t i = 0; i < g_tables.size(); i++)
         if (!g_tables[i].registered && (victim == g_tables.size() || g_tables[i].last_use < g_tables[victim].last_use)) victim = i;
     if (victim == g_tables.size()) return;             // only registered sets: let the vector grow (the caller owns their lifetime)
-    int cur = 0; cudaGetDevice(&cur); cudaSetDevice(g_tables[victim].device);
     drop_table(g_tables[victim]);
-    cudaSetDevice(cur);
     g_tables.erase(g_tables.begin() + victim);
 }
 
@@ -268,13 +291,13 @@ cudaError_t msm_register_bases(CurveId curve, const void *bases, uint32_t n, cud
     std::lock_guard<std::mutex> lock(g_table_mutex);
     TableEntry *hit = nullptr;
     for (auto &t : g_tables) if (t.device == dev && t.bases == bases) { hit = &t; break; }
-    if (hit) { drop_table(*hit); *hit = TableEntry{dev, curve, bases, n, 0, 0, true, nullptr, 0, 0, 0, nullptr, ++g_use_clock}; }
+    if (hit) { drop_table(*hit); *hit = TableEntry{dev, curve, bases, n, 0, 0, true, nullptr, 0, 0, 0, ++g_use_clock}; }
     else {
         evict_if_full_locked();
-        g_tables.push_back(TableEntry{dev, curve, bases, n, 0, 0, true, nullptr, 0, 0, 0, nullptr, ++g_use_clock});
+        g_tables.push_back(TableEntry{dev, curve, bases, n, 0, 0, true, nullptr, 0, 0, 0, ++g_use_clock});
         hit = &g_tables.back();
     }
-    if (default_table_mode() == MSM_TABLE_OFF || n < 1024) return cudaSuccess;
+    if (default_table_mode() == MSM_TABLE_OFF || n < 1024) return cudaSuccess;      // PANDA_MSM_PRECOMPUTE=0: windowed plan everywhere
     return build_table_locked(hit, curve, bases, n, 0, stream);
 }
 
@@ -291,11 +314,12 @@ cudaError_t msm_unregister_bases(const void *bases) {
     return cudaSuccess;                                // unknown pointer: nothing to do (idempotent)
 }
 
-// Looks `bases` up in the table cache (building the table when the mode asks for it).  On return *table is the table to use
-// (with its window width in *tc, its row length in *table_n and `stream` already waiting for the build) or nullptr: stay on the windowed path.
+// Looks `bases` up in the table cache (building the table when the mode asks for it).  On return *table holds a reference to the
+// table to use (with its window width in *tc, its row length in *table_n and `stream` already waiting for the build) or is empty:
+// stay on the windowed path.  The caller keeps the reference until its kernels are queued.
 static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, cudaStream_t stream, int table_mode, uint32_t c_override,
-                                 const void **table, uint32_t *tc, uint32_t *table_n) {
-    *table = nullptr;
+                                 std::shared_ptr<TableBuf> *table, uint32_t *tc, uint32_t *table_n) {
+    table->reset();
     *table_n = n;
     const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
     if (table_mode == MSM_TABLE_DEFAULT) table_mode = default_table_mode();
@@ -309,13 +333,14 @@ static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, c
                 t.last_use = ++g_use_clock;
                 if (!t.table) return cudaSuccess;
                 *table = t.table; *tc = t.c; *table_n = t.n;
-                cudaEvent_t ready = t.ready;
                 lock.unlock();
-                PB_CUDA(cudaStreamWaitEvent(stream, ready, 0));
+                PB_CUDA(cudaStreamWaitEvent(stream, (*table)->ready, 0));
                 return cudaSuccess;
             }
     }
-    // 1. content fingerprint of the bases (one pass over n * 64 bytes at HBM speed, 8 bytes read back)
+    if (table_mode == MSM_TABLE_REGISTERED) return cudaSuccess;        // unannounced pointer: windowed plan, nothing blocks, nothing is allocated
+    // opt-in modes (PANDA_MSM_PRECOMPUTE = 1 | 2, or the debug entry point):
+    // 1. content fingerprint of the bases (one pass over n * 64 bytes at HBM speed, 8 bytes read back -- a host synchronisation)
     unsigned long long *d_fp = nullptr, fp = 0;
     PB_CUDA(cudaMallocAsync((void **)&d_fp, 8, stream));
     cudaError_t e = msm_fingerprint_launch(bases, (size_t)n * 2 * fq_bytes, d_fp, stream);
@@ -328,14 +353,14 @@ static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, c
     std::unique_lock<std::mutex> lock(g_table_mutex);
     TableEntry *hit = nullptr;
     for (auto &t : g_tables)
-        if (t.device == dev && t.curve == curve && t.bases == bases && t.n == n) { hit = &t; break; }
+        if (!t.registered && t.device == dev && t.curve == curve && t.bases == bases && t.n == n) { hit = &t; break; }
     if (hit && hit->fingerprint != fp) {      // same pointer, different points: forget what we knew
         drop_table(*hit);
         hit->fingerprint = fp; hit->sightings = 0;
     }
     if (!hit) {
         evict_if_full_locked();
-        g_tables.push_back(TableEntry{dev, curve, bases, n, fp, 0, false, nullptr, 0, 0, 0, nullptr, 0});
+        g_tables.push_back(TableEntry{dev, curve, bases, n, fp, 0, false, nullptr, 0, 0, 0, 0});
         hit = &g_tables.back();
     }
     hit->sightings++;
@@ -345,9 +370,8 @@ static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, c
     if (hit->table) {
         *table = hit->table;
         *tc = hit->c;
-        cudaEvent_t ready = hit->ready;
         lock.unlock();
-        PB_CUDA(cudaStreamWaitEvent(stream, ready, 0));
+        PB_CUDA(cudaStreamWaitEvent(stream, (*table)->ready, 0));
     }
     return cudaSuccess;
 }
@@ -362,10 +386,11 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
         PB_CUDA(cudaMemsetAsync(result, 0, 3 * fq_bytes, stream));
         return cudaSuccess;
     }
-    const void *table = nullptr;
+    std::shared_ptr<TableBuf> table_ref;           // held until the kernels are queued
     uint32_t tc = 0;
     uint32_t table_n = n;
-    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, c_override, &table, &tc, &table_n));
+    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, c_override, &table_ref, &tc, &table_n));
+    const void *table = table_ref ? table_ref->ptr : nullptr;
     if (table) {
         // per-stage timings are an attribution pass over the unsplit pipeline; the product path splits large jobs in two chunks
         const uint32_t chunks = timings ? 1 : resident_chunks(n);
@@ -417,10 +442,11 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
         PB_CUDA(cudaMemsetAsync(result, 0, 3 * fq_bytes, stream));
         return cudaSuccess;
     }
-    const void *table = nullptr;
+    std::shared_ptr<TableBuf> table_ref;
     uint32_t tc = 0;
     uint32_t table_n = n;
-    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, 0, &table, &tc, &table_n));
+    PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, 0, &table_ref, &tc, &table_n));
+    const void *table = table_ref ? table_ref->ptr : nullptr;
     uint8_t *d_scal = nullptr;
     if (pool) PB_CUDA(cudaMallocFromPoolAsync((void **)&d_scal, (size_t)n * 32, pool, stream));
     else PB_CUDA(cudaMallocAsync((void **)&d_scal, (size_t)n * 32, stream));

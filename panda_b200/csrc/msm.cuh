@@ -55,16 +55,18 @@ struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_
 // the benchmark harness uses it to attribute time to kernels -- never set on the product path).
 struct MsmStageTimes { float digits, scan, scatter, accumulate, bucket_reduce, window_reduce, final; int folded; unsigned c, windows; };
 
-// How reused bases are handled (PANDA_MSM_PRECOMPUTE = 0 | 1 | 2 overrides the default AUTO):
-//   OFF   never build tables
-//   AUTO  a (device pointer, n) pair seen a second time with an identical 64-bit content fingerprint gets a table of
-//         2^(c*j) * P multiples (built once, ~10 MSMs of arithmetic, W*n*64 bytes), used from then on
-//   EAGER build at first sight
-enum MsmTableMode { MSM_TABLE_OFF = 0, MSM_TABLE_AUTO = 1, MSM_TABLE_EAGER = 2, MSM_TABLE_DEFAULT = -1 };
+// How reused bases are handled (PANDA_MSM_PRECOMPUTE = 0 | 1 | 2 | 3 overrides the default REGISTERED):
+//   OFF         never build tables, not even for registered sets
+//   AUTO        opt-in: an UNANNOUNCED (device pointer, n) pair seen a second time with an identical 64-bit content fingerprint gets a
+//               table (costs a fingerprint pass + an 8-byte read-back, i.e. a host synchronisation, on every call)
+//   EAGER       opt-in: unannounced pointers get a table at first sight
+//   REGISTERED  default: tables only for base sets announced with msm_register_bases (init_msm); an unannounced pointer runs the
+//               windowed plan -- execute never blocks the host and never allocates a table behind the caller's back
+enum MsmTableMode { MSM_TABLE_OFF = 0, MSM_TABLE_AUTO = 1, MSM_TABLE_EAGER = 2, MSM_TABLE_REGISTERED = 3, MSM_TABLE_DEFAULT = -1 };
 
 // bases: n affine points (x||y Montgomery), scalars: n x 32 B (Montgomery), result: 3 field elements.
-// pool may be nullptr (default pool).  Asynchronous on `stream` except for an 8-byte fingerprint read-back when the
-// table cache is enabled.
+// pool may be nullptr (default pool).  Asynchronous on `stream` (the opt-in table modes AUTO / EAGER add an 8-byte fingerprint
+// read-back, see MsmTableMode).
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result,
                     CoordType coord, cudaMemPool_t pool, cudaStream_t stream,
                     uint32_t c_override = 0, uint32_t seg_override = 0, MsmStageTimes *timings = nullptr,

@@ -841,6 +841,17 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         tm.mark();
         err = cudaGetLastError();
     } while (0);
+    if (err != cudaSuccess && (aux || uploading)) {
+        // error after work was queued on the side streams: they may still touch the workspace / the staged scalars, so `stream` (on which
+        // both are freed in stream order) has to wait for them first.  On the success path aux_done and the consumers of `fed` did that.
+        cudaGetLastError();
+        cudaEvent_t join = nullptr;
+        if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess) {
+            if (aux && cudaEventRecord(join, aux) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            if (uploading && cudaEventRecord(join, feed->copy_stream) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            cudaEventDestroy(join);
+        }
+    }
     if (fed) cudaEventDestroy(fed);
     if (sorted_ev) cudaEventDestroy(sorted_ev);
     if (aux_done) cudaEventDestroy(aux_done);

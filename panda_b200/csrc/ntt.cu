@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -422,39 +423,60 @@ __global__ void __launch_bounds__(256) k_ntt_bit_reverse(const uint32_t *__restr
 
 // ---- host side ---------------------------------------------------------------------------------------
 
+// Cache entries are reference counted: a caller holds its entry until its kernels are queued, so a concurrent eviction or
+// panda_ntt_tear_down on another thread cannot free the table underneath it (cudaFree waits for work that is already queued).
 struct NttCacheEntry {
-    int device;
-    int kind;               // 0: powers of a root of unity (transform tables); 1: powers of a coset generator (two-level table only)
-    unsigned log_n;
-    bool inverse;
-    std::array<uint32_t, 8> omega;
-    uint32_t *d_tab;
-    NttTableLayout layout;
+    int device = 0;
+    int kind = 0;           // 0: powers of a root of unity (transform tables); 1: powers of a coset generator (two-level table only)
+    unsigned log_n = 0;
+    bool inverse = false;
+    std::array<uint32_t, 8> omega{};
+    uint32_t *d_tab = nullptr;
+    cudaEvent_t ready = nullptr;     // recorded after the build on the builder's stream; every other stream waits on it
+    unsigned long long last_use = 0;
+    NttTableLayout layout{};
+    ~NttCacheEntry() {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
+        if (d_tab) cudaFree(d_tab);
+        if (ready) cudaEventDestroy(ready);
+        if (cur != device) cudaSetDevice(cur);
+    }
 };
+using NttTables = std::shared_ptr<NttCacheEntry>;
 
 static std::mutex g_ntt_mutex;
-static std::vector<NttCacheEntry *> g_ntt_cache;
+static std::vector<NttTables> g_ntt_cache;
+static unsigned long long g_ntt_clock = 0;
+static constexpr size_t NTT_CACHE_MAX = 16;
 
 #define PB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[panda-b200] CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); return e_; } } while (0)
 
-static cudaError_t ntt_get_tables(const NttShape &shape, const void *omega_host, bool inverse, cudaStream_t stream, NttCacheEntry **out, int kind = 0) {
+static cudaError_t ntt_get_tables(const NttShape &shape, const void *omega_host, bool inverse, cudaStream_t stream, NttTables *out, int kind = 0) {
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
     std::array<uint32_t, 8> om;
     memcpy(om.data(), omega_host, 32);
-    std::lock_guard<std::mutex> lock(g_ntt_mutex);
-    for (auto *e : g_ntt_cache)
-        if (e->device == dev && e->kind == kind && e->log_n == shape.log_n && e->inverse == inverse && e->omega == om) { *out = e; return cudaSuccess; }
-    auto *e = new NttCacheEntry();
+    std::unique_lock<std::mutex> lock(g_ntt_mutex);
+    for (auto &e : g_ntt_cache)
+        if (e->device == dev && e->kind == kind && e->log_n == shape.log_n && e->inverse == inverse && e->omega == om) {
+            e->last_use = ++g_ntt_clock;
+            *out = e;
+            lock.unlock();
+            // the table may still be being built on another stream
+            PB_CUDA(cudaStreamWaitEvent(stream, (*out)->ready, 0));
+            return cudaSuccess;
+        }
+    auto e = std::make_shared<NttCacheEntry>();
     e->device = dev; e->kind = kind; e->log_n = shape.log_n; e->inverse = inverse; e->omega = om;
     e->layout = ntt_table_layout(shape);
     if (kind == 1) {           // coset generator: only the two-level table (segments 0 and 1)
         e->layout.nseg = 2;
         e->layout.words = e->layout.off_sa;
     }
-    e->d_tab = nullptr;
     cudaError_t err = cudaMalloc((void **)&e->d_tab, e->layout.words * 4);
-    if (err != cudaSuccess) { delete e; return err; }
+    if (err != cudaSuccess) { e->d_tab = nullptr; return err; }
     // e->omega lives as long as the cache entry, so the async copy's source stays valid
     err = cudaMemcpyAsync(e->d_tab, e->omega.data(), 32, cudaMemcpyHostToDevice, stream);
     if (err == cudaSuccess) {
@@ -471,29 +493,36 @@ static cudaError_t ntt_get_tables(const NttShape &shape, const void *omega_host,
         k_ntt_tables<Bn254Fr><<<blocks, 128, 0, stream>>>(e->d_tab, ta);
         err = cudaGetLastError();
     }
-    if (err != cudaSuccess) { cudaFree(e->d_tab); delete e; return err; }
-    if (g_ntt_cache.size() >= 16) {            // bounded: drop the oldest entry (its stream work has long been queued)
-        NttCacheEntry *old = g_ntt_cache.front();
-        g_ntt_cache.erase(g_ntt_cache.begin());
-        cudaFree(old->d_tab);                  // cudaFree synchronises with outstanding work on the buffer
-        delete old;
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventRecord(e->ready, stream);
+    if (err != cudaSuccess) return err;          // e's destructor frees the table
+    e->last_use = ++g_ntt_clock;
+    NttTables victim;                            // freed after the lock is dropped (cudaFree synchronises the device)
+    if (g_ntt_cache.size() >= NTT_CACHE_MAX) {   // bounded: drop the least recently used entry
+        size_t v = 0;
+        for (size_t i = 1; i < g_ntt_cache.size(); i++) if (g_ntt_cache[i]->last_use < g_ntt_cache[v]->last_use) v = i;
+        victim = g_ntt_cache[v];
+        g_ntt_cache.erase(g_ntt_cache.begin() + v);
     }
     g_ntt_cache.push_back(e);
     *out = e;
+    lock.unlock();
+    victim.reset();
     return cudaSuccess;
 }
 
-cudaError_t ntt_release_tables() {
-    std::lock_guard<std::mutex> lock(g_ntt_mutex);
-    int cur = 0;
-    cudaGetDevice(&cur);
-    for (auto *e : g_ntt_cache) {
-        cudaSetDevice(e->device);
-        cudaFree(e->d_tab);
-        delete e;
+cudaError_t ntt_release_tables() {               // the current device's tables (one NTT unit per device, like panda_msm_tear_down)
+    std::vector<NttTables> dropped;
+    {
+        std::lock_guard<std::mutex> lock(g_ntt_mutex);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (size_t i = 0; i < g_ntt_cache.size();) {
+            if (g_ntt_cache[i]->device == cur) { dropped.push_back(g_ntt_cache[i]); g_ntt_cache.erase(g_ntt_cache.begin() + i); }
+            else i++;
+        }
     }
-    g_ntt_cache.clear();
-    cudaSetDevice(cur);
+    dropped.clear();                             // entries still referenced by a caller that is queueing kernels die when it lets go
     return cudaSuccess;
 }
 
@@ -505,7 +534,7 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
     const NttShape shape = ntt_shape(log_n);
     if (result_in_dst) *result_in_dst = shape.passes & 1;
     if (shape.passes == 0) return cudaSuccess;                         // n = 1: the transform is the identity
-    NttCacheEntry *tab = nullptr;
+    NttTables tab;                          // held until the kernels below are queued
     PB_CUDA(ntt_get_tables(shape, omega_host, inverse, stream, &tab));
     const NttTableLayout &t = tab->layout;
 
@@ -568,9 +597,9 @@ cudaError_t ntt_exchange(NttField field, const void *d_src, unsigned log_rows, u
     a.log_rows = log_rows; a.log_cols = log_cols; a.log_part_cols = log_cols - log_parts; a.row0 = row_offset;
     for (unsigned h = 0; h < parts; h++) { if (!dst[h]) return cudaErrorInvalidValue; a.dst[h] = (uint32_t *)dst[h]; }
     a.ld = ld; a.col_off = col_offset;
+    NttTables tab;
     if (omega_host) {
         if (log_n > 28) return cudaErrorInvalidValue;
-        NttCacheEntry *tab = nullptr;
         PB_CUDA(ntt_get_tables(ntt_shape(log_n), omega_host, inverse, stream, &tab));
         a.t_lo = tab->d_tab + tab->layout.off_lo; a.t_hi = tab->d_tab + tab->layout.off_hi;
         a.lo_bits = tab->layout.lo_bits; a.log_n = log_n;
@@ -583,12 +612,40 @@ cudaError_t ntt_exchange(NttField field, const void *d_src, unsigned log_rows, u
 cudaError_t ntt_coset_scale(NttField field, void *d_data, unsigned log_n, const void *gen_host, bool inverse, cudaStream_t stream) {
     (void)field;
     if (!d_data || !gen_host || log_n > 28) return cudaErrorInvalidValue;
-    NttCacheEntry *tab = nullptr;
+    NttTables tab;
     PB_CUDA(ntt_get_tables(ntt_shape(log_n), gen_host, inverse, stream, &tab, 1));
     const uint32_t n = 1u << log_n;
     k_ntt_coset_scale<Bn254Fr><<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256, 0, stream>>>((uint32_t *)d_data, n, tab->d_tab + tab->layout.off_lo,
                                                                                                 tab->d_tab + tab->layout.off_hi, tab->layout.lo_bits);
     return cudaGetLastError();
+}
+
+// omega^(2^k) on the host (Montgomery form in and out, BN254 Fr): the sub-roots of the multi-GPU four-step transform.
+// Plain CIOS Montgomery squaring on 4 x 64-bit limbs; a handful of calls per transform, nothing hot.
+void ntt_pow2k_host(const void *omega_host, unsigned k, void *out_host) {
+    typedef unsigned __int128 u128;
+    static const uint64_t P[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+    static const uint64_t NINV = 0xc2e1f593efffffffull;            // -r^-1 mod 2^64
+    uint64_t a[4];
+    memcpy(a, omega_host, 32);
+    for (unsigned it = 0; it < k; it++) {
+        uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 4; i++) {
+            u128 c = 0;
+            for (int j = 0; j < 4; j++) { c += (u128)a[j] * a[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+            c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+            const uint64_t m = t[0] * NINV;
+            c = (u128)m * P[0] + t[0]; c >>= 64;
+            for (int j = 1; j < 4; j++) { c += (u128)m * P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+            c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+        }
+        // conditional subtraction to [0, r)
+        uint64_t d[4]; unsigned __int128 br = 0;
+        for (int j = 0; j < 4; j++) { u128 v = (u128)t[j] - P[j] - (uint64_t)br; d[j] = (uint64_t)v; br = (v >> 64) & 1; }
+        const bool ge = t[4] != 0 || br == 0;
+        for (int j = 0; j < 4; j++) a[j] = ge ? d[j] : t[j];
+    }
+    memcpy(out_host, a, 32);
 }
 
 cudaError_t ntt_bit_reverse(NttField field, const void *d_src, void *d_dst, unsigned log_n, cudaStream_t stream) {

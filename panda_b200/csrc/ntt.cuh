@@ -34,7 +34,10 @@ cudaError_t ntt_coset_scale(NttField field, void *d_data, unsigned log_n, const 
 // d_dst[bitrev(i)] = d_src[i] (out of place): turns natural-order data into bit-reversed order and back
 cudaError_t ntt_bit_reverse(NttField field, const void *d_src, void *d_dst, unsigned log_n, cudaStream_t stream);
 
-// frees the cached twiddle tables of every device
+// omega^(2^k) on the HOST (32 bytes, Montgomery in / out): sub-roots of the multi-GPU four-step transform
+void ntt_pow2k_host(const void *omega_host, unsigned k, void *out_host);
+
+// frees the cached twiddle tables of the current device
 cudaError_t ntt_release_tables();
 
 }  // namespace pb

@@ -3,8 +3,8 @@
 // Same symbols, argument meaning and error convention as the reference's src/cuda/core/panda_interface.cu:11-191
 // (every function returns the cudaError_t value, 0 = success), plus the spellings the Rust bindings expect but the
 // reference never defined (src/gpu_ffi/binding.rs:14,16,54-56) and the BLS12-377 / sharding / inverse-NTT additions.
-#include "../../include/panda_interface.h"
-#include "../../include/panda_debug.h"
+#include "panda_interface.h"
+#include "panda_debug.h"
 #include "msm.cuh"
 #include "ntt.cuh"
 
@@ -101,13 +101,15 @@ static panda_error msm_execute(pb::CurveId curve, const panda_msm_configuration 
 }
 
 // Host-pointer variant: stage through the device on cfg.stream, synchronous like the reference's CPU path.
-static panda_error msm_execute_host(pb::CurveId curve, const panda_msm_configuration &cfg, size_t n) {
+static panda_error msm_execute_host(pb::CurveId curve, const panda_msm_configuration &cfg) {
+    if (!cfg.results || !cfg.bases || !cfg.scalars || cfg.log_scalars_count > 30) return perr(cudaErrorInvalidValue);   // before anything is queued
+    const size_t n = (size_t)1 << cfg.log_scalars_count;
     const size_t fq = curve == pb::CURVE_BLS12_377 ? 48 : 32;
     cudaStream_t s = cu(cfg.stream);
     uint8_t *d = nullptr;
     const size_t bases_bytes = n * 2 * fq, scalars_bytes = n * 32, off_s = (bases_bytes + 255) & ~(size_t)255,
                  off_r = off_s + ((scalars_bytes + 255) & ~(size_t)255);
-    cudaError_t e = cudaMallocAsync((void **)&d, off_r + 256, s);
+    cudaError_t e = cu(cfg.mem_pool) ? cudaMallocFromPoolAsync((void **)&d, off_r + 256, cu(cfg.mem_pool), s) : cudaMallocAsync((void **)&d, off_r + 256, s);
     if (e != cudaSuccess) return perr(e);
     do {
         if ((e = cudaMemcpyAsync(d, cfg.bases, bases_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess) break;
@@ -146,12 +148,15 @@ panda_error panda_msm_setup_bn254(void) { return panda_success; }          // no
 panda_error panda_msm_setup_bls12_377(void) { return panda_success; }
 panda_error panda_msm_tear_down(void) { return perr(pb::msm_release_tables()); }   // idempotent (wrapper.rs:297-312 calls it once per base set); drops cached tables
 
-panda_error panda_msm_execute_bn254(const panda_msm_configuration cfg) { return msm_execute(pb::CURVE_BN254, cfg, (size_t)1 << cfg.log_scalars_count); }
-panda_error panda_msm_execute_bn254_n(const panda_msm_configuration cfg, size_t n) { return msm_execute(pb::CURVE_BN254, cfg, n); }
-panda_error panda_msm_execute_bn254_host(const panda_msm_configuration cfg) {
-    return msm_execute_host(pb::CURVE_BN254, cfg, (size_t)1 << cfg.log_scalars_count);
+panda_error panda_msm_execute_bn254(const panda_msm_configuration cfg) {
+    if (cfg.log_scalars_count > 30) return perr(cudaErrorInvalidValue);
+    return msm_execute(pb::CURVE_BN254, cfg, (size_t)1 << cfg.log_scalars_count);
 }
+panda_error panda_msm_execute_bn254_n(const panda_msm_configuration cfg, size_t n) { return msm_execute(pb::CURVE_BN254, cfg, n); }
+panda_error panda_msm_execute_bn254_host(const panda_msm_configuration cfg) { return msm_execute_host(pb::CURVE_BN254, cfg); }
+panda_error panda_msm_execute_bls12_377_host(const panda_msm_configuration cfg) { return msm_execute_host(pb::CURVE_BLS12_377, cfg); }
 panda_error panda_msm_execute_bls12_377(const panda_msm_configuration cfg) {
+    if (cfg.log_scalars_count > 30) return perr(cudaErrorInvalidValue);
     return msm_execute(pb::CURVE_BLS12_377, cfg, (size_t)1 << cfg.log_scalars_count);
 }
 panda_error panda_msm_execute_bls12_377_n(const panda_msm_configuration cfg, size_t n) { return msm_execute(pb::CURVE_BLS12_377, cfg, n); }
@@ -165,15 +170,21 @@ panda_error panda_msm_combine_bls12_377(const void *partials, unsigned count, vo
 
 // ---- NTT (panda_interface.cu:172-191) -------------------------------------------------------------------------
 
+// setup state is per device (the reference keeps ONE process-global table, fft.cu:223, so two managers on two GPUs race)
+static constexpr int MAX_DEVICES = 64;
 static std::mutex g_omega_mutex;
-static unsigned char g_setup_omega[32];
-static bool g_setup_done = false;
+static unsigned char g_setup_omega[MAX_DEVICES][32];
+static bool g_setup_done[MAX_DEVICES] = {};
 
 panda_error panda_ntt_setup_bn254(void *input_omega) {
     if (!input_omega) return perr(cudaErrorInvalidValue);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return perr(e);
+    if (dev < 0 || dev >= MAX_DEVICES) return perr(cudaErrorInvalidDevice);
     std::lock_guard<std::mutex> lock(g_omega_mutex);
-    memcpy(g_setup_omega, input_omega, 32);      // fft.cu:62-73 copies omega to the device here; tables are built at first execute
-    g_setup_done = true;
+    memcpy(g_setup_omega[dev], input_omega, 32);      // fft.cu:62-73 copies omega to the device here; tables are built at first execute
+    g_setup_done[dev] = true;
     return panda_success;
 }
 
@@ -187,10 +198,13 @@ static panda_error ntt_execute(void *d_src, void *d_dst, unsigned log_n, const v
 
 panda_error panda_ntt_execute_bn254(panda_ntt_configuration cfg) {
     unsigned char omega[32];
+    int dev = 0;
+    cudaError_t de = cudaGetDevice(&dev);
+    if (de != cudaSuccess) return perr(de);
     {
         std::lock_guard<std::mutex> lock(g_omega_mutex);
-        if (!g_setup_done) return perr(cudaErrorNotReady);
-        memcpy(omega, g_setup_omega, 32);
+        if (dev < 0 || dev >= MAX_DEVICES || !g_setup_done[dev]) return perr(cudaErrorNotReady);
+        memcpy(omega, g_setup_omega[dev], 32);
     }
     return ntt_execute(cfg.d_src, cfg.d_dst, cfg.log_n, omega, false, cfg.stream, cfg.flag);
 }
@@ -227,15 +241,22 @@ panda_error panda_ntt_exchange_bn254(const panda_ntt_exchange_configuration *cfg
     return perr(pb::ntt_exchange(pb::NTT_BN254_FR, cfg->d_src, cfg->log_rows, cfg->log_cols, cfg->row_offset, cfg->omega, cfg->log_n, cfg->inverse != 0,
                                  cfg->parts, cfg->dst, cfg->ld, cfg->col_offset, cu(cfg->stream)));
 }
-panda_error panda_ntt_tear_down(void) {
-    {
+panda_error panda_ntt_tear_down(void) {       // the current device's NTT unit: its setup omega and its cached twiddle tables
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MAX_DEVICES) {
         std::lock_guard<std::mutex> lock(g_omega_mutex);
-        g_setup_done = false;
-    }
+        g_setup_done[dev] = false;
+    } else cudaGetLastError();
     return perr(pb::ntt_release_tables());
 }
 
 // ---- diagnostics (include/panda_debug.h) --------------------------------------------------------------------------
+
+panda_error panda_debug_fr_pow2k_host(const void *omega, unsigned k, void *out) {
+    if (!omega || !out) return perr(cudaErrorInvalidValue);
+    pb::ntt_pow2k_host(omega, k, out);
+    return panda_success;
+}
 
 panda_error panda_debug_msm_plan(int curve, size_t n, int folded, unsigned c_override, unsigned seg_override, panda_debug_msm_plan_info *out) {
     if (!out) return perr(cudaErrorInvalidValue);

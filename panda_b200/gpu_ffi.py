@@ -172,6 +172,18 @@ class NttExchangeConfiguration(C.Structure):  # include/panda_interface.h (addit
     ]
 
 
+class NttMultiConfiguration(C.Structure):  # include/panda_interface.h (addition: multi-GPU four-step transform, one process)
+    _fields_ = [
+        ("n_dev", C.c_uint),
+        ("streams", C.POINTER(PandaStream)),
+        ("d_src", C.POINTER(C.c_void_p)),
+        ("d_dst", C.POINTER(C.c_void_p)),
+        ("omega", C.c_void_p),
+        ("log_n", C.c_uint),
+        ("inverse", C.c_int),
+    ]
+
+
 PandaHostFn = C.CFUNCTYPE(None, C.c_void_p)
 
 
@@ -256,6 +268,12 @@ SIGNATURES: dict[str, list] = {
     "panda_ntt_coset_execute_bn254_v1": [NttconfigurationV1, _vp, _int],
     "panda_ntt_batch_execute_bn254_v1": [NttconfigurationV1, _uint, _int],
     "panda_ntt_exchange_bn254": [C.POINTER(NttExchangeConfiguration)],
+    "panda_msm_execute_bls12_377_host": [MSMConfiguration],
+    "panda_msm_execute_bn254_multi": [C.POINTER(MSMConfiguration), _int],
+    "panda_msm_execute_bn254_multi_n": [C.POINTER(MSMConfiguration), C.POINTER(SizeT), _int],
+    "panda_msm_execute_bls12_377_multi": [C.POINTER(MSMConfiguration), _int],
+    "panda_msm_execute_bls12_377_multi_n": [C.POINTER(MSMConfiguration), C.POINTER(SizeT), _int],
+    "panda_ntt_execute_bn254_multi": [C.POINTER(NttMultiConfiguration)],
     # diagnostics (include/panda_debug.h)
     "panda_debug_field_op": [_int, _int, _vp, _vp, _vp, SizeT, PandaStream],
     "panda_debug_curve_op": [_int, _int, _vp, _vp, _vp, SizeT, PandaStream],
@@ -263,6 +281,7 @@ SIGNATURES: dict[str, list] = {
     "panda_debug_msm_timed": [_int, MSMConfiguration, SizeT, _uint, _uint, _int, C.POINTER(C.c_float), C.POINTER(_uint)],
     "panda_debug_msm_streamed": [_int, MSMConfiguration, SizeT, _int, _uint],
     "panda_debug_int_peak": [_int, _uint, C.POINTER(C.c_float), C.POINTER(C.c_ulonglong)],
+    "panda_debug_fr_pow2k_host": [_vp, _uint, _vp],
 }
 
 for _name, _args in SIGNATURES.items():

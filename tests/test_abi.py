@@ -124,3 +124,42 @@ def test_shard_ranges_tile_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
+
+
+def test_host_side_sub_root_helper(oracle):
+    """omega^(2^k) on the host (the sub-roots of the multi-GPU four-step NTT) against the oracle's field arithmetic"""
+    import numpy as np
+    from panda_b200 import gpu_ffi as ffi
+
+    w = oracle.omega_bn254(26).copy()
+    for k in (0, 1, 5, 13, 26):
+        out = np.zeros(32, np.uint8)
+        assert ffi.lib.panda_debug_fr_pow2k_host(w.ctypes.data, k, out.ctypes.data) == 0
+        assert (out == oracle.f_pow2k(1, w, k)).all(), k
+    x = oracle.gen_scalars(1, 1234, 1)
+    out = np.zeros(32, np.uint8)
+    assert ffi.lib.panda_debug_fr_pow2k_host(x.ctypes.data, 3, out.ctypes.data) == 0
+    assert (out == oracle.f_pow2k(1, x, 3)).all()
+
+
+@pytest.mark.skipif(os.environ.get("PANDA_SKIP_CMAKE_TEST") == "1", reason="PANDA_SKIP_CMAKE_TEST=1")
+def test_cmake_drop_in_build_like_build_rs(tmp_path):
+    """the reference's build.rs:8-18 runs `cmake .. && make -j12` in src/cuda/build and links build/core/libpanda-cuda.a (:41-45);
+    panda_b200/csrc, put in place of src/cuda, must satisfy exactly that recipe"""
+    import shutil
+    import subprocess
+
+    if shutil.which("cmake") is None or shutil.which("nvcc") is None:
+        pytest.skip("cmake / nvcc not available")
+    cuda = tmp_path / "src" / "cuda"
+    shutil.copytree(os.path.join(ROOT, "panda_b200", "csrc"), cuda, ignore=shutil.ignore_patterns("build", "*.so", "*.a", "*.o"))
+    shutil.copytree(os.path.join(ROOT, "include"), cuda / "include")
+    build = cuda / "build"
+    build.mkdir()
+    proc = subprocess.run(["sh", "-c", "cmake .. && make -j12"], cwd=build, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    lib = build / "core" / "libpanda-cuda.a"
+    assert lib.exists()
+    syms = subprocess.run(["nm", "-g", "--defined-only", str(lib)], capture_output=True, text=True).stdout
+    for name in ("panda_msm_execute_bn254", "panda_ntt_execute_bn254_v1", "panda_msm_execute_bn254_multi", "panda_stream_synchronize"):
+        assert f" T {name}" in syms, name

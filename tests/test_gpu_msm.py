@@ -464,3 +464,104 @@ def test_randomised_differential(oracle, dev):
         s.sync()
         assert (affine(oracle, 0, d_r.to_numpy(), coord) == exp).all(), (case, n, coord, mode)
     assert ffi.lib.panda_msm_tear_down() == 0
+
+
+# ---- BASELINE.json configs at their full sizes (closed form: bases P_i = (a0 + i*d)*G, expected = (sum s_i*(a0 + i*d)) * G) ----------
+
+def _run_cfg(ffi, gu, curve, d_b, d_s, d_r, n, coord, stream, pool, info=None):
+    cfg = ffi.MSMConfiguration(pool, stream, d_b.ptr, d_s.ptr, d_r.ptr, max(n.bit_length() - 1, 0), coord)
+    if info is not None:
+        assert ffi.lib.panda_debug_msm_timed(curve, cfg, n, 0, 0, -1, None, info) == 0
+    else:
+        fn = ffi.lib.panda_msm_execute_bls12_377 if curve == 1 else ffi.lib.panda_msm_execute_bn254
+        assert fn(cfg) == 0
+    stream.sync()
+    return d_r.to_numpy()
+
+
+def test_config2_2_20_cached_bases_jacobian_and_projective(oracle, dev):
+    """config 2: BN254 MSM n = 2^20 on one GPU with CACHED bases (init_msm -> panda_msm_register_bases_bn254: the table plan
+    from the first call), Jacobian and Projective output, through the C ABI and through the host API's cached-input call"""
+    from panda_b200 import gpu_manager as gm
+
+    ffi, gu = dev
+    k, n = 20, 1 << 20
+    bases = oracle.gen_bases(0, oracle.seed_for(k), n)
+    scal = oracle.gen_scalars(1, oracle.seed_for(k) + 1, n)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, oracle.seed_for(k), scal, n))
+    d_b, d_s, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf.from_numpy(scal), gu.DevBuf(96)
+    stream, pool = ffi.PandaStream.new(), ffi.PandaMemPool.new(0)
+    assert ffi.lib.panda_msm_register_bases_bn254(d_b.ptr, n, stream) == 0
+    info = (C.c_uint * 3)()
+    for coord in (0, 1):
+        got = _run_cfg(ffi, gu, 0, d_b, d_s, d_r, n, coord, stream, pool, info)
+        assert info[0] == 1, "registered bases must run the table plan"
+        assert (affine(oracle, 0, got, coord) == exp).all(), coord
+        got = _run_cfg(ffi, gu, 0, d_b, d_s, d_r, n, coord, stream, pool)          # the stock entry point
+        assert (affine(oracle, 0, got, coord) == exp).all(), coord
+    assert ffi.lib.panda_msm_unregister_bases(d_b.ptr) == 0
+    for b in (d_b, d_s, d_r):
+        b.free()
+    m = gm.PandaGpuManager.init_all(0, gm.PandaGpuManagerInitUnitType.PandaGpuManagerInitUnitTypeMSM, [bases], [scal])
+    try:
+        assert (oracle.jac_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_input(m, 0, 0)) == exp).all()
+        m.set_config(gm.PandaMSMResultCoordinateType.Projective)
+        assert (oracle.proj_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_input(m, 0, 0)) == exp).all()
+        assert (oracle.proj_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_bases(m, scal, 0)) == exp).all()
+    finally:
+        m.deinit()
+
+
+@pytest.mark.parametrize("k", [25, 26])
+def test_config3_upper_sizes_single_gpu(oracle, dev, k):
+    """config 3's upper end on ONE GPU (2^24 is test_full_size_2_24_closed_form_and_linearity): first sighting (windowed plan), then
+    registered bases (table plan: 24 / 48 GiB of precomputed multiples), Jacobian and Projective"""
+    ffi, gu = dev
+    n = 1 << k
+    bases = oracle.gen_bases(0, oracle.seed_for(k), n)
+    scal = oracle.gen_scalars(1, oracle.seed_for(k) + 1, n)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, oracle.seed_for(k), scal, n))
+    d_b, d_s, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf.from_numpy(scal), gu.DevBuf(96)
+    del bases
+    stream, pool = ffi.PandaStream.new(), ffi.PandaMemPool.new(0)
+    info = (C.c_uint * 3)()
+    got = _run_cfg(ffi, gu, 0, d_b, d_s, d_r, n, 0, stream, pool, info)
+    assert info[0] == 0
+    assert (oracle.jac_to_affine(0, got) == exp).all()
+    assert ffi.lib.panda_msm_register_bases_bn254(d_b.ptr, n, stream) == 0
+    for coord in (0, 1):
+        got = _run_cfg(ffi, gu, 0, d_b, d_s, d_r, n, coord, stream, pool, info)
+        assert info[0] == 1
+        assert (affine(oracle, 0, got, coord) == exp).all(), coord
+    assert ffi.lib.panda_msm_unregister_bases(d_b.ptr) == 0
+    assert ffi.lib.panda_msm_tear_down() == 0
+    for b in (d_b, d_s, d_r):
+        b.free()
+
+
+def test_config5_bls12_377_2_24(oracle, dev):
+    """config 5: BLS12-377 G1 MSM n = 2^24 (12-limb Fq, 253-bit Fr): windowed plan on first sight, table plan once the bases are
+    registered, both output coordinates"""
+    ffi, gu = dev
+    k, n = 24, 1 << 24
+    bases = oracle.gen_bases(1, oracle.seed_for(k), n)
+    scal = oracle.gen_scalars(3, oracle.seed_for(k) + 1, n)
+    exp = oracle.jac_to_affine(1, oracle.expected_progression_msm(1, oracle.seed_for(k), scal, n))
+    d_b, d_s, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf.from_numpy(scal), gu.DevBuf(144)
+    del bases
+    stream, pool = ffi.PandaStream.new(), ffi.PandaMemPool.new(0)
+    info = (C.c_uint * 3)()
+    got = _run_cfg(ffi, gu, 1, d_b, d_s, d_r, n, 0, stream, pool, info)
+    assert info[0] == 0
+    assert (oracle.jac_to_affine(1, got) == exp).all()
+    assert ffi.lib.panda_msm_register_bases_bls12_377(d_b.ptr, n, stream) == 0
+    for coord in (0, 1):
+        got = _run_cfg(ffi, gu, 1, d_b, d_s, d_r, n, coord, stream, pool, info)
+        assert info[0] == 1
+        assert (affine(oracle, 1, got, coord) == exp).all(), coord
+        got = _run_cfg(ffi, gu, 1, d_b, d_s, d_r, n, coord, stream, pool)
+        assert (affine(oracle, 1, got, coord) == exp).all(), coord
+    assert ffi.lib.panda_msm_unregister_bases(d_b.ptr) == 0
+    assert ffi.lib.panda_msm_tear_down() == 0
+    for b in (d_b, d_s, d_r):
+        b.free()

@@ -168,3 +168,70 @@ def test_bit_reverse_permutation(oracle, dev, k):
             assert (y[j] == x.reshape(n, 32)[i]).all()
     assert (c.to_numpy(x.size) == x).all()
     assert ffi.lib.panda_ntt_bit_reverse_bn254(a.ptr, a.ptr, k, s) != 0          # in place is refused
+
+
+# ---- fixtures produced WITHOUT the oracle (tests/golden/make_ntt_golden.py: sympy's ntt + the definition on Python ints) ----
+
+def _golden_dir():
+    import os
+
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ntt")
+
+
+def test_golden_k10_sympy_and_reference_root(dev):
+    """the CUDA transform reproduces sympy.discrete.transforms.ntt (omega = 5^((r-1)/n): arkworks' root) and the definition
+    evaluated with the reference's root (bn254/paramter.cuh:241-258); forward and inverse"""
+    import os
+
+    ffi, gu = dev
+    rd = lambda name: np.fromfile(os.path.join(_golden_dir(), name), dtype=np.uint8)
+    x = rd("k10_x.bin")
+    for root in ("ark", "ref"):
+        w, y = rd(f"k10_omega_{root}.bin"), rd(f"k10_y_{root}.bin")
+        assert (run_ntt(ffi, gu, x, 10, w) == y).all(), root
+        assert (run_ntt(ffi, gu, y, 10, w, inverse=True) == x).all(), root
+
+
+@pytest.mark.parametrize("k", [13, 17, 20])
+def test_golden_digests(dev, k):
+    """2- and 3-pass sizes: sha256 of the output equals the digest sympy / the Python definition produced"""
+    import hashlib
+    import json
+    import os
+    import sys
+
+    ffi, gu = dev
+    sys.path.insert(0, os.path.dirname(_golden_dir()))
+    import make_ntt_golden as mk
+
+    d = json.load(open(os.path.join(_golden_dir(), "digests.json")))[str(k)]
+    x = np.frombuffer(mk.to_wire(mk.gen_input(k)), np.uint8).copy()
+    assert hashlib.sha256(x.tobytes()).hexdigest() == d["x_sha256"]
+    for root in ("ark", "ref"):
+        w = np.frombuffer(bytes.fromhex(d[f"omega_{root}"]), np.uint8).copy()
+        y = run_ntt(ffi, gu, x, k, w)
+        assert hashlib.sha256(y.tobytes()).hexdigest() == d[f"y_{root}_sha256"], root
+        assert (run_ntt(ffi, gu, y, k, w, inverse=True) == x).all(), root
+
+
+@pytest.mark.parametrize("k", [22, 26])
+def test_config4_sizes_forward_and_inverse(oracle, dev, k):
+    """BASELINE.json config 4 (NTT / INTT 2^20 .. 2^26; 2^20 and 2^24 are covered above): forward against the DFT definition at
+    spot indices, the inverse against ITS definition x[i] = n^-1 * sum_j y[j] * omega^(-i*j) at spot indices, and the round trip"""
+    ffi, gu = dev
+    n = 1 << k
+    x = oracle.gen_scalars(1, 26000 + k, n)
+    w = oracle.omega_bn254(k)
+    y = run_ntt(ffi, gu, x, k, w)
+    spots = (0, 1, n // 2 + 1, n - 1, 0x2B5A5A5 % n) if k <= 22 else (1, n - 1, 0x2B5A5A5 % n)    # O(n) each on the host
+    for j in spots:
+        assert (oracle.dft_at(1, x, k, w, j) == y[j * 32:(j + 1) * 32]).all(), j
+    back = run_ntt(ffi, gu, y, k, w, inverse=True)
+    assert (back == x).all()
+    del back
+    z = oracle.gen_scalars(1, 27000 + k, n)                      # inverse of data that is not a forward output of this code
+    iz = run_ntt(ffi, gu, z, k, w, inverse=True)
+    w_inv = oracle.f_inv(1, w)
+    n_inv = oracle.f_inv(1, oracle.f_to_mont(1, np.frombuffer(n.to_bytes(32, "little"), np.uint8).copy()))
+    for i in (spots[:3] if k <= 22 else spots[2:]):
+        assert (oracle.f_mul(1, oracle.dft_at(1, z, k, w_inv, i), n_inv) == iz[i * 32:(i + 1) * 32]).all(), i

@@ -268,3 +268,45 @@ def test_generators_are_deterministic_and_valid(oracle):
         assert oracle.aff_on_curve(cid, pts)
         fb = oracle.FQ_BYTES[cid]
         assert len({bytes(pts[i * 2 * fb:i * 2 * fb + fb]) for i in range(5000)}) == 5000
+
+
+# ---- NTT pinned to fixtures produced WITHOUT the oracle (tests/golden/make_ntt_golden.py: sympy + Python big ints) ----------
+
+def _ntt_golden():
+    import json
+    import os
+
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ntt")
+    rd = lambda name: np.fromfile(os.path.join(d, name), dtype=np.uint8)
+    return {"x": rd("k10_x.bin"), "omega_ark": rd("k10_omega_ark.bin"), "y_ark": rd("k10_y_ark.bin"), "omega_ref": rd("k10_omega_ref.bin"),
+            "y_ref": rd("k10_y_ref.bin"), "digests": json.load(open(os.path.join(d, "digests.json")))}
+
+
+def test_ntt_golden_k10_sympy_and_reference_root(oracle):
+    """the oracle's transform equals sympy's (omega = 5^((r-1)/n), arkworks' root) and the definition evaluated with the
+    reference's root 7^((r-1)/2^28)^(2^18) (paramter.cuh:241-258) -- outputs that share no code with panda_oracle.c"""
+    g = _ntt_golden()
+    assert (oracle.omega_bn254(10) == g["omega_ref"]).all()
+    assert (oracle.ntt(1, g["x"], 10, g["omega_ark"]) == g["y_ark"]).all()
+    assert (oracle.ntt(1, g["x"], 10, g["omega_ref"]) == g["y_ref"]).all()
+    for j in (0, 1, 513, 1023):
+        assert (oracle.dft_at(1, g["x"], 10, g["omega_ark"], j) == g["y_ark"][j * 32:(j + 1) * 32]).all()
+
+
+@pytest.mark.parametrize("k", [13, 17, 20])
+def test_ntt_golden_digests(oracle, k):
+    """sha256 of the output for inputs regenerated by the fixture script's pure-Python generator (multi-pass sizes)"""
+    import hashlib
+    import sys
+    import os
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_ntt_golden as mk
+
+    d = _ntt_golden()["digests"][str(k)]
+    x = np.frombuffer(mk.to_wire(mk.gen_input(k)), np.uint8).copy()
+    assert hashlib.sha256(x.tobytes()).hexdigest() == d["x_sha256"]
+    assert oracle.omega_bn254(k).tobytes().hex() == d["omega_ref"]
+    for root in ("ark", "ref"):
+        w = np.frombuffer(bytes.fromhex(d[f"omega_{root}"]), np.uint8).copy()
+        assert hashlib.sha256(oracle.ntt(1, x, k, w).tobytes()).hexdigest() == d[f"y_{root}_sha256"], root
