@@ -57,6 +57,10 @@ panda_error panda_debug_msm_streamed(int curve_id, const panda_msm_configuration
  * modular products executed). */
 panda_error panda_debug_int_peak(int kind, unsigned iters, float *ms, unsigned long long *ops);
 
+/* panda_ntt_execute_bn254_v1 / panda_intt_execute_bn254_v1 with the device time of every pass (HOST float[4], unused entries 0).
+ * Synchronises the stream. */
+panda_error panda_debug_ntt_timed(const panda_ntt_configuration_v1 cfg, int inverse, float *pass_ms);
+
 /* out = omega^(2^k) for a BN254 Fr element, HOST pointers, Montgomery in / out: the host-side helper the multi-GPU NTT derives its
  * sub-roots with (no device involved) */
 panda_error panda_debug_fr_pow2k_host(const void *omega, unsigned k, void *out);

@@ -527,7 +527,7 @@ cudaError_t ntt_release_tables() {               // the current device's tables 
 }
 
 cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, const void *omega_host, bool inverse,
-                    cudaStream_t stream, unsigned *result_in_dst, unsigned batch) {
+                    cudaStream_t stream, unsigned *result_in_dst, unsigned batch, float *pass_ms) {
     (void)field;
     if (log_n > 28 || !omega_host) return cudaErrorInvalidValue;      // 2-adicity of BN254 Fr (paramter.cuh:241)
     if (batch == 0 || ((uint64_t)batch << log_n) > ((uint64_t)1 << 31)) return cudaErrorInvalidValue;
@@ -550,7 +550,10 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
 
     uint32_t *src = (uint32_t *)d_src, *dst = (uint32_t *)d_dst;
     unsigned log_O = 0;
+    cudaEvent_t marks[5] = {};                                         // pass_ms (diagnostics only): events between the passes
+    if (pass_ms) for (unsigned p = 0; p <= shape.passes; p++) PB_CUDA(cudaEventCreate(&marks[p]));
     for (unsigned p = 0; p < shape.passes; p++) {
+        if (pass_ms) PB_CUDA(cudaEventRecord(marks[p], stream));
         NttPassArgs a{};
         a.log_n = log_n; a.r = shape.r[p]; a.log_O = log_O; a.lo_bits = t.lo_bits; a.passes = shape.passes;
         for (unsigned d = 0; d < 4; d++) a.rad[d] = shape.r[d];
@@ -582,6 +585,13 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
         PB_CUDA(cudaGetLastError());
         log_O += a.r;
         std::swap(src, dst);
+    }
+    if (pass_ms) {
+        PB_CUDA(cudaEventRecord(marks[shape.passes], stream));
+        PB_CUDA(cudaStreamSynchronize(stream));
+        for (unsigned p = 0; p < 4; p++) pass_ms[p] = 0.f;
+        for (unsigned p = 0; p < shape.passes; p++) cudaEventElapsedTime(&pass_ms[p], marks[p], marks[p + 1]);
+        for (unsigned p = 0; p <= shape.passes; p++) cudaEventDestroy(marks[p]);
     }
     return cudaSuccess;
 }

@@ -19,7 +19,7 @@ enum NttField { NTT_BN254_FR = 0 };
 // Asynchronous on `stream` (twiddle tables are built on first use of an (omega, log_n) pair and cached per device).
 // batch: number of independent 2^log_n-point transforms stored back to back in d_src (d_dst has the same size).
 cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, const void *omega_host, bool inverse,
-                    cudaStream_t stream, unsigned *result_in_dst, unsigned batch = 1);
+                    cudaStream_t stream, unsigned *result_in_dst, unsigned batch = 1, float *pass_ms = nullptr);   // pass_ms: HOST float[4], per-pass device time (diagnostics; synchronises)
 
 // Exchange step of the four-step (multi-GPU) transform: tiled transpose of the 2^log_rows x 2^log_cols matrix d_src fused
 // with the twiddle omega^((row_offset + r) * c) (omega_host = nullptr: none; omega of order 2^log_n, inverse: omega^-1);

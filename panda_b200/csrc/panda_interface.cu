@@ -252,6 +252,14 @@ panda_error panda_ntt_tear_down(void) {       // the current device's NTT unit: 
 
 // ---- diagnostics (include/panda_debug.h) --------------------------------------------------------------------------
 
+panda_error panda_debug_ntt_timed(const panda_ntt_configuration_v1 cfg, int inverse, float *pass_ms) {
+    if (!cfg.d_omega || !cfg.flag || !cfg.d_src || !cfg.d_dst || !pass_ms) return perr(cudaErrorInvalidValue);
+    unsigned in_dst = 0;
+    cudaError_t e = pb::ntt_run(pb::NTT_BN254_FR, cfg.d_src, cfg.d_dst, cfg.log_n, cfg.d_omega, inverse != 0, cu(cfg.stream), &in_dst, 1, pass_ms);
+    *static_cast<unsigned *>(cfg.flag) = in_dst;
+    return perr(e);
+}
+
 panda_error panda_debug_fr_pow2k_host(const void *omega, unsigned k, void *out) {
     if (!omega || !out) return perr(cudaErrorInvalidValue);
     pb::ntt_pow2k_host(omega, k, out);

@@ -68,20 +68,33 @@ class ShardedMsm:
         self.local_msm = local_msm or _cuda_local_msm(curve)
         self.combine = combine or _cuda_combine(curve)
 
-    def run(self, bases_t, scalars_t, n_local: int, coord: int = 0, stream: int = 0, pool: int = 0):
+    def run(self, bases_t, scalars_t, n_local: int, coord: int = 0, stream=None, pool: int = 0):
         """bases_t / scalars_t: uint8 torch tensors holding this rank's slice (on the device the backend works on).
-        Returns a uint8 tensor with the 3-coordinate result, identical on every rank."""
+        Returns a uint8 tensor with the 3-coordinate result, identical on every rank.
+        stream: raw CUDA stream handle or None (= torch's current stream).  The kernels AND torch's own work (allocations,
+        the all-gather) are ordered on that one stream: a foreign handle is entered as torch's current stream for the call."""
+        import contextlib
+
         import torch
 
-        nb = result_bytes(self.curve)
         dev = bases_t.device
-        partial = torch.empty(nb, dtype=torch.uint8, device=dev)
-        self.local_msm(bases_t.data_ptr(), scalars_t.data_ptr(), n_local, partial.data_ptr(), stream, pool)
-        if self.world > 1:
-            gathered = torch.empty(self.world * nb, dtype=torch.uint8, device=dev)
-            self.dist.all_gather_into_tensor(gathered, partial, group=self.group)   # the only exchange: world x 96 bytes
-        else:
-            gathered = partial
-        out = torch.empty(nb, dtype=torch.uint8, device=dev)
-        self.combine(gathered.data_ptr(), self.world, out.data_ptr(), coord, stream)
+        ctx = contextlib.nullcontext()
+        if dev.type == "cuda":
+            cur = torch.cuda.current_stream(dev).cuda_stream
+            if stream is None:
+                stream = cur
+            elif int(stream) != cur:
+                ctx = torch.cuda.stream(torch.cuda.ExternalStream(int(stream), device=dev))
+        stream = int(stream or 0)
+        nb = result_bytes(self.curve)
+        with ctx:
+            partial = torch.empty(nb, dtype=torch.uint8, device=dev)
+            self.local_msm(bases_t.data_ptr(), scalars_t.data_ptr(), n_local, partial.data_ptr(), stream, pool)
+            if self.world > 1:
+                gathered = torch.empty(self.world * nb, dtype=torch.uint8, device=dev)
+                self.dist.all_gather_into_tensor(gathered, partial, group=self.group)   # the only exchange: world x 96 bytes
+            else:
+                gathered = partial
+            out = torch.empty(nb, dtype=torch.uint8, device=dev)
+            self.combine(gathered.data_ptr(), self.world, out.data_ptr(), coord, stream)
         return out

@@ -173,11 +173,16 @@ class ShardedNtt:
         return self.recv
 
     def _stream(self, stream):
-        if stream is not None:
-            return stream
-        if self.device.type == "cuda":
-            return self.torch.cuda.current_stream(self.device).cuda_stream
-        return 0
+        """(raw handle, context manager): torch's own work of a call (copies, all_to_all, the symmetric-memory barriers) must be ordered on
+        the same stream as the C-ABI kernels, so a foreign handle is entered as torch's current stream for the duration of the call"""
+        import contextlib
+
+        if self.device.type != "cuda":
+            return int(stream or 0), contextlib.nullcontext()
+        cur = self.torch.cuda.current_stream(self.device).cuda_stream
+        if stream is None or int(stream) == cur:
+            return cur, contextlib.nullcontext()
+        return int(stream), self.torch.cuda.stream(self.torch.cuda.ExternalStream(int(stream), device=self.device))
 
     def _pick(self, ptr: int):
         for t in (self.buf_a, self.buf_b, self.recv):
@@ -189,32 +194,34 @@ class ShardedNtt:
         """x: this rank's column block (module docstring); never written.  Returns this rank's row block in a buffer owned by this
         object (valid until the next forward / inverse call).  Work is queued on torch's current stream."""
         l1, l2, lg, ops = self.l1, self.l2, self.lg, self.ops
-        stream = self._stream(stream)
+        stream, ctx = self._stream(stream)
         if x.numel() != self.local_elems * 32:
             raise ValueError("shard size mismatch")
         A, B = self.buf_a, self.buf_b
-        ops.exchange(x.data_ptr(), l1, l2 - lg, 0, None, 0, False, [A.data_ptr()], 1 << l1, 0, stream)            # 1. At[i2l][i1]
-        p = self._pick(ops.batch_ntt(A.data_ptr(), B.data_ptr(), l1, 1 << (l2 - lg), self.omega_rows, False, stream))   # 2. Yt[i2l][j1]
-        q = B if p is A else A
-        z = self._exchange(p, q, l2 - lg, l1, False, stream)                                                       # 3. Z[j1l][i2]
-        return self._pick(ops.batch_ntt(z.data_ptr(), A.data_ptr(), l2, 1 << (l1 - lg), self.omega_cols, False, stream))  # 4. X[j1l][j2]
+        with ctx:
+            ops.exchange(x.data_ptr(), l1, l2 - lg, 0, None, 0, False, [A.data_ptr()], 1 << l1, 0, stream)            # 1. At[i2l][i1]
+            p = self._pick(ops.batch_ntt(A.data_ptr(), B.data_ptr(), l1, 1 << (l2 - lg), self.omega_rows, False, stream))   # 2. Yt[i2l][j1]
+            q = B if p is A else A
+            z = self._exchange(p, q, l2 - lg, l1, False, stream)                                                       # 3. Z[j1l][i2]
+            return self._pick(ops.batch_ntt(z.data_ptr(), A.data_ptr(), l2, 1 << (l1 - lg), self.omega_cols, False, stream))  # 4. X[j1l][j2]
 
     def inverse(self, y, stream=None):
         """y: this rank's row block (the layout forward() returns).  Returns the column block of (1/n) DFT_{omega^-1}."""
         l1, l2, lg, ops = self.l1, self.l2, self.lg, self.ops
-        stream = self._stream(stream)
+        stream, ctx = self._stream(stream)
         if y.numel() != self.local_elems * 32:
             raise ValueError("shard size mismatch")
         A, B = self.buf_a, self.buf_b
-        if y.data_ptr() == B.data_ptr():
-            src, scratch = B, A
-        else:
-            if y.data_ptr() != A.data_ptr():
-                A.copy_(y)                           # the transforms ping-pong between their two buffers: keep the caller's (or recv) intact
-            src, scratch = A, B
-        p = self._pick(ops.batch_ntt(src.data_ptr(), scratch.data_ptr(), l2, 1 << (l1 - lg), self.omega_cols, True, stream))   # Z[j1l][i2]
-        q = B if p is A else A
-        w = self._exchange(p, q, l1 - lg, l2, True, stream)                                                        # W[i2l][j1]
-        p = self._pick(ops.batch_ntt(w.data_ptr(), A.data_ptr(), l1, 1 << (l2 - lg), self.omega_rows, True, stream))    # At[i2l][i1]
-        ops.exchange(p.data_ptr(), l2 - lg, l1, 0, None, 0, False, [B.data_ptr()], 1 << (l2 - lg), 0, stream)       # A[i1][i2l]
-        return B
+        with ctx:
+            if y.data_ptr() == B.data_ptr():
+                src, scratch = B, A
+            else:
+                if y.data_ptr() != A.data_ptr():
+                    A.copy_(y)                       # the transforms ping-pong between their two buffers: keep the caller's (or recv) intact
+                src, scratch = A, B
+            p = self._pick(ops.batch_ntt(src.data_ptr(), scratch.data_ptr(), l2, 1 << (l1 - lg), self.omega_cols, True, stream))   # Z[j1l][i2]
+            q = B if p is A else A
+            w = self._exchange(p, q, l1 - lg, l2, True, stream)                                                        # W[i2l][j1]
+            p = self._pick(ops.batch_ntt(w.data_ptr(), A.data_ptr(), l1, 1 << (l2 - lg), self.omega_rows, True, stream))    # At[i2l][i1]
+            ops.exchange(p.data_ptr(), l2 - lg, l1, 0, None, 0, False, [B.data_ptr()], 1 << (l2 - lg), 0, stream)       # A[i1][i2l]
+            return B

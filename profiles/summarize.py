@@ -1,5 +1,6 @@
 """Turn gpurun_out/*.ncu-rep / launch-list CSVs into the small text summaries committed under profiles/.
-usage: python profiles/summarize.py launches <csv> <out.md> | full <ncu-rep> <out.md>"""
+usage: python profiles/summarize.py launches <csv> <out.md> | full <ncu-rep> <out.md> | traffic <ncu-rep> <log_n> [<ncu-rep> <log_n> ...]
+`traffic` rewrites profiles/ncu_traffic.json (dram bytes per launch of every captured kernel), the file bench.py reads roofline.traffic from."""
 import csv
 import subprocess
 import sys
@@ -19,6 +20,9 @@ KEYS = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
+    "lts__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "launch__waves_per_multiprocessor",
 ]
 
 
@@ -61,5 +65,35 @@ def full(path, out):
             f.write("\n")
 
 
+def to_bytes(value, unit):
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    return float(value.replace(",", "")) * scale.get(unit, 1)
+
+
+def traffic(args):
+    import json
+    import os
+    import re
+
+    out = {"source": "ncu --set full --clock-control none captures: " + ", ".join(args[0::2]) + " (profiles/summarize.py traffic)", "kernels": []}
+    for path, log_n in zip(args[0::2], args[1::2]):
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        h, units = rows[0], rows[1]
+        ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+        seen = set()
+        for r in rows[2:]:
+            name = re.sub(r"^void ", "", r[ki]).split("(")[0]
+            if name in seen:
+                continue
+            seen.add(name)
+            out["kernels"].append({"kernel": name, "log_n": int(log_n), "dram_bytes_read": to_bytes(r[ri], units[ri]), "dram_bytes_write": to_bytes(r[wi], units[wi])})
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -502,11 +502,12 @@ def test_config2_2_20_cached_bases_jacobian_and_projective(oracle, dev):
     assert ffi.lib.panda_msm_unregister_bases(d_b.ptr) == 0
     for b in (d_b, d_s, d_r):
         b.free()
-    m = gm.PandaGpuManager.init_all(0, gm.PandaGpuManagerInitUnitType.PandaGpuManagerInitUnitTypeMSM, [bases], [scal])
+    m = gm.PandaGpuManager.init_all(0, gm.PandaGpuManagerInitUnitType.PandaGpuManagerInitUnitTypeMSM, [bases], None)
     try:
-        assert (oracle.jac_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_input(m, 0, 0)) == exp).all()
+        si = m.cache_scalars(scal)
+        assert (oracle.jac_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_input(m, si, 0)) == exp).all()
         m.set_config(gm.PandaMSMResultCoordinateType.Projective)
-        assert (oracle.proj_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_input(m, 0, 0)) == exp).all()
+        assert (oracle.proj_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_input(m, si, 0)) == exp).all()
         assert (oracle.proj_to_affine(0, gm.panda_msm_bn254_gpu_with_cached_bases(m, scal, 0)) == exp).all()
     finally:
         m.deinit()
