@@ -16,6 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpanda_oracle.so")
 REF_BIN = os.path.join(_HERE, "_ref", "ref_host_msm")
+REF_GPU_BIN = os.path.join(_HERE, "_ref", "ref_gpu_msm")
 REFERENCE_ROOT = "/root/reference"
 
 F_BN254_FQ, F_BN254_FR, F_BLS377_FQ, F_BLS377_FR = 0, 1, 2, 3
@@ -38,7 +39,7 @@ def build(force: bool = False) -> str:
 
 
 def build_ref() -> str | None:
-    if os.path.exists(REF_BIN):
+    if os.path.exists(REF_BIN) and os.path.exists(REF_GPU_BIN):
         return REF_BIN
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "cuda", "core")):
         return None
@@ -257,3 +258,20 @@ def ref_host_msm(bases, scalars, log_n, coord=0):
         proc = subprocess.run([REF_BIN, fb, fs, str(log_n), fo, str(coord)], capture_output=True, text=True, check=True)
         ms = float([l for l in proc.stdout.splitlines() if l.startswith("ref_time_ms")][0].split()[1])
         return np.fromfile(fo, dtype=np.uint8), ms
+
+
+def ref_gpu_available() -> bool:
+    return os.path.exists(REF_GPU_BIN)
+
+
+def ref_gpu_msm(bases, scalars, log_n, reps=3, timeout=600):
+    """Run the reference's OWN GPU MSM (panda_msm_execute_bn254, its kernels compiled unmodified for sm_100a) in a subprocess on
+    device 0.  Returns (96-byte Jacobian, best milliseconds, all milliseconds).  Diagnostic only."""
+    bases, scalars = _u8(bases), _u8(scalars)
+    with tempfile.TemporaryDirectory() as d:
+        fb, fs, fo = (os.path.join(d, x) for x in ("bases.bin", "scalars.bin", "out.bin"))
+        bases.tofile(fb)
+        scalars.tofile(fs)
+        proc = subprocess.run([REF_GPU_BIN, fb, fs, str(log_n), fo, str(reps)], capture_output=True, text=True, check=True, timeout=timeout)
+        vals = [float(v) for v in [l for l in proc.stdout.splitlines() if l.startswith("ref_gpu_ms")][0].split()[1:]]
+        return np.fromfile(fo, dtype=np.uint8), vals[0], vals[1:]

@@ -22,6 +22,7 @@ __global__ void k_field_op(int op, const uint32_t *a, const uint32_t *b, uint32_
             case PANDA_FOP_FROM_MONT: r = x.from_mont(); break;
             case PANDA_FOP_TO_MONT: r = x.to_mont(); break;
             case PANDA_FOP_INV: r = fe_inverse(x); break;
+            case PANDA_FOP_INV_GCD: r = fe_inverse_gcd(x); break;
             default: r = x.neg(); break;
         }
         r.canon().store(out + i * F::N);

@@ -23,6 +23,12 @@ struct Affine {
         a.y = F::load(reinterpret_cast<const uint32_t *>(p) + F::N);
         return a;
     }
+    PB_DEV static Affine load_gather(const void *p) {    // one point at a random address (bucket accumulation): 64-byte DRAM fetches
+        Affine a;
+        a.x = F::load_gather(p);
+        a.y = F::load_gather(reinterpret_cast<const uint32_t *>(p) + F::N);
+        return a;
+    }
     PB_DEV bool is_identity() const { return x.is_zero(); }
 };
 

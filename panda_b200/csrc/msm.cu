@@ -10,6 +10,7 @@
 #include "msm.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -31,6 +32,15 @@ cudaError_t msm_combine_bls12_377(const void *partials, uint32_t count, void *re
 
 // ----------------------------------------------------------------------------------------------------
 // plan
+
+// tunables of the batched-affine accumulation: environment at load time, msm_set_tuning (diagnostics / tests) afterwards
+static std::atomic<int> g_affine_rounds{[] { const char *e = getenv("PANDA_MSM_AFFINE"); return e ? atoi(e) : -1; }()};
+static std::atomic<int> g_affine_min_log{[] { const char *e = getenv("PANDA_MSM_AFFINE_MIN_LOG"); return e ? atoi(e) : 22; }()};
+
+void msm_set_tuning(int affine_min_log, int affine_rounds) {
+    if (affine_min_log >= 0) g_affine_min_log.store(affine_min_log);
+    if (affine_rounds >= -1) g_affine_rounds.store(affine_rounds);
+}
 
 static uint32_t windows_for(uint32_t bits, uint32_t c) {
     // signed digits need the top window to stay <= 2^(c-1) after the incoming carry: its bit width t must be <= c-1
@@ -133,14 +143,30 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
         if (forced) p.phases = std::min<uint32_t>(pow2_floor(forced), p.nb);
     }
 
-    // batched-affine bucket accumulation (table plan, one chunk): opt-in while it is being tuned (PANDA_MSM_AFFINE=1)
-    static const int affine_env = [] { const char *e = getenv("PANDA_MSM_AFFINE"); return e ? atoi(e) : 0; }();
-    p.affine = (folded && p.chunks == 1 && affine_env > 0 && n >= 4096) ? 1 : 0;
+    // batched-affine bucket accumulation (table plan): tree rounds of affine additions, 6 products per addition instead of 10, then the
+    // XYZZ pipeline on what is left (msm_affine.cuh).  PANDA_MSM_AFFINE = 0 switches it off, = r forces r rounds; PANDA_MSM_AFFINE_MIN_LOG
+    // is the smallest log2(entries) that uses it (every round costs a few small launches and one inversion latency).
+    const int affine_env = g_affine_rounds.load(), affine_min_log = g_affine_min_log.load();
+    p.affine = (folded && affine_env != 0 && entries >= (1ull << affine_min_log) && p.stride / p.nb >= 4) ? 1 : 0;
     if (p.affine) {
-        const uint64_t avg = std::max<uint64_t>(1, entries / p.nb);
-        uint32_t r = 1; while ((1ull << r) < 2 * avg) r++;          // buckets up to twice the average size end as one point
-        p.rounds = std::min<uint32_t>(std::max<uint32_t>(r + 1, 2), 24);
-        if (affine_env > 1) p.rounds = std::min<uint32_t>(affine_env, 24);
+        const uint64_t avg = std::max<uint64_t>(1, (uint64_t)p.stride / p.nb);      // entries per bucket of the largest chunk
+        uint32_t r = 1; while ((2ull << r) < 3 * avg) r++;                            // 2^r >= 1.5 * average: uniform buckets end as one point
+        p.rounds = std::min<uint32_t>(std::max<uint32_t>(r, 1), 16);
+        if (affine_env > 0) p.rounds = std::min<uint32_t>(affine_env, 16);
+        // capacity of the point lists: round r writes at most in/2 + nb points (every bucket may carry one odd entry over)
+        uint64_t cap = p.stride;
+        for (uint32_t i = 0; i < p.rounds; i++) {
+            cap = std::min<uint64_t>(cap, cap / 2 + p.nb);
+            if (i == 0) p.aff_cap_a = cap;
+            if (i == 1) p.aff_cap_b = cap;
+        }
+        if (p.rounds < 2) p.aff_cap_b = 1;
+        // the XYZZ tail runs over the final point lists (`cap` points per chunk at most, about one per bucket)
+        p.seg_len = seg_override ? seg_override : 8;
+        p.segs_ps = (uint32_t)((cap + p.seg_len - 1) / p.seg_len);
+        p.aff_ctas = 148 * (curve == CURVE_BLS12_377 ? 2 : 3);  // persistent CTAs: as many as fit an SM (launch bounds of aff_round_fused)
+        static const int stagger = [] { const char *e = getenv("PANDA_MSM_AFFINE_STAGGER_NS"); return e ? atoi(e) : 0; }();
+        p.aff_stagger_ns = (uint32_t)std::max(0, stagger);
     }
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
@@ -156,18 +182,11 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.off_chunks = off;  off = align(off + (size_t)p.sets * p.chunks_ps * 2 * 4 * fq_bytes);
     p.off_gsums = off;   off = align(off + (size_t)p.sets * (p.groups + 1) * 2 * 4 * fq_bytes);   // + the second stitch level
     if (p.affine) {
-        // outputs of round r: at most in/2 + nb (every bucket may carry one odd entry over)
-        const uint64_t out0 = std::min<uint64_t>(p.stride, (uint64_t)p.stride / 2 + p.nb);
-        const uint64_t out1 = std::min<uint64_t>(out0, out0 / 2 + p.nb);
-        const uint64_t per_cta = 256 * 32;
-        p.aff_ctas = (uint32_t)((out0 + per_cta - 1) / per_cta);
-        p.off_aff_a = off;    off = align(off + out0 * 2 * fq_bytes);
-        p.off_aff_b = off;    off = align(off + out1 * 2 * fq_bytes);
-        p.off_aff_pre = off;  off = align(off + (uint64_t)p.aff_ctas * per_cta * fq_bytes);
-        p.off_aff_tot = off;  off = align(off + (uint64_t)p.aff_ctas * 256 * fq_bytes);
-        p.off_aff_cta = off;  off = align(off + (uint64_t)p.aff_ctas * 3 * fq_bytes + 256);
-        p.off_aff_offs = off; off = align(off + (size_t)p.rounds * (p.nb + 1) * 4);
-        p.off_slots = p.off_aff_a;      // no partial-sum slots in this plan: the region is not used
+        const uint64_t per_cta = 128 * 128;              // AFF_PER_CTA (msm_affine.cuh)
+        p.off_aff_a = off;    off = align(off + (size_t)p.chunks * p.aff_cap_a * 2 * fq_bytes);
+        p.off_aff_b = off;    off = align(off + (size_t)p.chunks * p.aff_cap_b * 2 * fq_bytes);
+        p.off_aff_pre = off;  off = align(off + (size_t)p.chunks * p.aff_ctas * per_cta * fq_bytes);     // scratch ring of the persistent CTAs
+        p.off_aff_offs = off; off = align(off + (size_t)p.rounds * p.chunks * (p.nb + 1) * 4);
     }
     p.bytes = off;
     return p;
@@ -250,9 +269,23 @@ static size_t table_budget_bytes() {
 
 #define PB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[panda-b200] CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); return e_; } } while (0)
 
+// PANDA_L2_FETCH = 32 | 64 | 128: cudaLimitMaxL2FetchGranularity for the devices this library runs on (tuning experiment: the 64-byte point
+// gathers arrive as 128-byte lines by default)
+static void apply_l2_fetch_limit() {
+    static const int bytes = [] { const char *e = getenv("PANDA_L2_FETCH"); return e ? atoi(e) : 0; }();
+    static std::atomic<unsigned long long> done{0};
+    if (!bytes) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return;
+    const unsigned long long bit = 1ull << dev;
+    if (done.fetch_or(bit) & bit) return;
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes) != cudaSuccess) cudaGetLastError();
+}
+
 static cudaError_t run_pipeline(CurveId curve, const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord,
                                 cudaMemPool_t pool, cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed = nullptr) {
     if (timings) { timings->folded = (int)p.folded; timings->c = p.c; timings->windows = p.windows; }
+    apply_l2_fetch_limit();
     if (curve == CURVE_BLS12_377) return msm_pipeline_bls12_377(p, points, scalars, result, coord, pool, stream, timings, feed);
     return msm_pipeline_bn254(p, points, scalars, result, coord, pool, stream, timings, feed);
 }

@@ -252,6 +252,11 @@ panda_error panda_ntt_tear_down(void) {       // the current device's NTT unit: 
 
 // ---- diagnostics (include/panda_debug.h) --------------------------------------------------------------------------
 
+panda_error panda_debug_msm_tuning(int affine_min_log, int affine_rounds) {
+    pb::msm_set_tuning(affine_min_log, affine_rounds);
+    return panda_success;
+}
+
 panda_error panda_debug_ntt_timed(const panda_ntt_configuration_v1 cfg, int inverse, float *pass_ms) {
     if (!cfg.d_omega || !cfg.flag || !cfg.d_src || !cfg.d_dst || !pass_ms) return perr(cudaErrorInvalidValue);
     unsigned in_dst = 0;

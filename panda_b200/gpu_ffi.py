@@ -282,6 +282,7 @@ SIGNATURES: dict[str, list] = {
     "panda_debug_msm_streamed": [_int, MSMConfiguration, SizeT, _int, _uint],
     "panda_debug_int_peak": [_int, _uint, C.POINTER(C.c_float), C.POINTER(C.c_ulonglong)],
     "panda_debug_fr_pow2k_host": [_vp, _uint, _vp],
+    "panda_debug_msm_tuning": [_int, _int],
     "panda_debug_ntt_timed": [NttconfigurationV1, _int, C.POINTER(C.c_float)],
 }
 

@@ -5,7 +5,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-FIELD_OPS = [(0, "mul", 2), (1, "add", 2), (2, "sub", 2), (3, "sqr", 1), (4, "from_mont", 1), (5, "to_mont", 1), (6, "inv", 1), (7, "neg", 1)]
+FIELD_OPS = [(0, "mul", 2), (1, "add", 2), (2, "sub", 2), (3, "sqr", 1), (4, "from_mont", 1), (5, "to_mont", 1), (6, "inv", 1), (7, "neg", 1),
+             (8, "inv_gcd", 1)]
 
 
 @pytest.fixture(scope="module")
@@ -31,9 +32,9 @@ def test_field_ops_bit_exact(oracle, dev, fid):
         b[(3 - i) * fb:(4 - i) * fb] = v
     da, db, do = gu.DevBuf.from_numpy(a), gu.DevBuf.from_numpy(b), gu.DevBuf(a.size)
     ofn = {"mul": oracle.f_mul, "add": oracle.f_add, "sub": oracle.f_sub, "sqr": oracle.f_sqr, "from_mont": oracle.f_from_mont,
-           "to_mont": oracle.f_to_mont, "inv": oracle.f_inv, "neg": oracle.f_neg}
+           "to_mont": oracle.f_to_mont, "inv": oracle.f_inv, "neg": oracle.f_neg, "inv_gcd": oracle.f_inv}
     for op, name, arity in FIELD_OPS:
-        cnt = 512 if name == "inv" else n
+        cnt = 512 if name == "inv" else 2048 if name == "inv_gcd" else n
         assert ffi.lib.panda_debug_field_op(fid, op, da.ptr, db.ptr, do.ptr, cnt, ffi.PandaStream.null()) == 0
         assert ffi.lib.panda_stream_synchronize(ffi.PandaStream.null()) == 0
         got = do.to_numpy(cnt * fb)

@@ -389,20 +389,80 @@ def test_host_api_additions(oracle, dev):
         m.deinit()
 
 
-@pytest.mark.parametrize("k", [12, 15])
-def test_batched_affine_plan_opt_in(k):
-    """PANDA_MSM_AFFINE=1 (experimental plan, read once per process): tree rounds of batched affine additions with one field
-    inversion per round give the same point (closed form); tests/run_msm.py prints the verdict"""
-    import os
-    import subprocess
-    import sys
+@pytest.fixture
+def affine_everywhere(dev):
+    """the batched-affine accumulation normally starts at 2^22 bucket entries; the parity tests force it onto small cases"""
+    ffi, _gu = dev
+    assert ffi.lib.panda_debug_msm_tuning(0, -1) == 0
+    yield ffi
+    assert ffi.lib.panda_debug_msm_tuning(22, -1) == 0
 
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PANDA_MSM_AFFINE="1")
-    out = subprocess.run([sys.executable, os.path.join(root, "tests", "run_msm.py"), str(k), "1", "0", "0", "0", "2"], env=env, capture_output=True,
-                         text=True, timeout=600)
-    assert out.returncode == 0, out.stderr[-2000:]
-    assert "closed-form match: True" in out.stdout, out.stdout[-2000:]
+
+@pytest.mark.parametrize("k,curve,rounds", [(10, 0, -1), (12, 0, -1), (15, 0, -1), (18, 0, -1), (13, 0, 1), (13, 0, 2), (14, 0, 6), (14, 0, 12), (12, 1, -1), (14, 1, 3)])
+def test_batched_affine_plan(oracle, dev, affine_everywhere, k, curve, rounds):
+    """table plan with batched-affine tree rounds (one GCD inversion per 4096 additions) + XYZZ tail: automatic and forced round counts
+    (fewer rounds than the buckets need: the tail folds the rest; more: the extra rounds only carry points over), both curves, both coordinates"""
+    ffi, gu = dev
+    n = 1 << k
+    assert ffi.lib.panda_debug_msm_tuning(-1, rounds) == 0
+    bases = oracle.gen_bases(curve, 600 + k, n)
+    scal = oracle.gen_scalars(3 if curve else 1, 601 + k, n)
+    exp = oracle.jac_to_affine(curve, oracle.expected_progression_msm(curve, 600 + k, scal, n))
+    for coord in (0, 1):
+        got = gu.msm_device(bases, scal, n, coord, curve=curve, table_mode=2)
+        assert (affine(oracle, curve, got, coord) == exp).all(), coord
+    assert ffi.lib.panda_msm_tear_down() == 0
+
+
+@pytest.mark.parametrize("mode", ["all_equal", "small", "two_values", "top_heavy", "edge_bases", "golden_k13"])
+def test_batched_affine_plan_skew_and_edge_cases(oracle, dev, affine_everywhere, golden_k13, mode):
+    """the affine rounds meet P + P (tangent), P + (-P) (identity), identity operands, and buckets far larger than 2^rounds"""
+    ffi, gu = dev
+    k, n = 13, 1 << 13
+    bases = oracle.gen_bases(0, 5, n).reshape(n, 64).copy()
+    base = oracle.gen_scalars(1, 6, n).reshape(n, 32).copy()
+    if mode == "all_equal":
+        base[:] = base[0]
+    elif mode == "small":
+        small = np.zeros((n, 32), np.uint8); small[:, 0] = np.arange(n) % 3
+        base = oracle.f_to_mont(1, small.reshape(-1)).reshape(n, 32)
+    elif mode == "two_values":
+        base[::2] = base[0]; base[1::2] = base[1]
+    elif mode == "top_heavy":
+        small = np.zeros((n, 32), np.uint8); small[:, 0] = np.arange(n) % 7 + 1
+        base = oracle.f_neg(1, oracle.f_to_mont(1, small.reshape(-1))).reshape(n, 32)
+    elif mode == "edge_bases":       # identities, duplicates and negated pairs that share a scalar (so they meet in one bucket)
+        for i in range(0, n, 16):
+            bases[i] = 0
+            bases[i + 2] = bases[i + 1]; base[i + 2] = base[i + 1]
+            bases[i + 4] = bases[i + 3]; bases[i + 4, 32:] = oracle.f_neg(0, bases[i + 3, 32:].copy()); base[i + 4] = base[i + 3]
+    else:
+        bases, base = golden_k13["bases"].reshape(n, 64), golden_k13["scalars"].reshape(n, 32)      # 8192 copies of the generator
+    if mode == "golden_k13":
+        exp = golden_k13["result_affine"]
+    else:
+        exp = oracle.jac_to_affine(0, oracle.msm(0, bases.reshape(-1), base.reshape(-1), n, c=10))
+    for coord in (0, 1):
+        got = gu.msm_device(bases.reshape(-1), base.reshape(-1), n, coord, table_mode=2)
+        assert (affine(oracle, 0, got, coord) == exp).all(), coord
+    assert ffi.lib.panda_msm_tear_down() == 0
+
+
+def test_batched_affine_plan_streamed_chunks(oracle, dev, affine_everywhere):
+    """chunked (host scalars) pipeline on the affine plan: every chunk runs its own tree rounds, the chunks share the bucket reduction"""
+    ffi, gu = dev
+    n = 40001
+    bases = oracle.gen_bases(0, 650, n)
+    scal = oracle.gen_scalars(1, 651, n)
+    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, 650, scal, n))
+    d_b, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf(96)
+    s = ffi.PandaStream.new()
+    for chunks in (1, 2, 3, 5):
+        cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, scal.ctypes.data, d_r.ptr, 0, 0)
+        assert ffi.lib.panda_debug_msm_streamed(0, cfg, n, 2, chunks) == 0
+        s.sync()
+        assert (oracle.jac_to_affine(0, d_r.to_numpy()) == exp).all(), chunks
+    assert ffi.lib.panda_msm_tear_down() == 0
 
 
 @pytest.mark.parametrize("split", [2, 3])
