@@ -176,7 +176,7 @@ def run_reference_arm(args):
         rr = RefRunner(O, "ref")
         procs = rr.procs
         fixed, per_point, fit = rr.fit()
-        per_step = budget_s / max(1, args.steps + args.warmup)
+        per_step = min(budget_s / max(1, args.steps + args.warmup), 30.0)      # at most 30 s per step however few steps are asked for
         k_sample = 14
         while k_sample < 22 and fixed + per_point * (1 << (k_sample + 1)) <= per_step:
             k_sample += 1
@@ -708,24 +708,6 @@ def run_own_arm(args):
         except Exception as exc:
             bls = {"error": repr(exc)[:300]}
 
-    # ---- diagnostic (one GPU only): the reference's OWN GPU kernels (panda_msm_execute_bn254 of /root/reference, compiled unmodified for
-    #      sm_100a into oracle/_ref/ref_gpu_msm) on the same inputs, same box.  Not the reference arm (that is the CPU host path).
-    ref_gpu = None
-    if world == 1 and O.ref_gpu_available():
-        ref_gpu = {"what": "wall ms around the reference's synchronous panda_msm_execute_bn254 (msm_cuda.cuh:552-769), inputs resident on the device, "
-                           "best of 3 after one warm-up; result compared with this library's after normalising to affine"}
-        for kk in (20, LOG_N):
-            try:
-                nn = 1 << kk
-                bh = bases_h if kk == LOG_N else O.gen_bases(0, O.seed_for(kk), nn)
-                sh = scal_h if kk == LOG_N else O.gen_scalars(1, O.seed_for(kk) + 1, nn)
-                seed_k = seed if kk == LOG_N else O.seed_for(kk)
-                rj, best, allms = O.ref_gpu_msm(bh, sh, kk, reps=3, timeout=900)
-                exp_k = O.jac_to_affine(0, O.expected_progression_msm(0, seed_k, sh, nn))
-                ref_gpu[f"2^{kk}"] = {"reference_gpu_ms": best, "all_ms": allms, "matches_closed_form": bool((O.jac_to_affine(0, rj) == exp_k).all())}
-            except Exception as exc:
-                ref_gpu[f"2^{kk}"] = {"error": repr(exc)[:300]}
-
     cpu = cpu_baseline_leg(O, np)
     acc_traffic, acc_traffic_src = ncu_traffic(ACC_KERNEL.split(" ")[0], LOG_N) if n_local == 1 << LOG_N else (None, "per-rank point count differs from the captured 2^24 launch")
 
@@ -775,8 +757,6 @@ def run_own_arm(args):
         line["ntt_sharded"] = sharded_ntt
     if multi_capi is not None:
         line["msm_multi_capi"] = multi_capi
-    if ref_gpu is not None:
-        line["reference_gpu_kernels"] = ref_gpu
     emit(line)
     if world > 1:
         dist.destroy_process_group()

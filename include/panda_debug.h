@@ -12,16 +12,16 @@
 extern "C" {
 #endif
 
-/* field ids: 0 BN254 Fq, 1 BN254 Fr, 2 BLS12-377 Fq, 3 BLS12-377 Fr (same numbering as oracle/panda_oracle.c) */
+/* field ids: 0 BN254 Fq, 1 BN254 Fr, 2 BLS12-377 Fq, 3 BLS12-377 Fr, 4 BLS12-381 Fq, 5 BLS12-381 Fr (same numbering as oracle/panda_oracle.c;
+ * field 5 is 255 bits wide: canonical operands only, no PANDA_FOP_INV -- see Bls381Fr in csrc/field.cuh) */
 enum panda_debug_field_opcode {
     PANDA_FOP_MUL = 0, PANDA_FOP_ADD = 1, PANDA_FOP_SUB = 2, PANDA_FOP_SQR = 3, PANDA_FOP_FROM_MONT = 4,
-    PANDA_FOP_TO_MONT = 5, PANDA_FOP_INV = 6, PANDA_FOP_NEG = 7,
-    PANDA_FOP_INV_GCD = 8      /* the binary-GCD inversion of the batched-affine accumulation (0 -> 0, like PANDA_FOP_INV) */
+    PANDA_FOP_TO_MONT = 5, PANDA_FOP_INV = 6, PANDA_FOP_NEG = 7
 };
 /* out[i] = a[i] (op) b[i], canonical Montgomery limbs; b is ignored by unary ops */
 panda_error panda_debug_field_op(int field_id, int op, const void *a, const void *b, void *out, size_t count, panda_stream stream);
 
-/* curve ids: 0 BN254, 1 BLS12-377.  Points are Jacobian triples (x||y||z) except q of MADD (affine x||y). */
+/* curve ids: 0 BN254, 1 BLS12-377, 2 BLS12-381.  Points are Jacobian triples (x||y||z) except q of MADD (affine x||y). */
 enum panda_debug_curve_opcode {
     PANDA_COP_MADD = 0,        /* out = p + q(affine), through the XYZZ mixed addition the MSM uses */
     PANDA_COP_ADD = 1,         /* out = p + q, through the XYZZ addition */
@@ -57,11 +57,6 @@ panda_error panda_debug_msm_streamed(int curve_id, const panda_msm_configuration
  * 4 independent chains per thread.  Fills *ms (device time of the timed launch) and *ops (instructions of that kind /
  * modular products executed). */
 panda_error panda_debug_int_peak(int kind, unsigned iters, float *ms, unsigned long long *ops);
-
-/* Tunables of the batched-affine bucket accumulation (process-wide; the defaults come from the environment variables
- * PANDA_MSM_AFFINE_MIN_LOG and PANDA_MSM_AFFINE): affine_min_log >= 0 sets the smallest log2(n * windows) that uses the plan (-1: leave);
- * affine_rounds = -1 automatic round count, 0 plan off, r > 0 forces r tree rounds (-2: leave). */
-panda_error panda_debug_msm_tuning(int affine_min_log, int affine_rounds);
 
 /* panda_ntt_execute_bn254_v1 / panda_intt_execute_bn254_v1 with the device time of every pass (HOST float[4], unused entries 0).
  * Synchronises the stream. */

@@ -141,6 +141,18 @@ panda_error panda_msm_setup_bls12_377(void);
 panda_error panda_msm_execute_bls12_377(const panda_msm_configuration exec_cfg);
 panda_error panda_msm_execute_bls12_377_host(const panda_msm_configuration exec_cfg);   /* HOST pointers, 144-byte Jacobian result; see panda_msm_execute_bn254_host */
 
+/* BLS12-381 G1 (third curve; the reference's README.md:36 lists it as planned, it ships no parameters for it): same shapes as BLS12-377 --
+ * bases 96 B (x||y, 12 x u32 Montgomery), scalars 32 B (Fr, 255 bit, Montgomery), result 144 B.  Every entry point below exists for it under the
+ * same name with the curve replaced. */
+panda_error panda_msm_setup_bls12_381(void);
+panda_error panda_msm_execute_bls12_381(const panda_msm_configuration exec_cfg);
+panda_error panda_msm_execute_bls12_381_n(const panda_msm_configuration exec_cfg, size_t n);
+panda_error panda_msm_execute_bls12_381_host(const panda_msm_configuration exec_cfg);
+panda_error panda_msm_execute_bls12_381_host_scalars(const panda_msm_configuration exec_cfg, size_t n);
+panda_error panda_msm_register_bases_bls12_381(const void *d_bases, size_t n, panda_stream stream);
+panda_error panda_msm_combine_bls12_381(const void *partials, unsigned count, void *result,
+                                        panda_msm_result_coordinate_type coord, panda_stream stream);
+
 /* MSM over an arbitrary point count (a shard of a larger MSM): like panda_msm_execute_* but n need not be a
  * power of two; cfg.log_scalars_count is ignored. */
 panda_error panda_msm_execute_bn254_n(const panda_msm_configuration exec_cfg, size_t n);
@@ -229,6 +241,8 @@ panda_error panda_msm_execute_bn254_multi(const panda_msm_configuration *per_dev
 panda_error panda_msm_execute_bn254_multi_n(const panda_msm_configuration *per_device, const size_t *counts, int n_dev);
 panda_error panda_msm_execute_bls12_377_multi(const panda_msm_configuration *per_device, int n_dev);
 panda_error panda_msm_execute_bls12_377_multi_n(const panda_msm_configuration *per_device, const size_t *counts, int n_dev);
+panda_error panda_msm_execute_bls12_381_multi(const panda_msm_configuration *per_device, int n_dev);
+panda_error panda_msm_execute_bls12_381_multi_n(const panda_msm_configuration *per_device, const size_t *counts, int n_dev);
 
 /* Four-step NTT n = n1 * n2 (n1 = 2^floor(log_n / 2)) sharded over n_dev GPUs (a power of two <= 16, n_dev <= n1) with ONE exchange:
  * local transpose, batched n1-point transforms, panda_ntt_exchange_bn254 storing over NVLink straight into the peers' d_dst

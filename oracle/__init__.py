@@ -19,11 +19,11 @@ REF_BIN = os.path.join(_HERE, "_ref", "ref_host_msm")
 REF_GPU_BIN = os.path.join(_HERE, "_ref", "ref_gpu_msm")
 REFERENCE_ROOT = "/root/reference"
 
-F_BN254_FQ, F_BN254_FR, F_BLS377_FQ, F_BLS377_FR = 0, 1, 2, 3
-C_BN254, C_BLS377 = 0, 1
-FQ_OF = {C_BN254: F_BN254_FQ, C_BLS377: F_BLS377_FQ}
-FR_OF = {C_BN254: F_BN254_FR, C_BLS377: F_BLS377_FR}
-FQ_BYTES = {C_BN254: 32, C_BLS377: 48}
+F_BN254_FQ, F_BN254_FR, F_BLS377_FQ, F_BLS377_FR, F_BLS381_FQ, F_BLS381_FR = 0, 1, 2, 3, 4, 5
+C_BN254, C_BLS377, C_BLS381 = 0, 1, 2
+FQ_OF = {C_BN254: F_BN254_FQ, C_BLS377: F_BLS377_FQ, C_BLS381: F_BLS381_FQ}
+FR_OF = {C_BN254: F_BN254_FR, C_BLS377: F_BLS377_FR, C_BLS381: F_BLS381_FR}
+FQ_BYTES = {C_BN254: 32, C_BLS377: 48, C_BLS381: 48}
 
 # BN254 Fr 2^28-th root of unity, Montgomery form (reference curve/bn254/paramter.cuh:250-258)
 BN254_FR_OMEGA_2_28 = np.array(
@@ -272,6 +272,8 @@ def ref_gpu_msm(bases, scalars, log_n, reps=3, timeout=600):
         fb, fs, fo = (os.path.join(d, x) for x in ("bases.bin", "scalars.bin", "out.bin"))
         bases.tofile(fb)
         scalars.tofile(fs)
-        proc = subprocess.run([REF_GPU_BIN, fb, fs, str(log_n), fo, str(reps)], capture_output=True, text=True, check=True, timeout=timeout)
+        proc = subprocess.run([REF_GPU_BIN, fb, fs, str(log_n), fo, str(reps)], capture_output=True, text=True, timeout=timeout)
+        if proc.returncode != 0:
+            raise RuntimeError(f"ref_gpu_msm rc={proc.returncode}: {(proc.stderr or proc.stdout)[-300:].strip()}")
         vals = [float(v) for v in [l for l in proc.stdout.splitlines() if l.startswith("ref_gpu_ms")][0].split()[1:]]
         return np.fromfile(fo, dtype=np.uint8), vals[0], vals[1:]

@@ -78,8 +78,8 @@ static void parallel_for(long n, int threads, pf_body body, void *ctx) {
     for (int t = 0; t < threads; t++) if (th[t]) pthread_join(th[t], NULL);
 }
 
-enum { F_BN254_FQ = 0, F_BN254_FR = 1, F_BLS377_FQ = 2, F_BLS377_FR = 3, F_COUNT = 4 };
-enum { C_BN254 = 0, C_BLS377 = 1 };
+enum { F_BN254_FQ = 0, F_BN254_FR = 1, F_BLS377_FQ = 2, F_BLS377_FR = 3, F_BLS381_FQ = 4, F_BLS381_FR = 5, F_COUNT = 6 };
+enum { C_BN254 = 0, C_BLS377 = 1, C_BLS381 = 2 };
 
 static fctx FIELDS[F_COUNT];
 static int fields_ready = 0;
@@ -89,6 +89,10 @@ static const u64 MOD_BN254_FQ[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL
 static const u64 MOD_BN254_FR[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
 static const u64 MOD_BLS377_FQ[6] = {0x8508c00000000001ULL, 0x170b5d4430000000ULL, 0x1ef3622fba094800ULL,
                                      0x1a22d9f300f5138fULL, 0xc63b05c06ca1493bULL, 0x01ae3a4617c510eaULL};
+/* BLS12-381 (not in the reference's parameter files; README.md:36 lists the curve as planned): the standard moduli */
+static const u64 MOD_BLS381_FQ[6] = {0xb9feffffffffaaabULL, 0x1eabfffeb153ffffULL, 0x6730d2a0f6b0f624ULL,
+                                      0x64774b84f38512bfULL, 0x4b1ba7b6434bacd7ULL, 0x1a0111ea397fe69aULL};
+static const u64 MOD_BLS381_FR[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
 static const u64 MOD_BLS377_FR[4] = {0x0a11800000000001ULL, 0x59aa76fed0000001ULL, 0x60b44d1e5c37b001ULL, 0x12ab655e9a2ca556ULL};
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -205,10 +209,12 @@ static void ensure_fields(void) {
     field_init(&FIELDS[F_BN254_FR], MOD_BN254_FR, 4);
     field_init(&FIELDS[F_BLS377_FQ], MOD_BLS377_FQ, 6);
     field_init(&FIELDS[F_BLS377_FR], MOD_BLS377_FR, 4);
+    field_init(&FIELDS[F_BLS381_FQ], MOD_BLS381_FQ, 6);
+    field_init(&FIELDS[F_BLS381_FR], MOD_BLS381_FR, 4);
     fields_ready = 1;
 }
-static const fctx *fq_of(int cid) { ensure_fields(); return &FIELDS[cid == C_BLS377 ? F_BLS377_FQ : F_BN254_FQ]; }
-static const fctx *fr_of(int cid) { ensure_fields(); return &FIELDS[cid == C_BLS377 ? F_BLS377_FR : F_BN254_FR]; }
+static const fctx *fq_of(int cid) { ensure_fields(); return &FIELDS[cid == C_BLS381 ? F_BLS381_FQ : cid == C_BLS377 ? F_BLS377_FQ : F_BN254_FQ]; }
+static const fctx *fr_of(int cid) { ensure_fields(); return &FIELDS[cid == C_BLS381 ? F_BLS381_FR : cid == C_BLS377 ? F_BLS377_FR : F_BN254_FR]; }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* curve: Jacobian (the reference calls it "Projective"), a = 0                                      */
@@ -411,8 +417,9 @@ void po_proj_to_affine(int cid, const void *p, void *out, size_t count) {
 /* y^2 == x^3 + b (b = 3 for BN254, 1 for BLS12-377); identity (x == 0) counts as on-curve */
 int po_aff_on_curve(int cid, const void *p, size_t count) {
     const fctx *f = fq_of(cid); const int nb = 8 * f->nl;
-    u64 b[MAXL]; memcpy(b, f->one, sizeof b);
+    u64 b[MAXL]; memcpy(b, f->one, sizeof b);                       /* y^2 = x^3 + b: b = 3 (BN254), 1 (BLS12-377), 4 (BLS12-381) */
     if (cid == C_BN254) { u64 t[MAXL]; f_add(f, t, b, b); f_add(f, b, t, b); }
+    if (cid == C_BLS381) { f_add(f, b, b, b); f_add(f, b, b, b); }
     for (size_t i = 0; i < count; i++) {
         aff a; ld_aff(f, &a, (const uint8_t *)p + i * 2 * nb);
         if (aff_is_zero(f, &a)) continue;
@@ -562,10 +569,16 @@ static const u64 BLS377_GX[6] = {0xeab9b16eb21be9efULL, 0xd5481512ffcd394eULL, 0
 static const u64 BLS377_GY[6] = {0xfd82de55559c8ea6ULL, 0xc2fe3d3634a9591aULL, 0x6d182ad44fb82305ULL,
                                  0xbd7fb348ca3e52d9ULL, 0x1f674f5d30afeec4ULL, 0x01914a69c5102eff};
 
+static const u64 BLS381_GX[6] = {0xfb3af00adb22c6bbULL, 0x6c55e83ff97a1aefULL, 0xa14e3a3f171bac58ULL,
+                                 0xc3688c4f9774b905ULL, 0x2695638c4fa9ac0fULL, 0x17f1d3a73197d794ULL};
+static const u64 BLS381_GY[6] = {0x0caa232946c5e7e1ULL, 0xd03cc744a2888ae4ULL, 0x00db18cb2c04b3edULL,
+                                 0xfcf5e095d5d00af6ULL, 0xa09e30ed741d8ae4ULL, 0x08b3f481e3aaa0f1ULL};
+
 static void curve_generator(int cid, aff *g) {
     const fctx *fq = fq_of(cid);
     memset(g, 0, sizeof *g);
     if (cid == C_BN254) { u64 one[MAXL] = {1}, two[MAXL] = {2}; f_to_mont(fq, g->x, one); f_to_mont(fq, g->y, two); }
+    else if (cid == C_BLS381) { f_to_mont(fq, g->x, BLS381_GX); f_to_mont(fq, g->y, BLS381_GY); }
     else { f_to_mont(fq, g->x, BLS377_GX); f_to_mont(fq, g->y, BLS377_GY); }
 }
 void po_generator(int cid, void *out_aff) { const fctx *fq = fq_of(cid); aff g; curve_generator(cid, &g); st_aff(fq, (uint8_t *)out_aff, &g); }

@@ -22,7 +22,6 @@ __global__ void k_field_op(int op, const uint32_t *a, const uint32_t *b, uint32_
             case PANDA_FOP_FROM_MONT: r = x.from_mont(); break;
             case PANDA_FOP_TO_MONT: r = x.to_mont(); break;
             case PANDA_FOP_INV: r = fe_inverse(x); break;
-            case PANDA_FOP_INV_GCD: r = fe_inverse_gcd(x); break;
             default: r = x.neg(); break;
         }
         r.canon().store(out + i * F::N);
@@ -132,6 +131,8 @@ panda_error panda_debug_field_op(int field_id, int op, const void *a, const void
         case 1: return launch_field<FrBn254>(op, a, b, out, count, s);
         case 2: return launch_field<FqBls377>(op, a, b, out, count, s);
         case 3: return launch_field<FrBls377>(op, a, b, out, count, s);
+        case 4: return launch_field<Fe<Bls381Fq>>(op, a, b, out, count, s);
+        case 5: return launch_field<Fe<Bls381Fr>>(op, a, b, out, count, s);      // canonical operands only: see Bls381Fr in field.cuh
     }
     return (panda_error)cudaErrorInvalidValue;
 }
@@ -140,6 +141,7 @@ panda_error panda_debug_curve_op(int curve_id, int op, const void *p, const void
     cudaStream_t s = (cudaStream_t)stream.handle;
     if (curve_id == 0) return launch_curve<FqBn254>(op, p, q, out, count, s);
     if (curve_id == 1) return launch_curve<FqBls377>(op, p, q, out, count, s);
+    if (curve_id == 2) return launch_curve<Fe<Bls381Fq>>(op, p, q, out, count, s);
     return (panda_error)cudaErrorInvalidValue;
 }
 

@@ -120,6 +120,50 @@ struct Bls377Fr {
     }
 };
 
+// BLS12-381 (no parameter file in the reference; README.md:36 lists the curve as planned): standard moduli, constants derived like the others.
+struct Bls381Fq {
+    static constexpr int N = 12;
+    static constexpr int BITS = 381;
+    static constexpr uint32_t NINV = 0xfffcfffdu;
+    PB_DEV static constexpr uint32_t mod(int i) {
+        constexpr uint32_t v[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                    0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t one(int i) {
+        constexpr uint32_t v[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                                    0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t r2(int i) {
+        constexpr uint32_t v[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
+                                    0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+        return v[i];
+    }
+};
+
+// 255-bit scalar field: 4r > 2^256, so the lazy [0, 2p) domain of Fe does NOT close under multiplication for this modulus and the
+// folded square (which accumulates doubled terms) lacks its spare bit.  The MSM only ever takes canonical scalars out of Montgomery form
+// (from_mont: one product of a value < r by 1, then canon), which is exact; mul / add / sub / to_mont are exact on canonical operands
+// (tests/test_gpu_field_curve.py), sqr and fe_inverse must not be used with this parameter set.
+struct Bls381Fr {
+    static constexpr int N = 8;
+    static constexpr int BITS = 255;
+    static constexpr uint32_t NINV = 0xffffffffu;
+    PB_DEV static constexpr uint32_t mod(int i) {
+        constexpr uint32_t v[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t one(int i) {
+        constexpr uint32_t v[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return v[i];
+    }
+    PB_DEV static constexpr uint32_t r2(int i) {
+        constexpr uint32_t v[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return v[i];
+    }
+};
+
 // 2p limb i (p < 2^(32N-1) for every field here, so 2p fits N limbs)
 template <class P>
 PB_DEV constexpr uint32_t mod2(int i) {
@@ -386,86 +430,6 @@ PB_DEV Fe<P> fe_inverse(const Fe<P> &a) {
         base = base.sqr();
     }
     return acc;
-}
-
-// a^-1 by the binary extended Euclidean algorithm (HAC 14.61 for an odd modulus); Montgomery in / out, a != 0 (0 returns 0).
-// Shifts, adds and compares only: about 25 k ALU-pipe instructions and no multiplications at all, against the 380 dependent
-// Montgomery products (52 k IMAD.WIDE) of the Fermat version -- the multiply pipe is the resource the MSM kernels saturate, the
-// ALU pipe is mostly idle, so this is the inversion the batched-affine accumulation calls (once per 4096 additions, by one thread).
-// The control flow is data dependent: meant for a single active lane.
-template <class P>
-__device__ __noinline__ Fe<P> fe_inverse_gcd(Fe<P> am) {
-    constexpr int N = P::N;
-    const Fe<P> a = am.canon();
-    if (a.is_zero_raw()) return Fe<P>::zero();
-    uint32_t u[N], v[N], x1[N], x2[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) { u[i] = a.l[i]; v[i] = P::mod(i); x1[i] = i == 0; x2[i] = 0; }
-    auto shr1 = [](uint32_t *t, uint32_t top) {
-#pragma unroll
-        for (int i = 0; i < N - 1; i++) t[i] = __funnelshift_r(t[i], t[i + 1], 1);
-        t[N - 1] = (t[N - 1] >> 1) | (top << 31);
-    };
-    auto halve_mod = [&](uint32_t *t) {        // t / 2 mod p for t in [0, p): p is added first when t is odd (the sum may need one more bit)
-        uint32_t carry = 0;
-        if (t[0] & 1) {
-            t[0] = ptx::add_cc(t[0], P::mod(0));
-#pragma unroll
-            for (int i = 1; i < N; i++) t[i] = ptx::addc_cc(t[i], P::mod(i));
-            carry = ptx::addc(0, 0);
-        }
-        shr1(t, carry);
-    };
-    auto is_one = [](const uint32_t *t) {
-        uint32_t r = t[0] ^ 1u;
-#pragma unroll
-        for (int i = 1; i < N; i++) r |= t[i];
-        return r == 0;
-    };
-    auto sub_mod = [](uint32_t *t, const uint32_t *s) {   // t = t - s mod p, both in [0, p)
-        t[0] = ptx::sub_cc(t[0], s[0]);
-#pragma unroll
-        for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(t[i], s[i]);
-        const uint32_t borrow = ptx::subc(0, 0);
-        if (borrow) {
-            t[0] = ptx::add_cc(t[0], P::mod(0));
-#pragma unroll
-            for (int i = 1; i < N - 1; i++) t[i] = ptx::addc_cc(t[i], P::mod(i));
-            t[N - 1] = ptx::addc(t[N - 1], P::mod(N - 1));
-        }
-    };
-    const uint32_t *res;
-#pragma unroll 1
-    for (;;) {
-#pragma unroll 1
-        while (!(u[0] & 1)) { shr1(u, 0); halve_mod(x1); }
-        if (is_one(u)) { res = x1; break; }
-#pragma unroll 1
-        while (!(v[0] & 1)) { shr1(v, 0); halve_mod(x2); }
-        if (is_one(v)) { res = x2; break; }
-        // both odd and different (gcd = 1): subtract the smaller from the larger
-        uint32_t d[N];
-        d[0] = ptx::sub_cc(u[0], v[0]);
-#pragma unroll
-        for (int i = 1; i < N; i++) d[i] = ptx::subc_cc(u[i], v[i]);
-        const uint32_t borrow = ptx::subc(0, 0);
-        if (!borrow) {
-#pragma unroll
-            for (int i = 0; i < N; i++) u[i] = d[i];
-            sub_mod(x1, x2);
-        } else {
-            v[0] = ptx::sub_cc(v[0], u[0]);
-#pragma unroll
-            for (int i = 1; i < N - 1; i++) v[i] = ptx::subc_cc(v[i], u[i]);
-            v[N - 1] = ptx::subc(v[N - 1], u[N - 1]);
-            sub_mod(x2, x1);
-        }
-    }
-    // res = (a_mont)^-1 as a plain integer = a^-1 * R^-1; two Montgomery products by R^2 give a^-1 * R
-    Fe<P> r;
-#pragma unroll
-    for (int i = 0; i < N; i++) r.l[i] = res[i];
-    return Fe<P>::mul_inline(Fe<P>::mul_inline(r, Fe<P>::r2()), Fe<P>::r2());
 }
 
 using FqBn254 = Fe<Bn254Fq>;

@@ -19,11 +19,15 @@
 
 namespace pb {
 
-// per-curve instantiations (msm_bn254.cu / msm_bls12_377.cu)
+// per-curve instantiations (msm_bn254.cu / msm_bls12_377.cu / msm_bls12_381.cu)
 cudaError_t msm_pipeline_bn254(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
                                cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed);
 cudaError_t msm_pipeline_bls12_377(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
                                    cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed);
+cudaError_t msm_pipeline_bls12_381(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
+                                   cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed);
+cudaError_t msm_build_table_bls12_381(const void *bases, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, void *table, cudaStream_t stream);
+cudaError_t msm_combine_bls12_381(const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream);
 cudaError_t msm_build_table_bn254(const void *bases, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, void *table, cudaStream_t stream);
 cudaError_t msm_build_table_bls12_377(const void *bases, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, void *table, cudaStream_t stream);
 cudaError_t msm_fingerprint_launch(const void *data, size_t bytes, unsigned long long *d_out, cudaStream_t stream);
@@ -32,15 +36,6 @@ cudaError_t msm_combine_bls12_377(const void *partials, uint32_t count, void *re
 
 // ----------------------------------------------------------------------------------------------------
 // plan
-
-// tunables of the batched-affine accumulation: environment at load time, msm_set_tuning (diagnostics / tests) afterwards
-static std::atomic<int> g_affine_rounds{[] { const char *e = getenv("PANDA_MSM_AFFINE"); return e ? atoi(e) : -1; }()};
-static std::atomic<int> g_affine_min_log{[] { const char *e = getenv("PANDA_MSM_AFFINE_MIN_LOG"); return e ? atoi(e) : 22; }()};
-
-void msm_set_tuning(int affine_min_log, int affine_rounds) {
-    if (affine_min_log >= 0) g_affine_min_log.store(affine_min_log);
-    if (affine_rounds >= -1) g_affine_rounds.store(affine_rounds);
-}
 
 static uint32_t windows_for(uint32_t bits, uint32_t c) {
     // signed digits need the top window to stay <= 2^(c-1) after the incoming carry: its bit width t must be <= c-1
@@ -65,8 +60,8 @@ static bool balanced_windows(uint32_t bits, uint32_t c, uint32_t *W, uint32_t *w
 static uint32_t pow2_floor(uint64_t v) { uint32_t r = 1; while ((uint64_t)r * 2 <= v) r *= 2; return r; }
 
 MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget, uint32_t chunks) {
-    const uint32_t bits = curve == CURVE_BLS12_377 ? 253 : 254;
-    const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
+    const uint32_t bits = curve_scalar_bits(curve);
+    const size_t fq_bytes = curve_fq_bytes(curve);
     MsmPlan p{};
     p.n = n;
     p.table_n = n;
@@ -143,31 +138,6 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
         if (forced) p.phases = std::min<uint32_t>(pow2_floor(forced), p.nb);
     }
 
-    // batched-affine bucket accumulation (table plan): tree rounds of affine additions, 6 products per addition instead of 10, then the
-    // XYZZ pipeline on what is left (msm_affine.cuh).  PANDA_MSM_AFFINE = 0 switches it off, = r forces r rounds; PANDA_MSM_AFFINE_MIN_LOG
-    // is the smallest log2(entries) that uses it (every round costs a few small launches and one inversion latency).
-    const int affine_env = g_affine_rounds.load(), affine_min_log = g_affine_min_log.load();
-    p.affine = (folded && affine_env != 0 && entries >= (1ull << affine_min_log) && p.stride / p.nb >= 4) ? 1 : 0;
-    if (p.affine) {
-        const uint64_t avg = std::max<uint64_t>(1, (uint64_t)p.stride / p.nb);      // entries per bucket of the largest chunk
-        uint32_t r = 1; while ((2ull << r) < 3 * avg) r++;                            // 2^r >= 1.5 * average: uniform buckets end as one point
-        p.rounds = std::min<uint32_t>(std::max<uint32_t>(r, 1), 16);
-        if (affine_env > 0) p.rounds = std::min<uint32_t>(affine_env, 16);
-        // capacity of the point lists: round r writes at most in/2 + nb points (every bucket may carry one odd entry over)
-        uint64_t cap = p.stride;
-        for (uint32_t i = 0; i < p.rounds; i++) {
-            cap = std::min<uint64_t>(cap, cap / 2 + p.nb);
-            if (i == 0) p.aff_cap_a = cap;
-            if (i == 1) p.aff_cap_b = cap;
-        }
-        if (p.rounds < 2) p.aff_cap_b = 1;
-        // the XYZZ tail runs over the final point lists (`cap` points per chunk at most, about one per bucket)
-        p.seg_len = seg_override ? seg_override : 8;
-        p.segs_ps = (uint32_t)((cap + p.seg_len - 1) / p.seg_len);
-        p.aff_ctas = 148 * (curve == CURVE_BLS12_377 ? 2 : 3);  // persistent CTAs: as many as fit an SM (launch bounds of aff_round_fused)
-        static const int stagger = [] { const char *e = getenv("PANDA_MSM_AFFINE_STAGGER_NS"); return e ? atoi(e) : 0; }();
-        p.aff_stagger_ns = (uint32_t)std::max(0, stagger);
-    }
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     const size_t phys = (size_t)p.sets * p.chunks;                              // physical bucket sets
@@ -181,13 +151,6 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.off_slots = off;   off = align(off + phys * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);
     p.off_chunks = off;  off = align(off + (size_t)p.sets * p.chunks_ps * 2 * 4 * fq_bytes);
     p.off_gsums = off;   off = align(off + (size_t)p.sets * (p.groups + 1) * 2 * 4 * fq_bytes);   // + the second stitch level
-    if (p.affine) {
-        const uint64_t per_cta = 128 * 128;              // AFF_PER_CTA (msm_affine.cuh)
-        p.off_aff_a = off;    off = align(off + (size_t)p.chunks * p.aff_cap_a * 2 * fq_bytes);
-        p.off_aff_b = off;    off = align(off + (size_t)p.chunks * p.aff_cap_b * 2 * fq_bytes);
-        p.off_aff_pre = off;  off = align(off + (size_t)p.chunks * p.aff_ctas * per_cta * fq_bytes);     // scratch ring of the persistent CTAs
-        p.off_aff_offs = off; off = align(off + (size_t)p.rounds * p.chunks * (p.nb + 1) * 4);
-    }
     p.bytes = off;
     return p;
 }
@@ -287,6 +250,7 @@ static cudaError_t run_pipeline(CurveId curve, const MsmPlan &p, const void *poi
     if (timings) { timings->folded = (int)p.folded; timings->c = p.c; timings->windows = p.windows; }
     apply_l2_fetch_limit();
     if (curve == CURVE_BLS12_377) return msm_pipeline_bls12_377(p, points, scalars, result, coord, pool, stream, timings, feed);
+    if (curve == CURVE_BLS12_381) return msm_pipeline_bls12_381(p, points, scalars, result, coord, pool, stream, timings, feed);
     return msm_pipeline_bn254(p, points, scalars, result, coord, pool, stream, timings, feed);
 }
 
@@ -298,7 +262,8 @@ static cudaError_t build_table_locked(TableEntry *hit, CurveId curve, const void
     auto buf = std::make_shared<TableBuf>();
     PB_CUDA(cudaGetDevice(&buf->device));
     if (cudaMalloc(&buf->ptr, fp_plan.table_bytes) != cudaSuccess) { cudaGetLastError(); buf->ptr = nullptr; return cudaSuccess; }
-    cudaError_t be = curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, buf->ptr, stream)
+    cudaError_t be = curve == CURVE_BLS12_381 ? msm_build_table_bls12_381(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, buf->ptr, stream)
+                   : curve == CURVE_BLS12_377 ? msm_build_table_bls12_377(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, buf->ptr, stream)
                                               : msm_build_table_bn254(bases, n, fp_plan.c, fp_plan.windows, fp_plan.wide, buf->ptr, stream);
     if (be == cudaSuccess) be = cudaEventCreateWithFlags(&buf->ready, cudaEventDisableTiming);
     if (be == cudaSuccess) be = cudaEventRecord(buf->ready, stream);
@@ -354,7 +319,7 @@ static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, c
                                  std::shared_ptr<TableBuf> *table, uint32_t *tc, uint32_t *table_n) {
     table->reset();
     *table_n = n;
-    const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
+    const size_t fq_bytes = curve_fq_bytes(curve);
     if (table_mode == MSM_TABLE_DEFAULT) table_mode = default_table_mode();
     if (table_mode == MSM_TABLE_OFF || n < 1024) return cudaSuccess;
     int dev = 0;
@@ -414,7 +379,7 @@ static uint32_t resident_chunks(uint32_t n);
 
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
                     cudaMemPool_t pool, cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings, int table_mode) {
-    const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
+    const size_t fq_bytes = curve_fq_bytes(curve);
     if (n == 0) {   // empty sum: the identity, all-zero like the reference (msm_cuda.cuh:395,405)
         PB_CUDA(cudaMemsetAsync(result, 0, 3 * fq_bytes, stream));
         return cudaSuccess;
@@ -459,18 +424,19 @@ static cudaError_t side_stream_for_current_device(int which, cudaStream_t *out) 
 static cudaError_t copy_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(0, out); }
 static cudaError_t aux_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(1, out); }
 
-// chunks of a device-resident table-plan MSM.  Splitting in two (the second chunk's sort hides behind the first chunk's accumulation
-// on the higher-priority auxiliary stream) was measured at 2^24: the overlap wins 2 ms, the second set of partial sums costs 3
-// (40.7 vs 39.6 ms), so the default is one chunk; PANDA_MSM_SPLIT = q forces q chunks (tests, tuning).
+// chunks of a device-resident table-plan MSM: chunk q+1 sorts on the higher-priority auxiliary stream while chunk q accumulates, and every chunk's
+// scatter passes re-read only its own codes.  Measured (profiles/r2_sweep.md, product entry point): 2^24 38.4 vs 37.6 ms and 2^25 74.3 vs 73.6 ms
+// for 2 chunks vs 1 -- the second set of partial sums costs more than the overlap wins; 2^26 (where the scatter makes 32 passes over 3.2 GB of codes,
+// 16 % of the step) 143.8 ms with 4 chunks against 151.8 with 1 and 147.1 with 8.  PANDA_MSM_SPLIT = q forces q chunks (tests, tuning).
 static uint32_t resident_chunks(uint32_t n) {
     static const int forced = [] { const char *v = getenv("PANDA_MSM_SPLIT"); return v ? atoi(v) : 0; }();
-    (void)n;
-    return forced > 0 ? (uint32_t)forced : 1;
+    if (forced > 0) return (uint32_t)forced;
+    return n >= (1u << 26) ? 4 : 1;
 }
 
 cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_scalars, uint32_t n, void *result, CoordType coord,
                              cudaMemPool_t pool, cudaStream_t stream, int table_mode, uint32_t chunks_override) {
-    const size_t fq_bytes = curve == CURVE_BLS12_377 ? 48 : 32;
+    const size_t fq_bytes = curve_fq_bytes(curve);
     if (n == 0) {
         PB_CUDA(cudaMemsetAsync(result, 0, 3 * fq_bytes, stream));
         return cudaSuccess;
@@ -506,6 +472,7 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
 
 cudaError_t msm_combine(CurveId curve, const void *partials, uint32_t count, void *result, CoordType coord, cudaStream_t stream) {
     if (curve == CURVE_BLS12_377) return msm_combine_bls12_377(partials, count, result, coord, stream);
+    if (curve == CURVE_BLS12_381) return msm_combine_bls12_381(partials, count, result, coord, stream);
     return msm_combine_bn254(partials, count, result, coord, stream);
 }
 

@@ -11,7 +11,10 @@
 
 namespace pb {
 
-enum CurveId { CURVE_BN254 = 0, CURVE_BLS12_377 = 1 };
+enum CurveId { CURVE_BN254 = 0, CURVE_BLS12_377 = 1, CURVE_BLS12_381 = 2 };
+inline size_t curve_fq_bytes(CurveId c) { return c == CURVE_BN254 ? 32 : 48; }                                  // base-field element (8 or 12 limbs)
+inline uint32_t curve_scalar_bits(CurveId c) { return c == CURVE_BLS12_377 ? 253 : c == CURVE_BLS12_381 ? 255 : 254; }
+inline CurveId curve_from_id(int id) { return id == 1 ? CURVE_BLS12_377 : id == 2 ? CURVE_BLS12_381 : CURVE_BN254; }
 enum CoordType { COORD_JACOBIAN = 0, COORD_PROJECTIVE = 1 };   // curve.cuh:23-27
 
 struct MsmPlan {
@@ -34,15 +37,8 @@ struct MsmPlan {
     uint32_t chunk_first;  // points in chunk 0
     uint32_t chunk_n;      // points in every later chunk (the last one may be shorter)
     uint32_t phases;       // folded scatter: passes over the codes, one bucket range each (L2-resident output slice)
-    uint32_t affine;       // 1: buckets are first reduced by rounds of batched affine additions (msm_affine.cuh); seg_len / segs_ps then describe
-                           //    the XYZZ tail over the point lists the rounds leave
-    uint32_t rounds;       // affine: tree rounds (a bucket of up to 2^rounds entries ends as one point; longer ones go through the XYZZ tail)
-    uint64_t aff_cap_a, aff_cap_b;   // affine: capacity (points per chunk) of the two ping-pong point lists
     // workspace layout (byte offsets into one arena)
     size_t off_counts, off_offsets, off_cursor, off_biglist, off_tiles, off_digits, off_sorted, off_slots, off_chunks, off_gsums, bytes;
-    size_t off_aff_a, off_aff_b, off_aff_pre, off_aff_offs;   // affine: ping-pong point lists, prefix-product scratch ring, per-round offsets [round][chunk][nb + 1]
-    uint32_t aff_ctas;     // persistent CTAs of a round kernel
-    uint32_t aff_stagger_ns;   // start offset between the round kernel's CTAs that share an SM
     size_t table_bytes;    // folded: size of the precomputed table (W * n affine points)
 };
 
@@ -88,11 +84,6 @@ cudaError_t msm_combine(CurveId curve, const void *partials, uint32_t count, voi
 // lets every later MSM on `bases` (or a prefix of it) skip the content fingerprint and its host synchronisation.
 cudaError_t msm_register_bases(CurveId curve, const void *bases, uint32_t n, cudaStream_t stream);
 cudaError_t msm_unregister_bases(const void *bases);
-
-// Tunables of the batched-affine accumulation (diagnostics / tests; the defaults come from PANDA_MSM_AFFINE_MIN_LOG and PANDA_MSM_AFFINE):
-// affine_min_log >= 0: smallest log2(n * windows) that uses the plan; affine_rounds: -1 automatic, 0 plan off, r > 0 forces r tree rounds.
-// Values below the stated ranges leave the setting alone.
-void msm_set_tuning(int affine_min_log, int affine_rounds);
 
 // drops every table of the current device (registered or not); synchronises
 cudaError_t msm_release_tables();

@@ -3,7 +3,6 @@
 #pragma once
 #include "msm.cuh"
 #include "ec.cuh"
-#include "msm_affine.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -20,6 +19,12 @@ struct Bls377 {
     using Fq = Fe<Bls377Fq>;
     using Fr = Fe<Bls377Fr>;
     static constexpr int SCALAR_BITS = 253;
+};
+
+struct Bls381 {
+    using Fq = Fe<Bls381Fq>;
+    using Fr = Fe<Bls381Fr>;
+    static constexpr int SCALAR_BITS = 255;
 };
 
 static constexpr uint32_t DIGIT_SKIP = 0xFFFFu;     // digit 0: contributes nothing
@@ -252,15 +257,14 @@ PB_DEV void accumulate_body(const uint8_t *__restrict__ bases, const uint32_t *_
     uint32_t next_bd = __ldg(ow + b + 1);
 
     Pt acc = Pt::identity();
-    // sorted == nullptr: the points ARE the bucket-sorted list (tail of the batched-affine plan): entry = position, no sign
-    uint32_t e_next = sorted ? __ldg(sw + start) : start;
+    uint32_t e_next = __ldg(sw + start);
     Af p_next = Af::load_gather(bases + (size_t)(e_next & 0x7FFFFFFFu) * Af::BYTES);
 #pragma unroll 1
     for (uint32_t pos = start; pos < end; pos++) {
         const uint32_t e = e_next;
         Af p = p_next;
         if (pos + 1 < end) {           // prefetch the next point while this one is being added
-            e_next = sorted ? __ldg(sw + pos + 1) : pos + 1;
+            e_next = __ldg(sw + pos + 1);
             p_next = Af::load_gather(bases + (size_t)(e_next & 0x7FFFFFFFu) * Af::BYTES);
         }
         if (pos >= next_bd) {          // bucket boundary: emit the finished partial, skip empty buckets
@@ -730,8 +734,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             tm.mark();
             k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, p.nb, tiles_ps, tiles_q);
             k_scan_tops<<<p.sets, 1024, 0, sq>>>(tiles_q, tiles_ps, p.nb, offsets_q);
-            k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q,
-                                                                   p.affine ? nullptr : big_count_q, p.affine ? nullptr : big_list_q);
+            k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q, big_count_q, big_list_q);
             tm.mark();
             if (p.folded) {
                 uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
@@ -739,56 +742,14 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, sq>>>((const uint16_t *)codes_q, nq, p.nb, cursor_q, sorted_q);
             if (aux && (err = cudaEventRecord(sorted_ev, sq)) != cudaSuccess) break;
             tm.mark();
-            const uint32_t *acc_offsets = offsets_q;
-            const uint8_t *acc_points = (const uint8_t *)points;
-            const uint32_t *acc_sorted = sorted_q;
-            if (p.affine) {
-                // tree rounds: every round halves the buckets with batched affine additions (one field inversion per 4096 of them)
-                const size_t pt = 2 * sizeof(typename C::Fq);
-                uint8_t *buf_a = ws + p.off_aff_a + (size_t)q * p.aff_cap_a * pt, *buf_b = ws + p.off_aff_b + (size_t)q * p.aff_cap_b * pt;
-                const uint32_t *off_in = offsets_q;
-                uint64_t in_max = (uint64_t)nq * p.windows;
-                for (uint32_t r = 0; r < p.rounds; r++) {
-                    const bool last_round = r + 1 == p.rounds;
-                    uint32_t *off_out = (uint32_t *)(ws + p.off_aff_offs) + ((size_t)r * p.chunks + q) * (p.nb + 1);
-                    const uint64_t out_max = std::min<uint64_t>(in_max, in_max / 2 + p.nb);
-                    // batch length: AFF_K outputs per thread while that leaves every persistent CTA a few batches, shorter in the small rounds
-                    uint32_t kk = AFF_K;
-                    while (kk > 8 && out_max / ((uint64_t)AFF_THREADS * kk) < 4ull * p.aff_ctas) kk >>= 1;
-                    const uint32_t ctas = (uint32_t)std::min<uint64_t>((out_max + (uint64_t)AFF_THREADS * kk - 1) / ((uint64_t)AFF_THREADS * kk), p.aff_ctas);
-                    aff_next_counts<<<std::min<uint32_t>((p.nb + 255) / 256, 148 * 8), 256, 0, sq>>>(off_in, p.nb, counts_q);
-                    k_scan_tiles<<<dim3(tiles_ps, 1), 1024, 0, sq>>>(counts_q, p.nb, tiles_ps, tiles_q);
-                    k_scan_tops<<<1, 1024, 0, sq>>>(tiles_q, tiles_ps, p.nb, off_out);
-                    // the last round's offsets describe the lists the XYZZ tail works on: buckets still spanning many of its segments are listed
-                    k_scan_apply<<<dim3(tiles_ps, 1), 1024, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, off_out, nullptr,
-                                                                     last_round ? big_count_q : nullptr, last_round ? big_list_q : nullptr);
-                    AffRound ar{};
-                    ar.table = r == 0 ? (const uint8_t *)points : nullptr;
-                    ar.entries = r == 0 ? sorted_q : nullptr;
-                    ar.in = r == 0 ? nullptr : ((r & 1) ? buf_a : buf_b);
-                    ar.off_in = off_in; ar.off_out = off_out;
-                    ar.out = (r & 1) ? buf_b : buf_a;
-                    ar.pre = ws + p.off_aff_pre + (size_t)q * p.aff_ctas * AFF_PER_CTA * sizeof(typename C::Fq);
-                    ar.nb = p.nb;
-                    ar.sms = 148;
-                    ar.stagger_ns = p.aff_stagger_ns;
-                    ar.k = kk;
-                    aff_round_fused<C><<<std::max<uint32_t>(ctas, 1), AFF_THREADS, 0, sq>>>(ar);
-                    off_in = off_out;
-                    in_max = out_max;
-                    acc_points = ar.out;
-                }
-                acc_offsets = off_in;
-                acc_sorted = nullptr;
-            }
             {
                 // 12-limb fields (186 registers per thread): 64-thread CTAs fit 5 per SM (10 warps) where 128-thread ones fit 2 (8 warps)
                 const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
                 const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
                 const uint32_t blocks = (uint32_t)((threads + acc_threads - 1) / acc_threads);
-                if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sq>>>(acc_points, acc_sorted, acc_offsets, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
-                else k_accumulate<C><<<blocks, acc_threads, 0, sq>>>(acc_points, acc_sorted, acc_offsets, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
-                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, acc_offsets, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
+                if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                else k_accumulate<C><<<blocks, acc_threads, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
             }
             tm.mark();
             err = cudaGetLastError();
@@ -800,10 +761,8 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         }
         uint32_t log2m = 0; while ((1u << log2m) < p.chunk) log2m++;
         {
-            // affine plan: the offsets the partial slots were written against are the last round's ([round][chunk][nb + 1])
-            const uint32_t *red_offsets = p.affine ? (const uint32_t *)(ws + p.off_aff_offs) + (size_t)(p.rounds - 1) * p.chunks * (p.nb + 1) : offsets;
             const uint32_t threads = p.sets * p.chunks_ps;
-            k_bucket_reduce<C><<<(threads + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, stream>>>(slots, red_offsets, p.nb, p.seg_len, p.segs_ps,
+            k_bucket_reduce<C><<<(threads + RED_THREADS - 1) / RED_THREADS, RED_THREADS, 0, stream>>>(slots, offsets, p.nb, p.seg_len, p.segs_ps,
                                                                                                    p.sets, p.chunks, p.chunk, p.chunks_ps, chunks);
         }
         tm.mark();

@@ -62,7 +62,7 @@ cudaError_t enable_peer_access(const std::vector<int> &devs) {
 
 panda_error msm_multi(pb::CurveId curve, const panda_msm_configuration *cfgs, const size_t *counts, int n_dev) {
     if (!cfgs || n_dev <= 0 || n_dev > 64) return perr(cudaErrorInvalidValue);
-    const size_t fq = curve == pb::CURVE_BLS12_377 ? 48 : 32, rbytes = 3 * fq;
+    const size_t rbytes = 3 * pb::curve_fq_bytes(curve);
     DeviceGuard guard;
     std::vector<int> dev(n_dev);
     std::vector<size_t> n(n_dev);
@@ -137,6 +137,13 @@ panda_error panda_msm_execute_bls12_377_multi(const panda_msm_configuration *per
 }
 panda_error panda_msm_execute_bls12_377_multi_n(const panda_msm_configuration *per_device, const size_t *counts, int n_dev) {
     return counts ? msm_multi(pb::CURVE_BLS12_377, per_device, counts, n_dev) : perr(cudaErrorInvalidValue);
+}
+
+panda_error panda_msm_execute_bls12_381_multi(const panda_msm_configuration *per_device, int n_dev) {
+    return msm_multi(pb::CURVE_BLS12_381, per_device, nullptr, n_dev);
+}
+panda_error panda_msm_execute_bls12_381_multi_n(const panda_msm_configuration *per_device, const size_t *counts, int n_dev) {
+    return counts ? msm_multi(pb::CURVE_BLS12_381, per_device, counts, n_dev) : perr(cudaErrorInvalidValue);
 }
 
 panda_error panda_ntt_execute_bn254_multi(const panda_ntt_multi_configuration *cfg) {

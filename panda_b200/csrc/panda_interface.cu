@@ -104,7 +104,7 @@ static panda_error msm_execute(pb::CurveId curve, const panda_msm_configuration 
 static panda_error msm_execute_host(pb::CurveId curve, const panda_msm_configuration &cfg) {
     if (!cfg.results || !cfg.bases || !cfg.scalars || cfg.log_scalars_count > 30) return perr(cudaErrorInvalidValue);   // before anything is queued
     const size_t n = (size_t)1 << cfg.log_scalars_count;
-    const size_t fq = curve == pb::CURVE_BLS12_377 ? 48 : 32;
+    const size_t fq = pb::curve_fq_bytes(curve);
     cudaStream_t s = cu(cfg.stream);
     uint8_t *d = nullptr;
     const size_t bases_bytes = n * 2 * fq, scalars_bytes = n * 32, off_s = (bases_bytes + 255) & ~(size_t)255,
@@ -143,6 +143,23 @@ panda_error panda_msm_register_bases_bls12_377(const void *d_bases, size_t n, pa
     return perr(pb::msm_register_bases(pb::CURVE_BLS12_377, d_bases, (uint32_t)n, cu(stream)));
 }
 panda_error panda_msm_unregister_bases(const void *d_bases) { return perr(pb::msm_unregister_bases(d_bases)); }
+
+// BLS12-381 G1 (third curve; same shapes as BLS12-377: 96-byte points, 144-byte results, 32-byte scalars of 255 bits)
+panda_error panda_msm_setup_bls12_381(void) { return panda_success; }
+panda_error panda_msm_execute_bls12_381(const panda_msm_configuration cfg) {
+    if (cfg.log_scalars_count > 30) return perr(cudaErrorInvalidValue);
+    return msm_execute(pb::CURVE_BLS12_381, cfg, (size_t)1 << cfg.log_scalars_count);
+}
+panda_error panda_msm_execute_bls12_381_n(const panda_msm_configuration cfg, size_t n) { return msm_execute(pb::CURVE_BLS12_381, cfg, n); }
+panda_error panda_msm_execute_bls12_381_host(const panda_msm_configuration cfg) { return msm_execute_host(pb::CURVE_BLS12_381, cfg); }
+panda_error panda_msm_execute_bls12_381_host_scalars(const panda_msm_configuration cfg, size_t n) { return msm_execute_host_scalars(pb::CURVE_BLS12_381, cfg, n); }
+panda_error panda_msm_register_bases_bls12_381(const void *d_bases, size_t n, panda_stream stream) {
+    if (n > (size_t)1 << 30) return perr(cudaErrorInvalidValue);
+    return perr(pb::msm_register_bases(pb::CURVE_BLS12_381, d_bases, (uint32_t)n, cu(stream)));
+}
+panda_error panda_msm_combine_bls12_381(const void *partials, unsigned count, void *result, panda_msm_result_coordinate_type coord, panda_stream stream) {
+    return perr(pb::msm_combine(pb::CURVE_BLS12_381, partials, count, result, coord == PROJECTIVE ? pb::COORD_PROJECTIVE : pb::COORD_JACOBIAN, cu(stream)));
+}
 
 panda_error panda_msm_setup_bn254(void) { return panda_success; }          // nothing to prepare: msm_cuda.cuh:786-795 is empty too
 panda_error panda_msm_setup_bls12_377(void) { return panda_success; }
@@ -252,11 +269,6 @@ panda_error panda_ntt_tear_down(void) {       // the current device's NTT unit: 
 
 // ---- diagnostics (include/panda_debug.h) --------------------------------------------------------------------------
 
-panda_error panda_debug_msm_tuning(int affine_min_log, int affine_rounds) {
-    pb::msm_set_tuning(affine_min_log, affine_rounds);
-    return panda_success;
-}
-
 panda_error panda_debug_ntt_timed(const panda_ntt_configuration_v1 cfg, int inverse, float *pass_ms) {
     if (!cfg.d_omega || !cfg.flag || !cfg.d_src || !cfg.d_dst || !pass_ms) return perr(cudaErrorInvalidValue);
     unsigned in_dst = 0;
@@ -273,7 +285,7 @@ panda_error panda_debug_fr_pow2k_host(const void *omega, unsigned k, void *out) 
 
 panda_error panda_debug_msm_plan(int curve, size_t n, int folded, unsigned c_override, unsigned seg_override, panda_debug_msm_plan_info *out) {
     if (!out) return perr(cudaErrorInvalidValue);
-    pb::MsmPlan p = pb::msm_make_plan(curve == 1 ? pb::CURVE_BLS12_377 : pb::CURVE_BN254, (uint32_t)n, folded != 0, c_override, seg_override);
+    pb::MsmPlan p = pb::msm_make_plan(pb::curve_from_id(curve), (uint32_t)n, folded != 0, c_override, seg_override);
     out->window_bits = p.c; out->windows = p.windows; out->buckets_per_window = p.nb; out->segment_len = p.seg_len;
     out->segments_per_window = p.segs_ps; out->reduce_chunk = p.chunk; out->workspace_bytes = p.bytes;
     out->folded = p.folded; out->bucket_sets = p.sets; out->groups = p.groups; out->phases = p.phases; out->table_bytes = p.table_bytes;
@@ -284,7 +296,7 @@ panda_error panda_debug_msm_timed(int curve, const panda_msm_configuration cfg, 
                                   float *stage_ms, unsigned *info) {
     pb::MsmStageTimes t{};
     pb::CoordType coord = cfg.msm_result_coordinate_type == PROJECTIVE ? pb::COORD_PROJECTIVE : pb::COORD_JACOBIAN;
-    cudaError_t e = pb::msm_run(curve == 1 ? pb::CURVE_BLS12_377 : pb::CURVE_BN254, cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, coord,
+    cudaError_t e = pb::msm_run(pb::curve_from_id(curve), cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, coord,
                                 cu(cfg.mem_pool), cu(cfg.stream), c_override, seg_override, (stage_ms || info) ? &t : nullptr, table_mode);
     if (stage_ms) {
         stage_ms[0] = t.digits; stage_ms[1] = t.scan; stage_ms[2] = t.scatter; stage_ms[3] = t.accumulate;
@@ -296,7 +308,7 @@ panda_error panda_debug_msm_timed(int curve, const panda_msm_configuration cfg, 
 
 panda_error panda_debug_msm_streamed(int curve, const panda_msm_configuration cfg, size_t n, int table_mode, unsigned chunks) {
     pb::CoordType coord = cfg.msm_result_coordinate_type == PROJECTIVE ? pb::COORD_PROJECTIVE : pb::COORD_JACOBIAN;
-    return perr(pb::msm_run_streamed(curve == 1 ? pb::CURVE_BLS12_377 : pb::CURVE_BN254, cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, coord,
+    return perr(pb::msm_run_streamed(pb::curve_from_id(curve), cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, coord,
                                      cu(cfg.mem_pool), cu(cfg.stream), table_mode, chunks));
 }
 

@@ -269,6 +269,15 @@ SIGNATURES: dict[str, list] = {
     "panda_ntt_batch_execute_bn254_v1": [NttconfigurationV1, _uint, _int],
     "panda_ntt_exchange_bn254": [C.POINTER(NttExchangeConfiguration)],
     "panda_msm_execute_bls12_377_host": [MSMConfiguration],
+    "panda_msm_setup_bls12_381": [],
+    "panda_msm_execute_bls12_381": [MSMConfiguration],
+    "panda_msm_execute_bls12_381_n": [MSMConfiguration, SizeT],
+    "panda_msm_execute_bls12_381_host": [MSMConfiguration],
+    "panda_msm_execute_bls12_381_host_scalars": [MSMConfiguration, SizeT],
+    "panda_msm_register_bases_bls12_381": [_vp, SizeT, PandaStream],
+    "panda_msm_combine_bls12_381": [_vp, _uint, _vp, _int, PandaStream],
+    "panda_msm_execute_bls12_381_multi": [C.POINTER(MSMConfiguration), _int],
+    "panda_msm_execute_bls12_381_multi_n": [C.POINTER(MSMConfiguration), C.POINTER(SizeT), _int],
     "panda_msm_execute_bn254_multi": [C.POINTER(MSMConfiguration), _int],
     "panda_msm_execute_bn254_multi_n": [C.POINTER(MSMConfiguration), C.POINTER(SizeT), _int],
     "panda_msm_execute_bls12_377_multi": [C.POINTER(MSMConfiguration), _int],
@@ -282,7 +291,6 @@ SIGNATURES: dict[str, list] = {
     "panda_debug_msm_streamed": [_int, MSMConfiguration, SizeT, _int, _uint],
     "panda_debug_int_peak": [_int, _uint, C.POINTER(C.c_float), C.POINTER(C.c_ulonglong)],
     "panda_debug_fr_pow2k_host": [_vp, _uint, _vp],
-    "panda_debug_msm_tuning": [_int, _int],
     "panda_debug_ntt_timed": [NttconfigurationV1, _int, C.POINTER(C.c_float)],
 }
 

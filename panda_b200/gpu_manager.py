@@ -45,6 +45,12 @@ def _load() -> C.CDLL:
         "panda_host_ntt_bn254_gpu_v1": [vp, vp, sz, vp, u32],
         "panda_host_intt_bn254_gpu_v1": [vp, vp, sz, vp, u32],
         "panda_host_msm_bls12_377_gpu": [vp, vp, sz, vp, sz, vp],
+        "panda_host_manager_cache_bases_curve": [vp, i32, vp, sz, C.POINTER(sz)],
+        "panda_host_msm_gpu": [vp, i32, vp, sz, vp, sz, vp],
+        "panda_host_msm_gpu_with_cached_bases": [vp, i32, vp, sz, sz, vp],
+        "panda_host_msm_gpu_with_cached_scalars": [vp, i32, sz, vp, sz, vp],
+        "panda_host_msm_gpu_with_cached_input": [vp, i32, sz, sz, vp],
+        "panda_host_msm_gpu_host": [vp, i32, vp, sz, vp, sz, vp],
     }
     for name, args in sigs.items():
         fn = getattr(h, name)
@@ -137,10 +143,11 @@ class PandaGpuManager:
         _ok(host.panda_host_init_ntt(_bytes(omega).ctypes.data))
 
     # init_msm_cached_bases / init_msm_cached_scalars + push into d_bases / d_scalars / scalars_len (wrapper.rs:15-17,154-197)
-    def cache_bases(self, bases) -> int:
+    def cache_bases(self, bases, curve: int = 0) -> int:
+        """curve: 0 BN254 (64-byte points), 1 BLS12-377 (96-byte points)"""
         b = _bytes(bases)
         idx = C.c_size_t()
-        _ok(host.panda_host_manager_cache_bases(self._h, b.ctypes.data, b.size, C.byref(idx)))
+        _ok(host.panda_host_manager_cache_bases_curve(self._h, curve, b.ctypes.data, b.size, C.byref(idx)))
         return idx.value
 
     def cache_scalars(self, scalars) -> int:
@@ -229,9 +236,38 @@ def panda_intt_bn254_gpu_v1(gm: PandaGpuManager, scalars: np.ndarray, omega, log
     _ok(host.panda_host_intt_bn254_gpu_v1(gm._h, s.ctypes.data, s.size, om.ctypes.data, log_n))
 
 
+BLS12_377 = 1
+
+
 def panda_msm_bls12_377_gpu(gm: PandaGpuManager, scalars, bases) -> np.ndarray:
     """BLS12-377 G1 MSM: bases 96 B per point, scalars 32 B, 144-byte result in the manager's coordinate type"""
     s, b = _bytes(scalars), _bytes(bases)
     r = np.zeros(144, np.uint8)
-    _ok(host.panda_host_msm_bls12_377_gpu(gm._h, s.ctypes.data, s.size, b.ctypes.data, b.size, r.ctypes.data))
+    _ok(host.panda_host_msm_gpu(gm._h, BLS12_377, s.ctypes.data, s.size, b.ctypes.data, b.size, r.ctypes.data))
+    return r
+
+
+def panda_msm_bls12_377_gpu_with_cached_bases(gm: PandaGpuManager, scalars, bases_index: int) -> np.ndarray:
+    """bases cached with gm.cache_bases(bases, curve=1); the host scalars are streamed in chunks like the BN254 call"""
+    s, r = _bytes(scalars), np.zeros(144, np.uint8)
+    _ok(host.panda_host_msm_gpu_with_cached_bases(gm._h, BLS12_377, s.ctypes.data, s.size, bases_index, r.ctypes.data))
+    return r
+
+
+def panda_msm_bls12_377_gpu_with_cached_scalars(gm: PandaGpuManager, scalars_index: int, bases) -> np.ndarray:
+    b, r = _bytes(bases), np.zeros(144, np.uint8)
+    _ok(host.panda_host_msm_gpu_with_cached_scalars(gm._h, BLS12_377, scalars_index, b.ctypes.data, b.size, r.ctypes.data))
+    return r
+
+
+def panda_msm_bls12_377_gpu_with_cached_input(gm: PandaGpuManager, scalars_index: int, bases_index: int) -> np.ndarray:
+    r = np.zeros(144, np.uint8)
+    _ok(host.panda_host_msm_gpu_with_cached_input(gm._h, BLS12_377, scalars_index, bases_index, r.ctypes.data))
+    return r
+
+
+def panda_msm_bls12_377_gpu_host(gm: PandaGpuManager, scalars, bases) -> np.ndarray:
+    """host pointers straight into panda_msm_execute_bls12_377_host (always Jacobian, like the BN254 host entry)"""
+    s, b, r = _bytes(scalars), _bytes(bases), np.zeros(144, np.uint8)
+    _ok(host.panda_host_msm_gpu_host(gm._h, BLS12_377, s.ctypes.data, s.size, b.ctypes.data, b.size, r.ctypes.data))
     return r

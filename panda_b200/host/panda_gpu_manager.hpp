@@ -79,6 +79,9 @@ struct PandaMemPool {
 
 struct PandaDeviceInfo { uint64_t free = 0, total = 0; };
 enum class PandaMSMResultCoordinateType { Jacobian = 0, Projective = 1 };
+// curves of the MSM entry points (no counterpart in the reference's Rust API, which is BN254 only; README.md:36 announces the others)
+enum class PandaCurve { Bn254 = 0, Bls12_377 = 1 };
+inline size_t fq_len(PandaCurve c) { return c == PandaCurve::Bls12_377 ? 48 : 32; }   // bytes of a base-field element; scalars are 32 bytes on both
 
 // ---- gpu_manager/common.rs ---------------------------------------------------------------------------------------------------
 inline uint32_t log_2(size_t num) {
@@ -171,11 +174,12 @@ class PandaGpuManager {
     // cached bases are announced to the library (panda_msm_register_bases_bn254): it builds its table of precomputed multiples
     // once, here, and every MSM on the cached pointer runs without a content check.  No counterpart in wrapper.rs: the
     // reference's panda_msm_setup_bn254 is an empty hook (msm_cuda.cuh:786-795).
-    static void *upload_bases(const ByteSlice &b) {
+    static void *upload_bases(const ByteSlice &b, PandaCurve curve = PandaCurve::Bn254) {
         void *d = upload(b);
         panda_stream null_stream{nullptr};
-        const size_t points = b.len / (2 * FIELD_ELEMENT_LEN);
-        if (points) check(panda_msm_register_bases_bn254(d, points, null_stream), PandaGpuError::SetBasesErr);
+        const size_t points = b.len / (2 * fq_len(curve));
+        if (points) check(curve == PandaCurve::Bls12_377 ? panda_msm_register_bases_bls12_377(d, points, null_stream)
+                                                         : panda_msm_register_bases_bn254(d, points, null_stream), PandaGpuError::SetBasesErr);
         return d;
     }
     static std::vector<void *> init_msm(const std::vector<ByteSlice> &bases) {   // wrapper.rs:122-152
@@ -184,7 +188,7 @@ class PandaGpuManager {
         check(panda_msm_setup_bn254(), PandaGpuError::CreateContextError);
         return out;
     }
-    static void *init_msm_cached_bases(const ByteSlice &bases) { return upload_bases(bases); } // wrapper.rs:154-170
+    static void *init_msm_cached_bases(const ByteSlice &bases, PandaCurve curve = PandaCurve::Bn254) { return upload_bases(bases, curve); } // wrapper.rs:154-170
     static void *init_msm_cached_scalars(const ByteSlice &scalars) { return upload(scalars); }   // wrapper.rs:172-188
     static std::pair<void *, void *> init_msm_cached(const ByteSlice &scalars, const ByteSlice &bases) {   // wrapper.rs:190-197
         void *s = init_msm_cached_scalars(scalars);
@@ -256,11 +260,12 @@ inline void memory_copy_and_free(uint8_t *h, size_t len, void *d, const PandaStr
 // ---- gpu_manager/unit.rs -----------------------------------------------------------------------------------------------------
 namespace detail {
 
-// steps 3-7 of unit.rs:31-100, shared by the four device MSM variants
+// steps 3-7 of unit.rs:31-100, shared by the four device MSM variants (of either curve)
 inline std::vector<uint8_t> msm_execute_and_fetch(const PandaGpuManager &gm, void *d_scalars, void *d_bases, size_t scalars_len,
-                                                  bool free_scalars, bool free_bases, bool scalars_on_host = false) {
+                                                  bool free_scalars, bool free_bases, bool scalars_on_host = false, PandaCurve curve = PandaCurve::Bn254) {
     const uint32_t log_scalars_count = log_2(scalars_len / FIELD_ELEMENT_LEN);
-    const size_t result_buf_len = FIELD_ELEMENT_LEN * 3;
+    const size_t result_buf_len = fq_len(curve) * 3;
+    const bool bls = curve == PandaCurve::Bls12_377;
     void *d_result = nullptr;
     malloc_from_pool_async(&d_result, result_buf_len, gm.get_mem_pool(), gm.get_exec_stream());   // fix: exec stream (A12)
     panda_msm_configuration cfg{};
@@ -271,10 +276,11 @@ inline std::vector<uint8_t> msm_execute_and_fetch(const PandaGpuManager &gm, voi
     cfg.results = d_result;
     cfg.log_scalars_count = log_scalars_count;
     cfg.msm_result_coordinate_type = static_cast<panda_msm_result_coordinate_type>(gm.get_msm_result_coordinate_type());
-    if (scalars_on_host) check(panda_msm_execute_bn254_host_scalars(cfg, (size_t)1 << log_scalars_count), PandaGpuError::SchedulingErr);
-    else check(panda_msm_execute_bn254(cfg), PandaGpuError::SchedulingErr);
+    const size_t n = (size_t)1 << log_scalars_count;
+    if (scalars_on_host) check(bls ? panda_msm_execute_bls12_377_host_scalars(cfg, n) : panda_msm_execute_bn254_host_scalars(cfg, n), PandaGpuError::SchedulingErr);
+    else check(bls ? panda_msm_execute_bls12_377(cfg) : panda_msm_execute_bn254(cfg), PandaGpuError::SchedulingErr);
     std::vector<uint8_t> out(result_buf_len);
-    // fix: unit.rs:67-74 allocates (and leaks) a pinned staging buffer per call; 96 bytes go straight into the result vector
+    // fix: unit.rs:67-74 allocates (and leaks) a pinned staging buffer per call; the result bytes go straight into the result vector
     panda_error rc = panda_memcpy_async(out.data(), d_result, result_buf_len, gm.get_exec_stream().raw);
     if (rc == panda_success) rc = panda_stream_synchronize(gm.get_exec_stream().raw);               // unit.rs:60-62 + :76
     if (rc != panda_success) throw PandaGpuException(PandaGpuError::CreateContextError);
@@ -286,43 +292,44 @@ inline std::vector<uint8_t> msm_execute_and_fetch(const PandaGpuManager &gm, voi
 
 }  // namespace detail
 
+// The five MSM shapes of unit.rs, with the curve as a parameter; the reference's names (BN254) and the BLS12-377 names follow.
 // unit.rs:10-101
-inline std::vector<uint8_t> panda_msm_bn254_gpu(const PandaGpuManager &gm, const ByteSlice &scalars, const ByteSlice &bases) {
+inline std::vector<uint8_t> panda_msm_gpu(const PandaGpuManager &gm, PandaCurve curve, const ByteSlice &scalars, const ByteSlice &bases) {
+    if (bases.len / (2 * fq_len(curve)) < ((size_t)1 << log_2(scalars.len / FIELD_ELEMENT_LEN))) throw PandaGpuException(PandaGpuError::MSMBasesAddrError);
     void *d_scalars = memory_alloc_and_copy(gm, scalars, gm.get_h2d_stream());
     void *d_bases = memory_alloc_and_copy(gm, bases, gm.get_h2d_stream());
     gm.wait_h2d();
-    return detail::msm_execute_and_fetch(gm, d_scalars, d_bases, scalars.len, true, true);
+    return detail::msm_execute_and_fetch(gm, d_scalars, d_bases, scalars.len, true, true, false, curve);
 }
 // unit.rs:103-188
-inline std::vector<uint8_t> panda_msm_bn254_gpu_with_cached_bases(const PandaGpuManager &gm, const ByteSlice &scalars, size_t bases_index) {
+inline std::vector<uint8_t> panda_msm_gpu_with_cached_bases(const PandaGpuManager &gm, PandaCurve curve, const ByteSlice &scalars, size_t bases_index) {
     void *d_bases = gm.get_params_bases_ptr_mut(bases_index);
     if (!d_bases) throw PandaGpuException(PandaGpuError::BasesIndexErr);
-    // fix: unit.rs:113-131 uploads every scalar before the MSM starts; panda_msm_execute_bn254_host_scalars streams them in chunks
+    // fix: unit.rs:113-131 uploads every scalar before the MSM starts; panda_msm_execute_*_host_scalars streams them in chunks
     // on the library's copy stream and overlaps the upload with the sort / accumulation of the chunks already on the device
-    return detail::msm_execute_and_fetch(gm, const_cast<uint8_t *>(scalars.data), d_bases, scalars.len, false, false, true);
+    return detail::msm_execute_and_fetch(gm, const_cast<uint8_t *>(scalars.data), d_bases, scalars.len, false, false, true, curve);
 }
 // unit.rs:190-275
-inline std::vector<uint8_t> panda_msm_bn254_gpu_with_cached_scalars(const PandaGpuManager &gm, size_t scalars_index, const ByteSlice &bases) {
+inline std::vector<uint8_t> panda_msm_gpu_with_cached_scalars(const PandaGpuManager &gm, PandaCurve curve, size_t scalars_index, const ByteSlice &bases) {
     const size_t len = gm.get_params_scalars_len(scalars_index);
     void *d_scalars = gm.get_params_scalars_ptr_mut(scalars_index);
     if (len == 0 || !d_scalars) throw PandaGpuException(PandaGpuError::BasesIndexErr);
     void *d_bases = memory_alloc_and_copy(gm, bases, gm.get_h2d_stream());
     gm.wait_h2d();
-    return detail::msm_execute_and_fetch(gm, d_scalars, d_bases, len, false, true);
+    return detail::msm_execute_and_fetch(gm, d_scalars, d_bases, len, false, true, false, curve);
 }
 // unit.rs:277-361
-inline std::vector<uint8_t> panda_msm_bn254_gpu_with_cached_input(const PandaGpuManager &gm, size_t scalars_index, size_t bases_index) {
+inline std::vector<uint8_t> panda_msm_gpu_with_cached_input(const PandaGpuManager &gm, PandaCurve curve, size_t scalars_index, size_t bases_index) {
     const size_t len = gm.get_params_scalars_len(scalars_index);
     if (len == 0) throw PandaGpuException(PandaGpuError::BasesIndexErr);
     void *d_scalars = gm.get_params_scalars_ptr_mut(scalars_index);
     void *d_bases = gm.get_params_bases_ptr_mut(bases_index);
     if (!d_scalars || !d_bases) throw PandaGpuException(PandaGpuError::BasesIndexErr);
-    return detail::msm_execute_and_fetch(gm, d_scalars, d_bases, len, false, false);
+    return detail::msm_execute_and_fetch(gm, d_scalars, d_bases, len, false, false, false, curve);
 }
-// unit.rs:363-416: host pointers straight into panda_msm_execute_bn254_host
-inline std::vector<uint8_t> panda_msm_bn254_gpu_host(const PandaGpuManager &gm, const ByteSlice &scalars, const ByteSlice &bases) {
-    const size_t result_buf_len = FIELD_ELEMENT_LEN * 3;
-    std::vector<uint8_t> out(result_buf_len);
+// unit.rs:363-416: host pointers straight into panda_msm_execute_*_host
+inline std::vector<uint8_t> panda_msm_gpu_host(const PandaGpuManager &gm, PandaCurve curve, const ByteSlice &scalars, const ByteSlice &bases) {
+    std::vector<uint8_t> out(fq_len(curve) * 3);
     panda_msm_configuration cfg{};
     cfg.mem_pool = gm.get_mem_pool().raw;
     cfg.stream = gm.get_exec_stream().raw;
@@ -331,8 +338,25 @@ inline std::vector<uint8_t> panda_msm_bn254_gpu_host(const PandaGpuManager &gm, 
     cfg.results = out.data();
     cfg.log_scalars_count = log_2(scalars.len / FIELD_ELEMENT_LEN);
     cfg.msm_result_coordinate_type = static_cast<panda_msm_result_coordinate_type>(gm.get_msm_result_coordinate_type());
-    check(panda_msm_execute_bn254_host(cfg), PandaGpuError::SchedulingErr);
+    check(curve == PandaCurve::Bls12_377 ? panda_msm_execute_bls12_377_host(cfg) : panda_msm_execute_bn254_host(cfg), PandaGpuError::SchedulingErr);
     return out;
+}
+
+// the reference's API (BN254)
+inline std::vector<uint8_t> panda_msm_bn254_gpu(const PandaGpuManager &gm, const ByteSlice &scalars, const ByteSlice &bases) {
+    return panda_msm_gpu(gm, PandaCurve::Bn254, scalars, bases);
+}
+inline std::vector<uint8_t> panda_msm_bn254_gpu_with_cached_bases(const PandaGpuManager &gm, const ByteSlice &scalars, size_t bases_index) {
+    return panda_msm_gpu_with_cached_bases(gm, PandaCurve::Bn254, scalars, bases_index);
+}
+inline std::vector<uint8_t> panda_msm_bn254_gpu_with_cached_scalars(const PandaGpuManager &gm, size_t scalars_index, const ByteSlice &bases) {
+    return panda_msm_gpu_with_cached_scalars(gm, PandaCurve::Bn254, scalars_index, bases);
+}
+inline std::vector<uint8_t> panda_msm_bn254_gpu_with_cached_input(const PandaGpuManager &gm, size_t scalars_index, size_t bases_index) {
+    return panda_msm_gpu_with_cached_input(gm, PandaCurve::Bn254, scalars_index, bases_index);
+}
+inline std::vector<uint8_t> panda_msm_bn254_gpu_host(const PandaGpuManager &gm, const ByteSlice &scalars, const ByteSlice &bases) {
+    return panda_msm_gpu_host(gm, PandaCurve::Bn254, scalars, bases);
 }
 
 namespace detail {
@@ -388,33 +412,22 @@ inline void panda_intt_bn254_gpu_v1(const PandaGpuManager &gm, uint8_t *scalars,
     detail::ntt_fetch(gm, scalars, len, d_src, d_dst, flag);
 }
 
-constexpr size_t BLS12_377_FQ_LEN = 48;
-
-// BLS12-377 G1 MSM: bases 96 B per point (x || y, 12 x u32 Montgomery), scalars 32 B, result 144 B (Jacobian or Projective per set_config)
+// BLS12-377 G1 (bases 96 B per point: x || y, 12 x u32 Montgomery; scalars 32 B; result 144 B, Jacobian or Projective per set_config):
+// the same five shapes.  Cached bases of this curve are uploaded with init_msm_cached_bases(bases, PandaCurve::Bls12_377).
 inline std::vector<uint8_t> panda_msm_bls12_377_gpu(const PandaGpuManager &gm, const ByteSlice &scalars, const ByteSlice &bases) {
-    const uint32_t log_scalars_count = log_2(scalars.len / FIELD_ELEMENT_LEN);
-    if (bases.len / (2 * BLS12_377_FQ_LEN) < (size_t(1) << log_scalars_count)) throw PandaGpuException(PandaGpuError::MSMBasesAddrError);
-    void *d_scalars = memory_alloc_and_copy(gm, scalars, gm.get_h2d_stream());
-    void *d_bases = memory_alloc_and_copy(gm, bases, gm.get_h2d_stream());
-    gm.wait_h2d();
-    const size_t result_buf_len = BLS12_377_FQ_LEN * 3;
-    void *d_result = nullptr;
-    malloc_from_pool_async(&d_result, result_buf_len, gm.get_mem_pool(), gm.get_exec_stream());
-    panda_msm_configuration cfg{};
-    cfg.mem_pool = gm.get_mem_pool().raw;
-    cfg.stream = gm.get_exec_stream().raw;
-    cfg.bases = d_bases; cfg.scalars = d_scalars; cfg.results = d_result;
-    cfg.log_scalars_count = log_scalars_count;
-    cfg.msm_result_coordinate_type = static_cast<panda_msm_result_coordinate_type>(gm.get_msm_result_coordinate_type());
-    check(panda_msm_execute_bls12_377(cfg), PandaGpuError::SchedulingErr);
-    std::vector<uint8_t> out(result_buf_len);
-    panda_error rc = panda_memcpy_async(out.data(), d_result, result_buf_len, gm.get_exec_stream().raw);
-    if (rc == panda_success) rc = panda_stream_synchronize(gm.get_exec_stream().raw);
-    free_async(d_scalars, gm.get_exec_stream());
-    free_async(d_bases, gm.get_exec_stream());
-    free_async(d_result, gm.get_exec_stream());
-    if (rc != panda_success) throw PandaGpuException(PandaGpuError::CreateContextError);
-    return out;
+    return panda_msm_gpu(gm, PandaCurve::Bls12_377, scalars, bases);
+}
+inline std::vector<uint8_t> panda_msm_bls12_377_gpu_with_cached_bases(const PandaGpuManager &gm, const ByteSlice &scalars, size_t bases_index) {
+    return panda_msm_gpu_with_cached_bases(gm, PandaCurve::Bls12_377, scalars, bases_index);
+}
+inline std::vector<uint8_t> panda_msm_bls12_377_gpu_with_cached_scalars(const PandaGpuManager &gm, size_t scalars_index, const ByteSlice &bases) {
+    return panda_msm_gpu_with_cached_scalars(gm, PandaCurve::Bls12_377, scalars_index, bases);
+}
+inline std::vector<uint8_t> panda_msm_bls12_377_gpu_with_cached_input(const PandaGpuManager &gm, size_t scalars_index, size_t bases_index) {
+    return panda_msm_gpu_with_cached_input(gm, PandaCurve::Bls12_377, scalars_index, bases_index);
+}
+inline std::vector<uint8_t> panda_msm_bls12_377_gpu_host(const PandaGpuManager &gm, const ByteSlice &scalars, const ByteSlice &bases) {
+    return panda_msm_gpu_host(gm, PandaCurve::Bls12_377, scalars, bases);
 }
 
 }  // namespace panda

@@ -58,6 +58,13 @@ int panda_host_manager_cache_bases(void *gm, const void *bases, size_t len, size
         *index = m->d_bases.size() - 1;
     });
 }
+int panda_host_manager_cache_bases_curve(void *gm, int curve, const void *bases, size_t len, size_t *index) {
+    return guarded([&] {
+        auto *m = static_cast<PandaGpuManager *>(gm);
+        m->d_bases.push_back(PandaGpuManager::init_msm_cached_bases(bs(bases, len), static_cast<PandaCurve>(curve)));
+        *index = m->d_bases.size() - 1;
+    });
+}
 int panda_host_manager_cache_scalars(void *gm, const void *scalars, size_t len, size_t *index) {
     return guarded([&] {
         auto *m = static_cast<PandaGpuManager *>(gm);
@@ -97,8 +104,24 @@ int panda_host_ntt_bn254_gpu_v1(void *gm, void *scalars, size_t len, const void 
 int panda_host_intt_bn254_gpu_v1(void *gm, void *scalars, size_t len, const void *omega, unsigned log_n) {
     return guarded([&] { panda_intt_bn254_gpu_v1(*static_cast<PandaGpuManager *>(gm), static_cast<uint8_t *>(scalars), len, bs(omega, 32), log_n); });
 }
+// the five MSM shapes with the curve as a parameter (0 BN254, 1 BLS12-377); result receives 3 base-field elements (96 / 144 bytes)
+int panda_host_msm_gpu(void *gm, int curve, const void *scalars, size_t scalars_len, const void *bases, size_t bases_len, void *result) {
+    return guarded([&] { auto r = panda_msm_gpu(*static_cast<PandaGpuManager *>(gm), static_cast<PandaCurve>(curve), bs(scalars, scalars_len), bs(bases, bases_len)); memcpy(result, r.data(), r.size()); });
+}
+int panda_host_msm_gpu_with_cached_bases(void *gm, int curve, const void *scalars, size_t scalars_len, size_t bases_index, void *result) {
+    return guarded([&] { auto r = panda_msm_gpu_with_cached_bases(*static_cast<PandaGpuManager *>(gm), static_cast<PandaCurve>(curve), bs(scalars, scalars_len), bases_index); memcpy(result, r.data(), r.size()); });
+}
+int panda_host_msm_gpu_with_cached_scalars(void *gm, int curve, size_t scalars_index, const void *bases, size_t bases_len, void *result) {
+    return guarded([&] { auto r = panda_msm_gpu_with_cached_scalars(*static_cast<PandaGpuManager *>(gm), static_cast<PandaCurve>(curve), scalars_index, bs(bases, bases_len)); memcpy(result, r.data(), r.size()); });
+}
+int panda_host_msm_gpu_with_cached_input(void *gm, int curve, size_t scalars_index, size_t bases_index, void *result) {
+    return guarded([&] { auto r = panda_msm_gpu_with_cached_input(*static_cast<PandaGpuManager *>(gm), static_cast<PandaCurve>(curve), scalars_index, bases_index); memcpy(result, r.data(), r.size()); });
+}
+int panda_host_msm_gpu_host(void *gm, int curve, const void *scalars, size_t scalars_len, const void *bases, size_t bases_len, void *result) {
+    return guarded([&] { auto r = panda_msm_gpu_host(*static_cast<PandaGpuManager *>(gm), static_cast<PandaCurve>(curve), bs(scalars, scalars_len), bs(bases, bases_len)); memcpy(result, r.data(), r.size()); });
+}
 int panda_host_msm_bls12_377_gpu(void *gm, const void *scalars, size_t scalars_len, const void *bases, size_t bases_len, void *result144) {
-    return guarded([&] { auto r = panda_msm_bls12_377_gpu(*static_cast<PandaGpuManager *>(gm), bs(scalars, scalars_len), bs(bases, bases_len)); memcpy(result144, r.data(), r.size()); });
+    return panda_host_msm_gpu(gm, 1, scalars, scalars_len, bases, bases_len, result144);
 }
 
 }  // extern "C"

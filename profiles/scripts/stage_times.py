@@ -1,5 +1,6 @@
-"""Stage times of the table-plan MSM at 2^k with the batched-affine accumulation off / automatic / forced round counts.
-usage: python profiles/scripts/affine_sweep.py K [curve] [rounds ...]   (rounds: 0 = off, -1 = automatic)"""
+"""Stage times of the table-plan (registered bases) MSM at 2^k: per-stage device times from the instrumented entry point, wall time of the
+product entry point, closed-form check.  The command the ncu launch lists / full captures under profiles/ are taken from.
+usage: python profiles/scripts/stage_times.py K [curve]"""
 import ctypes as C
 import json
 import os
@@ -14,7 +15,6 @@ from panda_b200 import gpu_ffi as ffi
 
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 cid = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-settings = [int(x) for x in sys.argv[3:]] or [0, -1]
 n = 1 << k
 fq = O.FQ_BYTES[cid]
 bases = O.gen_bases(cid, O.seed_for(k), n)
@@ -27,9 +27,7 @@ assert reg(d_b.ptr, n, stream) == 0
 stream.sync()
 cfg = ffi.MSMConfiguration(pool, stream, d_b.ptr, d_s.ptr, d_r.ptr, k, 0)
 names = ["digits", "scan", "scatter", "accumulate", "bucket_reduce", "window_reduce", "final"]
-assert ffi.lib.panda_debug_msm_tuning(0, -2) == 0
-for rounds in settings:
-    assert ffi.lib.panda_debug_msm_tuning(-1, rounds) == 0
+for _ in range(1):
     st, info = (C.c_float * 7)(), (C.c_uint * 3)()
     acc = np.zeros(7)
     reps = 3
@@ -51,5 +49,5 @@ for rounds in settings:
         assert fn(cfg) == 0
     stream.sync()
     wall = (time.perf_counter() - t0) / 5 * 1e3
-    print(json.dumps({"k": k, "curve": cid, "affine_rounds": rounds, "ok": ok, "c": info[1], "W": info[2], "total_ms": float(acc.sum()), "call_ms_wall": wall,
+    print(json.dumps({"k": k, "curve": cid, "ok": ok, "c": info[1], "W": info[2], "total_ms": float(acc.sum()), "call_ms_wall": wall,
                       "stage_ms": {a: round(float(b), 3) for a, b in zip(names, acc)}}), flush=True)

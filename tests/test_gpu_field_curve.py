@@ -5,8 +5,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-FIELD_OPS = [(0, "mul", 2), (1, "add", 2), (2, "sub", 2), (3, "sqr", 1), (4, "from_mont", 1), (5, "to_mont", 1), (6, "inv", 1), (7, "neg", 1),
-             (8, "inv_gcd", 1)]
+FIELD_OPS = [(0, "mul", 2), (1, "add", 2), (2, "sub", 2), (3, "sqr", 1), (4, "from_mont", 1), (5, "to_mont", 1), (6, "inv", 1), (7, "neg", 1)]
 
 
 @pytest.fixture(scope="module")
@@ -17,7 +16,7 @@ def dev():
     return ffi, gpu_util
 
 
-@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+@pytest.mark.parametrize("fid", [0, 1, 2, 3, 4, 5])
 def test_field_ops_bit_exact(oracle, dev, fid):
     ffi, gu = dev
     n = 8192
@@ -32,9 +31,12 @@ def test_field_ops_bit_exact(oracle, dev, fid):
         b[(3 - i) * fb:(4 - i) * fb] = v
     da, db, do = gu.DevBuf.from_numpy(a), gu.DevBuf.from_numpy(b), gu.DevBuf(a.size)
     ofn = {"mul": oracle.f_mul, "add": oracle.f_add, "sub": oracle.f_sub, "sqr": oracle.f_sqr, "from_mont": oracle.f_from_mont,
-           "to_mont": oracle.f_to_mont, "inv": oracle.f_inv, "neg": oracle.f_neg, "inv_gcd": oracle.f_inv}
+           "to_mont": oracle.f_to_mont, "inv": oracle.f_inv, "neg": oracle.f_neg}
     for op, name, arity in FIELD_OPS:
-        cnt = 512 if name == "inv" else 2048 if name == "inv_gcd" else n
+        if fid == 5 and name in ("inv", "sqr"):
+            continue            # 255-bit modulus: the folded square and chained lazy products need one spare bit (field.cuh, Bls381Fr); the MSM
+                                # only takes scalars out of Montgomery form in Fr
+        cnt = 512 if name == "inv" else n
         assert ffi.lib.panda_debug_field_op(fid, op, da.ptr, db.ptr, do.ptr, cnt, ffi.PandaStream.null()) == 0
         assert ffi.lib.panda_stream_synchronize(ffi.PandaStream.null()) == 0
         got = do.to_numpy(cnt * fb)
@@ -53,7 +55,7 @@ def _rand_jac(oracle, cid, seed, n):
     return np.concatenate([x, y, lam], axis=1).copy(), aff.copy()
 
 
-@pytest.mark.parametrize("cid", [0, 1])
+@pytest.mark.parametrize("cid", [0, 1, 2])
 def test_curve_ops_match_reference_formulas(oracle, dev, cid):
     """XYZZ madd / add / dbl and Jacobian dbl / to_homogeneous vs the restated reference formulas
     (projective.cuh:163-314, 66-77), including p = inf, q = inf, p == q (doubling) and p == -q."""

@@ -150,6 +150,68 @@ def test_bls12_377(oracle, dev, k):
         assert (affine(oracle, 1, gu.msm_device(bases, scal, n, coord, curve=1), coord) == exp).all()
 
 
+def run_curve(ffi, gu, curve, bases, scal, n, coord, registered=False, host_scalars=False):
+    """MSM of any curve through its own C-ABI names (panda_msm_execute_<curve>[_n | _host_scalars], register_bases_<curve>)"""
+    name = {0: "bn254", 1: "bls12_377", 2: "bls12_381"}[curve]
+    fq = 32 if curve == 0 else 48
+    d_b, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf(3 * fq)
+    s = ffi.PandaStream.new()
+    if registered:
+        assert getattr(ffi.lib, f"panda_msm_register_bases_{name}")(d_b.ptr, n, s) == 0
+    if host_scalars:
+        hs = np.ascontiguousarray(scal)
+        cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, hs.ctypes.data, d_r.ptr, 0, coord)
+        assert getattr(ffi.lib, f"panda_msm_execute_{name}_host_scalars")(cfg, n) == 0
+    else:
+        d_s = gu.DevBuf.from_numpy(scal)
+        cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, d_s.ptr, d_r.ptr, max(n.bit_length() - 1, 0), coord)
+        fn = getattr(ffi.lib, f"panda_msm_execute_{name}") if n & (n - 1) == 0 else None
+        assert (fn(cfg) if fn else getattr(ffi.lib, f"panda_msm_execute_{name}_n")(cfg, n)) == 0
+    s.sync()
+    out = d_r.to_numpy()
+    if registered:
+        assert ffi.lib.panda_msm_unregister_bases(d_b.ptr) == 0
+    return out
+
+
+@pytest.mark.parametrize("k", [0, 4, 10, 13, 16, 18])
+def test_bls12_381(oracle, dev, k):
+    """third curve (12-limb Fq, 255-bit Fr): windowed and table plans, device and host scalars, both coordinates, a ragged count,
+    the host-pointer entry and the partial-sum combine"""
+    ffi, gu = dev
+    n = 1 << k
+    bases = oracle.gen_bases(2, oracle.seed_for(k) + 7, n)
+    scal = oracle.gen_scalars(5, oracle.seed_for(k) + 8, n)
+    if k >= 13:
+        exp = oracle.jac_to_affine(2, oracle.expected_progression_msm(2, oracle.seed_for(k) + 7, scal, n))
+    else:
+        exp = oracle.jac_to_affine(2, oracle.msm(2, bases, scal, n, c=min(max(k, 4), 10)))
+    for coord in (0, 1):
+        for registered in (False, True):
+            assert (affine(oracle, 2, run_curve(ffi, gu, 2, bases, scal, n, coord, registered), coord) == exp).all(), (coord, registered)
+        assert (affine(oracle, 2, run_curve(ffi, gu, 2, bases, scal, n, coord, True, host_scalars=True), coord) == exp).all(), coord
+    if k == 13:
+        m = 5000                                                     # not a power of two
+        e2 = oracle.jac_to_affine(2, oracle.expected_progression_msm(2, oracle.seed_for(k) + 7, scal[:m * 32], m))
+        assert (oracle.jac_to_affine(2, run_curve(ffi, gu, 2, bases[:m * 96], scal[:m * 32], m, 0)) == e2).all()
+        one = oracle.field_const(5, 1)
+        edge = scal.reshape(n, 32).copy()
+        edge[0] = 0; edge[1] = one; edge[2] = oracle.f_neg(5, one)    # 0, 1, r - 1: the 255-bit top window
+        e3 = oracle.jac_to_affine(2, oracle.msm(2, bases, edge.reshape(-1), n, c=10))
+        assert (oracle.jac_to_affine(2, run_curve(ffi, gu, 2, bases, edge.reshape(-1), n, 0, True)) == e3).all()
+        host_out = np.zeros(144, np.uint8)
+        cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), ffi.PandaStream.null(), bases.ctypes.data, scal.ctypes.data, host_out.ctypes.data, k, 0)
+        assert ffi.lib.panda_msm_execute_bls12_381_host(cfg) == 0
+        assert (oracle.jac_to_affine(2, host_out) == exp).all()
+        half = n // 2
+        parts = np.concatenate([run_curve(ffi, gu, 2, bases[:half * 96], scal[:half * 32], half, 0), run_curve(ffi, gu, 2, bases[half * 96:], scal[half * 32:], half, 0)])
+        d_p, d_o = gu.DevBuf.from_numpy(parts), gu.DevBuf(144)
+        assert ffi.lib.panda_msm_combine_bls12_381(d_p.ptr, 2, d_o.ptr, 0, ffi.PandaStream.null()) == 0
+        assert ffi.lib.panda_stream_synchronize(ffi.PandaStream.null()) == 0
+        assert (oracle.jac_to_affine(2, d_o.to_numpy()) == exp).all()
+    assert ffi.lib.panda_msm_tear_down() == 0
+
+
 def test_inputs_are_not_modified_and_calls_repeat(oracle, dev):
     """cached scalars / bases stay intact (the reference converts scalars in place, msm_cuda.cuh:155) and a second call on
     the same cached input returns the same point"""
@@ -369,7 +431,7 @@ def test_registered_bases(oracle, dev):
 
 
 def test_host_api_additions(oracle, dev):
-    """panda_msm_bls12_377_gpu and panda_intt_bn254_gpu_v1: the second curve and the inverse transform in the host API's shape"""
+    """panda_msm_bls12_377_gpu* (all five shapes of unit.rs on the second curve) and panda_intt_bn254_gpu_v1 in the host API's shape"""
     from panda_b200 import gpu_manager as gm
 
     k, n = 11, 1 << 11
@@ -378,8 +440,16 @@ def test_host_api_additions(oracle, dev):
     m = gm.PandaGpuManager.new(0)
     try:
         assert (oracle.jac_to_affine(1, gm.panda_msm_bls12_377_gpu(m, scal, bases)) == exp).all()
+        bi = m.cache_bases(bases, curve=1)                 # init_msm for the second curve: registered, table plan
+        si = m.cache_scalars(scal)
+        assert (oracle.jac_to_affine(1, gm.panda_msm_bls12_377_gpu_with_cached_bases(m, scal, bi)) == exp).all()
+        assert (oracle.jac_to_affine(1, gm.panda_msm_bls12_377_gpu_with_cached_scalars(m, si, bases)) == exp).all()
+        for _ in range(2):
+            assert (oracle.jac_to_affine(1, gm.panda_msm_bls12_377_gpu_with_cached_input(m, si, bi)) == exp).all()
+        assert (oracle.jac_to_affine(1, gm.panda_msm_bls12_377_gpu_host(m, scal, bases)) == exp).all()
         m.set_config(gm.PandaMSMResultCoordinateType.Projective)
         assert (oracle.proj_to_affine(1, gm.panda_msm_bls12_377_gpu(m, scal, bases)) == exp).all()
+        assert (oracle.proj_to_affine(1, gm.panda_msm_bls12_377_gpu_with_cached_input(m, si, bi)) == exp).all()
         x = oracle.gen_scalars(1, 502, n)
         w = oracle.omega_bn254(k)
         y = x.copy(); gm.panda_ntt_bn254_gpu_v1(m, y, w, k)
@@ -387,82 +457,6 @@ def test_host_api_additions(oracle, dev):
         assert (y == x).all()
     finally:
         m.deinit()
-
-
-@pytest.fixture
-def affine_everywhere(dev):
-    """the batched-affine accumulation normally starts at 2^22 bucket entries; the parity tests force it onto small cases"""
-    ffi, _gu = dev
-    assert ffi.lib.panda_debug_msm_tuning(0, -1) == 0
-    yield ffi
-    assert ffi.lib.panda_debug_msm_tuning(22, -1) == 0
-
-
-@pytest.mark.parametrize("k,curve,rounds", [(10, 0, -1), (12, 0, -1), (15, 0, -1), (18, 0, -1), (13, 0, 1), (13, 0, 2), (14, 0, 6), (14, 0, 12), (12, 1, -1), (14, 1, 3)])
-def test_batched_affine_plan(oracle, dev, affine_everywhere, k, curve, rounds):
-    """table plan with batched-affine tree rounds (one GCD inversion per 4096 additions) + XYZZ tail: automatic and forced round counts
-    (fewer rounds than the buckets need: the tail folds the rest; more: the extra rounds only carry points over), both curves, both coordinates"""
-    ffi, gu = dev
-    n = 1 << k
-    assert ffi.lib.panda_debug_msm_tuning(-1, rounds) == 0
-    bases = oracle.gen_bases(curve, 600 + k, n)
-    scal = oracle.gen_scalars(3 if curve else 1, 601 + k, n)
-    exp = oracle.jac_to_affine(curve, oracle.expected_progression_msm(curve, 600 + k, scal, n))
-    for coord in (0, 1):
-        got = gu.msm_device(bases, scal, n, coord, curve=curve, table_mode=2)
-        assert (affine(oracle, curve, got, coord) == exp).all(), coord
-    assert ffi.lib.panda_msm_tear_down() == 0
-
-
-@pytest.mark.parametrize("mode", ["all_equal", "small", "two_values", "top_heavy", "edge_bases", "golden_k13"])
-def test_batched_affine_plan_skew_and_edge_cases(oracle, dev, affine_everywhere, golden_k13, mode):
-    """the affine rounds meet P + P (tangent), P + (-P) (identity), identity operands, and buckets far larger than 2^rounds"""
-    ffi, gu = dev
-    k, n = 13, 1 << 13
-    bases = oracle.gen_bases(0, 5, n).reshape(n, 64).copy()
-    base = oracle.gen_scalars(1, 6, n).reshape(n, 32).copy()
-    if mode == "all_equal":
-        base[:] = base[0]
-    elif mode == "small":
-        small = np.zeros((n, 32), np.uint8); small[:, 0] = np.arange(n) % 3
-        base = oracle.f_to_mont(1, small.reshape(-1)).reshape(n, 32)
-    elif mode == "two_values":
-        base[::2] = base[0]; base[1::2] = base[1]
-    elif mode == "top_heavy":
-        small = np.zeros((n, 32), np.uint8); small[:, 0] = np.arange(n) % 7 + 1
-        base = oracle.f_neg(1, oracle.f_to_mont(1, small.reshape(-1))).reshape(n, 32)
-    elif mode == "edge_bases":       # identities, duplicates and negated pairs that share a scalar (so they meet in one bucket)
-        for i in range(0, n, 16):
-            bases[i] = 0
-            bases[i + 2] = bases[i + 1]; base[i + 2] = base[i + 1]
-            bases[i + 4] = bases[i + 3]; bases[i + 4, 32:] = oracle.f_neg(0, bases[i + 3, 32:].copy()); base[i + 4] = base[i + 3]
-    else:
-        bases, base = golden_k13["bases"].reshape(n, 64), golden_k13["scalars"].reshape(n, 32)      # 8192 copies of the generator
-    if mode == "golden_k13":
-        exp = golden_k13["result_affine"]
-    else:
-        exp = oracle.jac_to_affine(0, oracle.msm(0, bases.reshape(-1), base.reshape(-1), n, c=10))
-    for coord in (0, 1):
-        got = gu.msm_device(bases.reshape(-1), base.reshape(-1), n, coord, table_mode=2)
-        assert (affine(oracle, 0, got, coord) == exp).all(), coord
-    assert ffi.lib.panda_msm_tear_down() == 0
-
-
-def test_batched_affine_plan_streamed_chunks(oracle, dev, affine_everywhere):
-    """chunked (host scalars) pipeline on the affine plan: every chunk runs its own tree rounds, the chunks share the bucket reduction"""
-    ffi, gu = dev
-    n = 40001
-    bases = oracle.gen_bases(0, 650, n)
-    scal = oracle.gen_scalars(1, 651, n)
-    exp = oracle.jac_to_affine(0, oracle.expected_progression_msm(0, 650, scal, n))
-    d_b, d_r = gu.DevBuf.from_numpy(bases), gu.DevBuf(96)
-    s = ffi.PandaStream.new()
-    for chunks in (1, 2, 3, 5):
-        cfg = ffi.MSMConfiguration(ffi.PandaMemPool.null(), s, d_b.ptr, scal.ctypes.data, d_r.ptr, 0, 0)
-        assert ffi.lib.panda_debug_msm_streamed(0, cfg, n, 2, chunks) == 0
-        s.sync()
-        assert (oracle.jac_to_affine(0, d_r.to_numpy()) == exp).all(), chunks
-    assert ffi.lib.panda_msm_tear_down() == 0
 
 
 @pytest.mark.parametrize("split", [2, 3])

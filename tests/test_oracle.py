@@ -9,7 +9,9 @@ P_BN254 = 2188824287183927522224640574525727508869631115729782366268903789464522
 R_BN254 = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 P_BLS377 = 0x01AE3A4617C510EAC63B05C06CA1493B1A22D9F300F5138F1EF3622FBA094800170B5D44300000008508C00000000001
 R_BLS377 = 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001
-MODS = {0: P_BN254, 1: R_BN254, 2: P_BLS377, 3: R_BLS377}
+P_BLS381 = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+R_BLS381 = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+MODS = {0: P_BN254, 1: R_BN254, 2: P_BLS377, 3: R_BLS377, 4: P_BLS381, 5: R_BLS381}
 
 
 def to_int(b):
@@ -33,7 +35,7 @@ def test_field_constants_match_reference_tables(oracle):
     assert to_int(oracle.field_const(3, 2)) & 0xFFFFFFFF == 0xB861857B      # bls12-377 Fr R2 limb 0
 
 
-@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+@pytest.mark.parametrize("fid", [0, 1, 2, 3, 4, 5])
 def test_field_ops_against_python_bigints(oracle, fid):
     p = MODS[fid]
     nb = oracle.field_bytes(fid)
@@ -137,7 +139,7 @@ def test_reference_host_path_config1_k16(oracle):
     assert (oracle.jac_to_affine(0, oracle.msm(0, bases, scal, n, c=13)) == exp).all()
 
 
-@pytest.mark.parametrize("cid,k,c", [(0, 8, 7), (0, 12, 11), (0, 14, 13), (1, 10, 9), (1, 12, 16)])
+@pytest.mark.parametrize("cid,k,c", [(0, 8, 7), (0, 12, 11), (0, 14, 13), (1, 10, 9), (1, 12, 16), (2, 10, 9), (2, 12, 13)])
 def test_fast_msm_equals_closed_form(oracle, cid, k, c):
     """po_msm with any window width equals the O(n) closed form for progression bases, on both curves."""
     n = 1 << k
@@ -263,11 +265,27 @@ def test_generators_are_deterministic_and_valid(oracle):
     assert (a == b).all()
     vals = [to_int(a[i * 32:(i + 1) * 32]) for i in range(100)]
     assert all(v < R_BN254 for v in vals) and len(set(vals)) == 100
-    for cid in (0, 1):
+    for cid in (0, 1, 2):
         pts = oracle.gen_bases(cid, 5, 5000)
         assert oracle.aff_on_curve(cid, pts)
         fb = oracle.FQ_BYTES[cid]
         assert len({bytes(pts[i * 2 * fb:i * 2 * fb + fb]) for i in range(5000)}) == 5000
+
+
+def test_bls12_381_generator_and_group_order(oracle):
+    """third curve: the standard G1 generator lies on y^2 = x^3 + 4, r * G is the identity, (r - 1) * G = -G"""
+    g = oracle.generator(2)
+    gx, gy = to_int(g[:48]), to_int(g[48:])
+    R = 1 << 384
+    x, y = gx * pow(R, -1, P_BLS381) % P_BLS381, gy * pow(R, -1, P_BLS381) % P_BLS381
+    assert x == 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb
+    assert (y * y - x ** 3 - 4) % P_BLS381 == 0 and oracle.aff_on_curve(2, g)
+    minus_one = oracle.f_neg(5, oracle.field_const(5, 1))              # r - 1 in Montgomery form
+    got = oracle.jac_to_affine(2, oracle.scalar_mul(2, g, minus_one))
+    assert (got[:48] == g[:48]).all() and (got[48:] == oracle.f_neg(4, g[48:])).all()
+    two = oracle.f_add(5, oracle.field_const(5, 1), oracle.field_const(5, 1))
+    dbl = oracle.jac_to_affine(2, oracle.jac_dbl(2, np.concatenate([g, oracle.field_const(4, 1)])))
+    assert (oracle.jac_to_affine(2, oracle.scalar_mul(2, g, two)) == dbl).all()
 
 
 # ---- NTT pinned to fixtures produced WITHOUT the oracle (tests/golden/make_ntt_golden.py: sympy + Python big ints) ----------
