@@ -30,6 +30,10 @@
 namespace pb {
 
 static constexpr int NTT_THREADS = 256;
+#ifndef PANDA_NTT_GROUP
+#define PANDA_NTT_GROUP 3
+#endif
+static constexpr unsigned NTT_GROUP = PANDA_NTT_GROUP;  // radix-2 stages a thread does on register-resident elements between two shared-memory exchanges
 static constexpr unsigned NTT_MAX_RADIX_LOG = 8;      // fft.cu:10 MAX_LOG2_RADIX
 static constexpr unsigned NTT_MAX_PARTS = 16;         // destination buffers of the exchange step (GPUs of one box)
 static constexpr unsigned NTT_DIRECT_LOG = 20;        // pass boundaries with at most 2^20 distinct twiddles get a direct table (32 MiB, L2-resident);
@@ -166,7 +170,7 @@ PB_DEV void sm_store(uint32_t *sm, uint32_t LS, uint32_t idx, const F &x) {
 // DIF stages s .. s+G-1 of an N = 2^r point transform on the 2^G elements a thread holds:
 // x[k] is row hi * 2^(r-s) + k * 2^(r-G-s) + low.  Butterfly (u, v) -> (u + v, (u - v) * w^(j << stage)), j = lower row mod half.
 template <class F, int G>
-PB_DEV void radix_unit(F (&x)[8], unsigned s, unsigned r, uint32_t low, const uint32_t *__restrict__ stage_tw) {
+PB_DEV void radix_unit(F (&x)[1 << G], unsigned s, unsigned r, uint32_t low, const uint32_t *__restrict__ stage_tw) {
 #pragma unroll
     for (int t = 0; t < G; t++) {
         constexpr int size = 1 << G;
@@ -186,10 +190,10 @@ PB_DEV void radix_unit(F (&x)[8], unsigned s, unsigned r, uint32_t low, const ui
 }
 
 // stage groups of a pass: ceil(r / 3) groups, as even as possible
-struct NttGroups { unsigned n, g[3]; };
+struct NttGroups { unsigned n, g[8]; };
 PB_DEV NttGroups ntt_groups(unsigned r) {
     NttGroups q{};
-    q.n = (r + 2) / 3;
+    q.n = (r + NTT_GROUP - 1) / NTT_GROUP;
     for (unsigned i = 0; i < q.n; i++) q.g[i] = r / q.n + (i < r % q.n ? 1 : 0);
     return q;
 }
@@ -208,7 +212,7 @@ PB_DEV void run_group(unsigned s, unsigned r, unsigned logC, bool row_fastest, c
         else { col = u & ((1u << logC) - 1); rest = u >> logC; }
         const uint32_t low = rest & ((1u << lowbits) - 1), hi = rest >> lowbits;
         const uint32_t row0 = (hi << (r - s)) + low;
-        F x[8];
+        F x[1 << G];
 #pragma unroll
         for (int k = 0; k < (1 << G); k++) x[k] = ld(row0 + ((uint32_t)k << lowbits), col);
         radix_unit<F, G>(x, s, r, low, stage_tw);
@@ -230,11 +234,9 @@ PB_DEV void tile_transform(uint32_t *sm, uint32_t LS, uint32_t CP, unsigned r, u
         auto ld = [&](uint32_t row, uint32_t col) -> F { return first ? gl(row, col) : sm_load<F>(sm, LS, row * CP + col); };
         auto st = [&](uint32_t row, uint32_t col, const F &x) { if (last) gs(row, col, x); else sm_store(sm, LS, row * CP + col, x); };
         const bool rf = first && !last && first_row_fastest;
-        switch (q.g[gi]) {
-            case 3: run_group<F, 3>(s, r, logC, rf, stage_tw, ld, st); break;
-            case 2: run_group<F, 2>(s, r, logC, rf, stage_tw, ld, st); break;
-            default: run_group<F, 1>(s, r, logC, rf, stage_tw, ld, st); break;
-        }
+        if (NTT_GROUP >= 3 && q.g[gi] == 3) { if constexpr (NTT_GROUP >= 3) run_group<F, 3>(s, r, logC, rf, stage_tw, ld, st); }
+        else if (q.g[gi] == 2) run_group<F, 2>(s, r, logC, rf, stage_tw, ld, st);
+        else run_group<F, 1>(s, r, logC, rf, stage_tw, ld, st);
         if (!last) __syncthreads();
         s += q.g[gi];
     }
