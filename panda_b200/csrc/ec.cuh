@@ -130,6 +130,80 @@ struct Xyzz {
         zz = zz * o.zz * pp;
         zzz = zzz * o.zzz * ppp;
     }
+    // this += o with the independent field products of every dependency level issued side by side (F::mul_batch): same formulas and
+    // results as add(), five levels of products (6, 2, 3, 2, 1) instead of fourteen in a row.  For the stitching kernels, where a handful
+    // of warps walk chains of dependent point additions and the latency of ONE addition is what the kernel time is made of.
+    PB_DEV void add_ilp(const Xyzz &o) {
+        if (o.is_identity()) return;
+        if (is_identity()) { *this = o; return; }
+        F r6[6];
+        {
+            const F a6[6] = {x, y, o.x, o.y, zz, zzz};
+            const F b6[6] = {o.zz, o.zzz, zz, zzz, o.zz, o.zzz};
+            F::template mul_batch<6>(r6, a6, b6);
+        }
+        const F u1 = r6[0], s1 = r6[1];
+        const F p = r6[2] - u1, r = r6[3] - s1;
+        if (p.is_zero()) {
+            if (r.is_zero()) *this = dbl();
+            else *this = identity();
+            return;
+        }
+        F r2[2];
+        {
+            const F a2[2] = {p, r};
+            F::template mul_batch<2>(r2, a2, a2);
+        }
+        const F pp = r2[0], rr = r2[1];
+        F r3[3];
+        {
+            const F a3[3] = {p, u1, r6[4]};
+            const F b3[3] = {pp, pp, pp};
+            F::template mul_batch<3>(r3, a3, b3);
+        }
+        const F ppp = r3[0], q = r3[1];
+        const F x3 = rr - ppp - q.dbl();
+        F r4[3];
+        {
+            const F a4[3] = {s1, r6[5], r};
+            const F b4[3] = {ppp, ppp, q - x3};
+            F::template mul_batch<3>(r4, a4, b4);
+        }
+        y = r4[2] - r4[0];
+        x = x3;
+        zz = r3[2];
+        zzz = r4[1];
+    }
+    // 2 * this, products side by side like add_ilp: four levels (2, 4, 2, 1) instead of nine in a row
+    PB_DEV Xyzz dbl_ilp() const {
+        if (is_identity()) return *this;
+        const F u = y.dbl();
+        F r1[2];
+        {
+            const F a1[2] = {u, x};
+            F::template mul_batch<2>(r1, a1, a1);
+        }
+        const F v = r1[0], m = r1[1].dbl() + r1[1];
+        F r2[4];
+        {
+            const F a2[4] = {u, x, v, m};
+            const F b2[4] = {v, v, zz, m};
+            F::template mul_batch<4>(r2, a2, b2);
+        }
+        const F w = r2[0], s = r2[1];
+        Xyzz r;
+        r.x = r2[3] - s.dbl();
+        F r3[3];
+        {
+            const F a3[3] = {w, w, m};
+            const F b3[3] = {y, zzz, s - r.x};
+            F::template mul_batch<3>(r3, a3, b3);
+        }
+        r.y = r3[2] - r3[0];
+        r.zz = r2[2];
+        r.zzz = r3[1];
+        return r;
+    }
 };
 
 // Jacobian point in the reference's result layout (x || y || z, Montgomery, canonical limbs).

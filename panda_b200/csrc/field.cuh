@@ -306,6 +306,35 @@ struct Fe {
         r.l[N - 1] = ptx::addc(A[N - 1], 0);
         return r;
     }
+    // K independent products with their rows interleaved (row i of every product, then row i + 1, ..): a single product is one long
+    // dependent chain of carry-propagating multiply-adds, which is what a lone warp of the latency-bound stitching kernels waits on; side by
+    // side the chains of different products fill each other's issue gaps.  Same arithmetic as mul_inline, product by product.
+    template <int K>
+    PB_DEV static void mul_batch(Fe (&r)[K], const Fe (&a)[K], const Fe (&b)[K]) {
+        uint32_t A[K][N], B[K][N];
+        _Pragma("unroll") for (int k = 0; k < K; k++) {
+            const uint32_t bi = b[k].l[0];
+            _Pragma("unroll") for (int j = 0; j < N; j += 2) {
+                ptx::mul_wide(A[k][j], A[k][j + 1], a[k].l[j], bi);
+                ptx::mul_wide(B[k][j], B[k][j + 1], a[k].l[j + 1], bi);
+            }
+        }
+        _Pragma("unroll") for (int k = 0; k < K; k++) reduce_row(A[k], B[k]);
+        _Pragma("unroll") for (int i = 1; i < N; i++) {
+            _Pragma("unroll") for (int k = 0; k < K; k++) {
+                if (i & 1) mul_row(B[k], A[k], a[k].l, b[k].l[i]); else mul_row(A[k], B[k], a[k].l, b[k].l[i]);
+            }
+            _Pragma("unroll") for (int k = 0; k < K; k++) {
+                if (i & 1) reduce_row(B[k], A[k]); else reduce_row(A[k], B[k]);
+            }
+        }
+        _Pragma("unroll") for (int k = 0; k < K; k++) {
+            r[k].l[0] = ptx::add_cc(A[k][0], B[k][1]);
+            _Pragma("unroll") for (int q = 1; q < N - 1; q++) r[k].l[q] = ptx::addc_cc(A[k][q], B[k][q + 1]);
+            r[k].l[N - 1] = ptx::addc(A[k][N - 1], 0);
+        }
+    }
+
     // Montgomery square: the rows of the product above with the symmetric terms folded -- row i multiplies a_i into
     // (a_i, 2a_{i+1}, (2a)_{i+2}, ..) and skips the columns below i, whose products the earlier rows already added twice.
     // N(N+1)/2 + N^2 + N multiply-adds instead of 2N^2 + N (108 vs 136 for N = 8); the skipped columns become carry-only adds.
@@ -330,10 +359,21 @@ struct Fe {
         return r;
     }
 
-    // Montgomery -> canonical integer (multiply by 1): reduction rows only.  Output canonical.
+    // Montgomery -> canonical integer: the N reduction rows of a product by 1 without its N^2 multiply-adds (N^2 + N instead of
+    // 2N^2 + N; the MSM sort recodes every scalar once or twice per call).  Output canonical.
     PB_DEV Fe from_mont() const {
-        Fe o = zero(); o.l[0] = 1;
-        return (*this * o).canon();
+        uint32_t A[N], B[N];
+        _Pragma("unroll") for (int j = 0; j < N; j++) { A[j] = l[j]; B[j] = 0; }
+        reduce_row(A, B);
+        _Pragma("unroll") for (int i = 1; i < N; i++) {
+            if (i & 1) { shift_row(B, A); reduce_row(B, A); }
+            else       { shift_row(A, B); reduce_row(A, B); }
+        }
+        Fe r;
+        r.l[0] = ptx::add_cc(A[0], B[1]);
+        _Pragma("unroll") for (int k = 1; k < N - 1; k++) r.l[k] = ptx::addc_cc(A[k], B[k + 1]);
+        r.l[N - 1] = ptx::addc(A[N - 1], 0);
+        return r.canon();
     }
     PB_DEV Fe to_mont() const { return *this * r2(); }
 
@@ -383,6 +423,16 @@ private:
             E[j + 1] = ptx::madc_hi_cc(P::mod(j), m, E[j + 1]);
         }
         O[N - 1] = ptx::addc(O[N - 1], 0);
+    }
+    // mul_row with a zero multiplier: only the change of frame (divide by 2^32) and its carries
+    PB_DEV static void shift_row(uint32_t *Y, uint32_t *Z) {
+        Y[0] = ptx::add_cc(Y[0], Z[1]);
+        _Pragma("unroll") for (int j = 0; j < N - 2; j += 2) {
+            Z[j] = ptx::addc_cc(Z[j + 2], 0);
+            Z[j + 1] = ptx::addc_cc(Z[j + 3], 0);
+        }
+        Z[N - 2] = ptx::addc(0, 0);
+        Z[N - 1] = 0;
     }
     // Entering a new row: Y was odd-aligned, Z was even-aligned with Z[0] == 0.  Divide by 2^32:
     // Y becomes the even accumulator, Z (dropping two limbs) the odd one; Z[1] folds into Y[0].

@@ -59,13 +59,15 @@ static bool balanced_windows(uint32_t bits, uint32_t c, uint32_t *W, uint32_t *w
 
 static uint32_t pow2_floor(uint64_t v) { uint32_t r = 1; while ((uint64_t)r * 2 <= v) r *= 2; return r; }
 
-MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget, uint32_t chunks) {
+MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget, uint32_t chunks,
+                      uint32_t class_log2) {
     const uint32_t bits = curve_scalar_bits(curve);
     const size_t fq_bytes = curve_fq_bytes(curve);
     MsmPlan p{};
     p.n = n;
     p.table_n = n;
     p.folded = folded ? 1 : 0;
+    p.class_log2 = class_log2;
     const uint32_t c_lo = 8, c_hi = folded ? 23 : 16;          // windowed digit codes are 16 bit
     uint32_t best_c = 0;
     double best = 1e300;
@@ -93,8 +95,8 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.windows = windows_for(bits, p.c);
     p.wide = p.windows;
     if (folded) balanced_windows(bits, p.c, &p.windows, &p.wide);
-    p.nb = 1u << (p.c - 1);
-    p.sets = folded ? 1 : p.windows;
+    p.nb = (1u << (p.c - 1)) >> class_log2;                     // a bucket-class shard reduces its own residue class only (both cost terms
+    p.sets = folded ? 1 : p.windows;                            // above shrink by the class count, so the window width is the whole job's)
     // chunks (folded only): every chunk is a physical bucket set of its own (counts, sorted list, partial slots); the bucket
     // reduction merges the chunks of a logical set
     p.chunks = folded ? std::max<uint32_t>(1, std::min<uint32_t>(chunks, std::max<uint32_t>(1, n / 4096))) : 1;
@@ -110,7 +112,7 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.table_bytes = folded ? (size_t)n * p.windows * 2 * fq_bytes : 0;
     // segment length: about one average bucket, so that most buckets end up with one or two partial sums, but
     // never so long that the accumulation kernel has fewer than ~4 waves of threads (148 SMs x 384 threads)
-    const uint64_t entries = (uint64_t)n * p.windows;
+    const uint64_t entries = ((uint64_t)n * p.windows) >> class_log2;           // expected (uniform digits)
     uint32_t L = pow2_floor(std::max<uint64_t>(1, entries / ((uint64_t)p.nb * p.sets)));
     L = std::min<uint32_t>(L, pow2_floor(std::max<uint64_t>(1, entries / (148ull * 384 * 4))));
     L = std::min<uint32_t>(std::max<uint32_t>(L, 8), 512);
@@ -134,7 +136,7 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.phases = 1;
     if (folded) {
         static const uint32_t forced = [] { const char *e = getenv("PANDA_MSM_PHASES"); return e ? (uint32_t)atoi(e) : 0u; }();
-        while (p.phases < p.nb && (uint64_t)p.stride * 4 / p.phases > ((uint64_t)128 << 20)) p.phases *= 2;
+        while (p.phases < p.nb && (((uint64_t)p.stride * 4) >> class_log2) / p.phases > ((uint64_t)128 << 20)) p.phases *= 2;
         if (forced) p.phases = std::min<uint32_t>(pow2_floor(forced), p.nb);
     }
 
@@ -146,7 +148,7 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.off_cursor = off;  off = align(off + phys * p.nb * 4);
     p.off_biglist = off; off = align(off + phys * p.nb * 4);
     p.off_tiles = off;   off = align(off + phys * ((p.nb + 4095) / 4096) * 4);
-    p.off_digits = off;  off = align(off + (folded ? (size_t)p.chunks * p.stride * 4 : (size_t)p.windows * n * 2));
+    p.off_digits = off;  off = align(off + (class_log2 ? 0 : folded ? (size_t)p.chunks * p.stride * 4 : (size_t)p.windows * n * 2));   // class shards recode the scalars in both passes
     p.off_sorted = off;  off = align(off + phys * p.stride * 4);
     p.off_slots = off;   off = align(off + phys * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);
     p.off_chunks = off;  off = align(off + (size_t)p.sets * p.chunks_ps * 2 * 4 * fq_bytes);
@@ -378,8 +380,12 @@ static cudaError_t aux_stream_for_current_device(cudaStream_t *out);
 static uint32_t resident_chunks(uint32_t n);
 
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
-                    cudaMemPool_t pool, cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings, int table_mode) {
+                    cudaMemPool_t pool, cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings, int table_mode,
+                    uint32_t class_count, uint32_t class_index) {
     const size_t fq_bytes = curve_fq_bytes(curve);
+    if (class_count == 0 || class_count > 64 || (class_count & (class_count - 1)) || class_index >= class_count) return cudaErrorInvalidValue;
+    uint32_t class_log2 = 0;
+    while ((1u << class_log2) < class_count) class_log2++;
     if (n == 0) {   // empty sum: the identity, all-zero like the reference (msm_cuda.cuh:395,405)
         PB_CUDA(cudaMemsetAsync(result, 0, 3 * fq_bytes, stream));
         return cudaSuccess;
@@ -391,9 +397,11 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
     const void *table = table_ref ? table_ref->ptr : nullptr;
     if (table) {
         // per-stage timings are an attribution pass over the unsplit pipeline; the product path splits large jobs in two chunks
-        const uint32_t chunks = timings ? 1 : resident_chunks(n);
-        MsmPlan p = msm_make_plan(curve, n, true, tc, seg_override, ~(size_t)0, chunks);
+        const uint32_t chunks = (timings || class_log2) ? 1 : resident_chunks(n);
+        MsmPlan p = msm_make_plan(curve, n, true, tc, seg_override, ~(size_t)0, chunks, class_log2);
+        if (!p.c) return cudaErrorInvalidValue;
         p.table_n = table_n;
+        p.class_index = class_index;
         if (p.chunks > 1) {
             MsmFeed feed{nullptr, nullptr, nullptr, nullptr};
             PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
@@ -401,7 +409,9 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
         }
         return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings);
     }
-    MsmPlan p = msm_make_plan(curve, n, false, c_override <= 16 ? c_override : 0, seg_override);
+    MsmPlan p = msm_make_plan(curve, n, false, c_override <= 16 ? c_override : 0, seg_override, ~(size_t)0, 1, class_log2);
+    if (!p.c) return cudaErrorInvalidValue;
+    p.class_index = class_index;
     return run_pipeline(curve, p, bases, scalars, result, coord, pool, stream, timings);
 }
 

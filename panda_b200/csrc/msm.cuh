@@ -37,6 +37,8 @@ struct MsmPlan {
     uint32_t chunk_first;  // points in chunk 0
     uint32_t chunk_n;      // points in every later chunk (the last one may be shorter)
     uint32_t phases;       // folded scatter: passes over the codes, one bucket range each (L2-resident output slice)
+    uint32_t class_log2;   // bucket-class shard (multi-GPU): this run only takes the digits whose bucket index is congruent to class_index
+    uint32_t class_index;  //    modulo 2^class_log2; nb counts the buckets of that class.  0 / 0: the whole MSM
     // workspace layout (byte offsets into one arena)
     size_t off_counts, off_offsets, off_cursor, off_biglist, off_tiles, off_digits, off_sorted, off_slots, off_chunks, off_gsums, bytes;
     size_t table_bytes;    // folded: size of the precomputed table (W * n affine points)
@@ -44,7 +46,7 @@ struct MsmPlan {
 
 // window width / segment length selection; c_override = 0 -> cost model.  table_budget: bytes available for a table (folded only).
 MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget = ~(size_t)0,
-                      uint32_t chunks = 1);
+                      uint32_t chunks = 1, uint32_t class_log2 = 0);
 
 // How a chunked pipeline is fed: host_scalars != nullptr: chunk q is uploaded on copy_stream right before its kernels are queued;
 // aux_stream != nullptr: odd chunks run on it, so that one chunk's sort overlaps the previous chunk's accumulation.
@@ -69,7 +71,13 @@ enum MsmTableMode { MSM_TABLE_OFF = 0, MSM_TABLE_AUTO = 1, MSM_TABLE_EAGER = 2, 
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result,
                     CoordType coord, cudaMemPool_t pool, cudaStream_t stream,
                     uint32_t c_override = 0, uint32_t seg_override = 0, MsmStageTimes *timings = nullptr,
-                    int table_mode = MSM_TABLE_DEFAULT);
+                    int table_mode = MSM_TABLE_DEFAULT, uint32_t class_count = 1, uint32_t class_index = 0);
+
+// Bucket-class shards (class_count > 1, a power of two <= 64): the run adds up only the digits whose bucket index is congruent to
+// class_index modulo class_count and returns  sum_{b = class_index (mod class_count)} (b + 1) * B_b  as a Jacobian point; the class_count
+// partials add up to the MSM (msm_combine).  Every GPU of a sharded MSM sees ALL points and ALL scalars but does 1 / class_count of the
+// additions AND of the bucket reduction with the window width of the whole job -- a shard by point range repeats the reduction on every
+// GPU and has to narrow its windows.  Adjacent buckets belong to different classes, so skewed digit distributions stay balanced.
 
 // Same MSM with the scalars in HOST memory (pinned for full overlap; pageable works).  With a table for `bases` the points are
 // processed in chunks that share the bucket reduction, so the upload of chunk q+1 overlaps the sort / accumulation of chunk q;

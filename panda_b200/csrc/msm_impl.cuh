@@ -39,19 +39,34 @@ static constexpr uint32_t BIG_SPAN = 8;             // buckets with more partial
 // Windows 0 .. wide-1 are c bits wide, the others c-1 (the table plan balances its windows this way so that no window is short;
 // wide = W gives uniform windows).  Calls f(window, magnitude (1 .. 2^(width-1)), negative) for every non-zero digit.
 template <class Fr, class F>
-PB_DEV void for_each_digit(Fr s, uint32_t c, uint32_t W, uint32_t wide, F &&f) {
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < W; w++) {
-        const uint32_t cw = w < wide ? c : c - 1;
-        const uint32_t v = (s.l[0] & ((1u << cw) - 1)) + carry;
-#pragma unroll
-        for (int k = 0; k < Fr::N - 1; k++) s.l[k] = __funnelshift_r(s.l[k], s.l[k + 1], cw);
-        s.l[Fr::N - 1] >>= cw;
+PB_DEV void for_each_digit(const Fr &s, uint32_t c, uint32_t W, uint32_t wide, F &&f) {
+    // The limbs are fed one by one (static register indices) into a 64-bit bit buffer from which the windows are cut: ~15 instructions per
+    // window where shifting the whole 256-bit value down after every window took ~35 (the class-shard passes were instruction-bound:
+    // ncu, 658 warp instructions per scalar).  The inner loop's trip count depends on c only, so the warp stays converged.
+    uint64_t buf = 0;
+    uint32_t have = 0, w = 0, carry = 0;
+    uint32_t cw = w < wide ? c : c - 1;
+    auto emit = [&](uint32_t bits) {
+        const uint32_t v = bits + carry;
         uint32_t mag = v, neg = 0;
         carry = 0;
         if (w + 1 < W && v > (1u << (cw - 1))) { mag = (1u << cw) - v; neg = 1; carry = 1; }   // the top window is never recoded
         if (mag) f(w, mag, neg);
+        w++;
+        cw = w < wide ? c : c - 1;
+    };
+#pragma unroll
+    for (int k = 0; k < Fr::N; k++) {
+        if (have <= 32) buf |= (uint64_t)s.l[k] << have;      // (beyond that only the top window is left and the remaining limbs are zero)
+        have += 32;
+        while (have >= cw && w + 1 < W) {
+            const uint32_t bits = (uint32_t)buf & ((1u << cw) - 1);
+            buf >>= cw;
+            have -= cw;
+            emit(bits);
+        }
     }
+    if (w < W) emit((uint32_t)buf);        // the top window takes whatever is left (W * c covers the scalar width)
 }
 
 // K1: scalars -> per-bucket counts and the digit codes, window-major (code[w*n + i]).
@@ -61,7 +76,7 @@ PB_DEV void for_each_digit(Fr s, uint32_t c, uint32_t W, uint32_t wide, F &&f) {
 static constexpr uint32_t CODE_SKIP32 = 0xFFFFFFFFu;
 template <class C, bool FOLDED>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, uint32_t nb,
-                                                void *__restrict__ codes_out, uint32_t *__restrict__ counts) {
+                                                uint32_t class_log2, uint32_t class_index, void *__restrict__ codes_out, uint32_t *__restrict__ counts) {
     using Fr = typename C::Fr;
     using Code = typename std::conditional<FOLDED, uint32_t, uint16_t>::type;
     Code *codes = static_cast<Code *>(codes_out);
@@ -70,11 +85,15 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; the input is left untouched
         uint32_t next_w = 0;
+        const uint32_t class_mask = (1u << class_log2) - 1;
         for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t mag, uint32_t neg) {
+            // bucket-class shard: only the buckets congruent to class_index survive, renumbered 0 .. nb-1 (bucket = local * 2^class_log2 + class_index)
+            if (((mag - 1) & class_mask) != class_index) return;
+            const uint32_t local = (mag - 1) >> class_log2;
             for (; next_w < w; next_w++) codes[(size_t)next_w * n + i] = SKIP;
-            codes[(size_t)w * n + i] = (Code)((mag - 1) | (neg << SIGN_BIT));
+            codes[(size_t)w * n + i] = (Code)(local | (neg << SIGN_BIT));
             next_w = w + 1;
-            atomicAdd(&counts[(FOLDED ? (size_t)0 : (size_t)w * nb) + (mag - 1)], 1u);
+            atomicAdd(&counts[(FOLDED ? (size_t)0 : (size_t)w * nb) + local], 1u);
         });
         for (; next_w < W; next_w++) codes[(size_t)next_w * n + i] = SKIP;
     }
@@ -226,6 +245,31 @@ static __global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *_
     }
 }
 
+// K1 / K3 of a bucket-class shard (msm.cuh): 1 / 2^class_log2 of the digits survive, so a dense code array would be mostly "skip" words
+// written and re-read for nothing (measured on one class of eight at 2^24: 1.40 ms against 0.19 ms for the digits of a 2^21-point slice).
+// Both passes recode the scalars instead -- 32 B read per scalar and pass, no code array: the first counts the surviving digits per bucket,
+// the second (SCATTER) places them, one bucket range per launch row (blockIdx.y) like k_scatter_folded.
+template <class C, bool FOLDED, bool SCATTER>
+__global__ void __launch_bounds__(256) k_class_pass(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, uint32_t nb,
+                                                    uint32_t class_log2, uint32_t class_index, uint32_t n_total, uint32_t point0, uint32_t stride,
+                                                    uint32_t log2_span, uint32_t *__restrict__ counters, uint32_t *__restrict__ sorted) {
+    using Fr = typename C::Fr;
+    const uint32_t class_mask = (1u << class_log2) - 1, phase = blockIdx.y;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();
+        for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t mag, uint32_t neg) {
+            if (((mag - 1) & class_mask) != class_index) return;
+            const uint32_t local = (mag - 1) >> class_log2;
+            uint32_t *ctr = counters + (FOLDED ? (size_t)0 : (size_t)w * nb) + local;      // counts (first pass) / cursor (second pass)
+            if (!SCATTER) { atomicAdd(ctr, 1u); return; }
+            if ((local >> log2_span) != phase) return;
+            const uint32_t pos = atomicAdd(ctr, 1u);
+            const uint32_t entry = FOLDED ? w * n_total + point0 + i : i;
+            sorted[(FOLDED ? (size_t)0 : (size_t)w * stride) + pos] = entry | (neg << 31);
+        });
+    }
+}
+
 // K4: bucket accumulation.  Thread (w, s) owns sorted entries [s*L, (s+1)*L) of bucket set w -- a fixed amount
 // of work whatever the bucket sizes are -- and emits one partial sum per bucket it touches into slot
 // (s + bucket), which is unique and makes a bucket's partials contiguous.
@@ -339,10 +383,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const uint8_t *__
 
 // ---- cold-path wrappers: the stitching kernels below are latency-bound one-offs; keeping the group law out of
 // line there keeps code size (and compile time) down without touching the hot accumulate / bucket kernels.
+// 8-limb fields: the latency-oriented forms (ec.cuh add_ilp / dbl_ilp); with 12 limbs six products side by side do not fit the register file.
 template <class F>
-__device__ __noinline__ void add_cold(Xyzz<F> &a, const Xyzz<F> &b) { a.add(b); }
+__device__ __noinline__ void add_cold(Xyzz<F> &a, const Xyzz<F> &b) { if constexpr (F::N <= 8) a.add_ilp(b); else a.add(b); }
 template <class F>
-__device__ __noinline__ void dbl_cold(Xyzz<F> &a) { a = a.dbl(); }
+__device__ __noinline__ void dbl_cold(Xyzz<F> &a) { if constexpr (F::N <= 8) a = a.dbl_ilp(); else a = a.dbl(); }
 
 // ---- warp-shuffle helpers -------------------------------------------------------------------------
 
@@ -530,7 +575,7 @@ __global__ void __launch_bounds__(WIN_THREADS) k_group_reduce(const uint8_t *__r
 // mode: a single set, no doublings), conversion to the reference's result coordinates, canonical store.
 template <class C>
 __global__ void __launch_bounds__(32) k_final(const uint8_t *__restrict__ gsums, uint32_t sets, uint32_t groups, uint32_t log2_group_unit, uint32_t c,
-                                              int coord, uint8_t *__restrict__ result) {
+                                              uint32_t class_log2, uint32_t class_index, int coord, uint8_t *__restrict__ result) {
     using Fq = typename C::Fq;
     using Pt = Xyzz<Fq>;
     const uint32_t lane = threadIdx.x;
@@ -547,6 +592,22 @@ __global__ void __launch_bounds__(32) k_final(const uint8_t *__restrict__ gsums,
             uint32_t active = 1; while (active < groups) active <<= 1;
             warp_running_sums(P, R, wR, lane, active);
             if (lane == 0) add_cold(P, mul_pow2(wR, log2_group_unit));
+        }
+        if (lane == 0 && class_log2) {
+            // bucket-class shard: local bucket q stands for bucket b = q * K + g (K = 2^class_log2, g = class_index), whose weight is
+            // b + 1 = K * (q + 1) - (K - 1 - g):   S_set = K * P - (K - 1 - g) * R     (P = sum (q+1) B_q, R = sum B_q)
+            P = mul_pow2(P, class_log2);
+            const uint32_t k = (1u << class_log2) - 1 - class_index;
+            if (k) {
+                Pt kr = Pt::identity();
+#pragma unroll 1
+                for (int bit = (int)class_log2 - 1; bit >= 0; bit--) {
+                    dbl_cold(kr);
+                    if ((k >> bit) & 1) add_cold(kr, R);
+                }
+                kr.y = kr.y.neg();
+                add_cold(P, kr);
+            }
         }
         if (lane == 0) {
             if (set + 1 < sets) {          // acc = 2^c * acc + S_set
@@ -729,14 +790,21 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             uint8_t *slots_q = slots + set0 * slot_stride;
             tm.mark();
             const uint32_t sblocks = std::min<uint32_t>((nq + 255) / 256, 148 * 8);
-            if (p.folded) k_digits<C, true><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, codes_q, counts_q);
-            else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, codes_q, counts_q);
+            if (p.class_log2) {
+                if (p.folded) k_class_pass<C, true, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, p.table_n, point0, p.stride, 0, counts_q, nullptr);
+                else k_class_pass<C, false, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, nq, 0, p.stride, 0, counts_q, nullptr);
+            } else if (p.folded) k_digits<C, true><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, codes_q, counts_q);
+            else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, codes_q, counts_q);
             tm.mark();
             k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, p.nb, tiles_ps, tiles_q);
             k_scan_tops<<<p.sets, 1024, 0, sq>>>(tiles_q, tiles_ps, p.nb, offsets_q);
             k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q, big_count_q, big_list_q);
             tm.mark();
-            if (p.folded) {
+            if (p.class_log2) {
+                uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
+                if (p.folded) k_class_pass<C, true, true><<<dim3(sblocks, p.phases), 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, p.table_n, point0, p.stride, log2_span, cursor_q, sorted_q);
+                else k_class_pass<C, false, true><<<dim3(sblocks, 1), 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, nq, 0, p.stride, 31, cursor_q, sorted_q);
+            } else if (p.folded) {
                 uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
                 k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, sq>>>((const uint32_t *)codes_q, nq, p.windows, p.table_n, point0, log2_span, cursor_q, sorted_q);
             } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, sq>>>((const uint16_t *)codes_q, nq, p.nb, cursor_q, sorted_q);
@@ -780,7 +848,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             final_in = gsums2; final_groups = 1;
         }
         tm.mark();
-        k_final<C><<<1, 32, 0, stream>>>(final_in, p.sets, final_groups, final_unit, p.c, (int)coord, (uint8_t *)result);
+        k_final<C><<<1, 32, 0, stream>>>(final_in, p.sets, final_groups, final_unit, p.c, p.class_log2, p.class_index, (int)coord, (uint8_t *)result);
         tm.mark();
         err = cudaGetLastError();
     } while (0);

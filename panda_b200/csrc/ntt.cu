@@ -29,15 +29,29 @@
 
 namespace pb {
 
-static constexpr int NTT_THREADS = 256;
+// Tile shape, measured at 2^24 on B200 (profiles/r2_ntt_variants.md): 256 threads x radix-8 units (124 registers, 2 CTAs of 72 KB per SM)
+// 4.10 ms; 128 threads x radix-4 units capped at 5 CTAs per SM (92 registers, 36 KB tiles) 3.86 ms -- more, smaller CTAs overlap one
+// tile's global loads and barriers with the others' butterflies; 128 x radix-8 4.14, 256 x radix-4 4.26, 6 CTAs per SM (80 registers) 3.93.
+#ifndef PANDA_NTT_THREADS
+#define PANDA_NTT_THREADS 128
+#endif
+static constexpr int NTT_THREADS = PANDA_NTT_THREADS;  // threads per CTA; a tile holds 8 elements per thread (one radix-8 unit each)
+#ifndef PANDA_NTT_MIN_CTAS
+#define PANDA_NTT_MIN_CTAS 5
+#endif
+static constexpr int NTT_MIN_CTAS = PANDA_NTT_MIN_CTAS;  // __launch_bounds__ minimum of resident CTAs per SM (caps the registers)
+static constexpr unsigned NTT_TILE_LOG = NTT_THREADS == 128 ? 10 : NTT_THREADS == 512 ? 12 : 11;
+static constexpr unsigned NTT_MIN_LOGC = NTT_TILE_LOG - 8;       // columns per tile of a full radix-256 pass: 32-byte elements in runs of 2^NTT_MIN_LOGC
 #ifndef PANDA_NTT_GROUP
-#define PANDA_NTT_GROUP 3
+#define PANDA_NTT_GROUP 2
 #endif
 static constexpr unsigned NTT_GROUP = PANDA_NTT_GROUP;  // radix-2 stages a thread does on register-resident elements between two shared-memory exchanges
 static constexpr unsigned NTT_MAX_RADIX_LOG = 8;      // fft.cu:10 MAX_LOG2_RADIX
 static constexpr unsigned NTT_MAX_PARTS = 16;         // destination buffers of the exchange step (GPUs of one box)
-static constexpr unsigned NTT_DIRECT_LOG = 20;        // pass boundaries with at most 2^20 distinct twiddles get a direct table (32 MiB, L2-resident);
-                                                      // 2^24 entries (512 MiB) measured no better in steady state: 4.16 vs 4.10 ms at 2^24
+static constexpr unsigned NTT_DIRECT_LOG = 26;        // pass boundaries with at most 2^26 distinct twiddles get a direct table (one product per element
+                                                      // instead of two through the two-level table): 32 B of extra HBM traffic per element of that pass,
+                                                      // 512 MiB per cached (omega, 2^24) pair.  With the small tiles above 3.68 vs 3.86 ms at 2^24, 16.5 vs
+                                                      // 17.1 ms at 2^26; a table that does not fit falls back to 2^20 (ntt_get_tables)
 
 struct NttShape {
     unsigned log_n, passes;
@@ -73,7 +87,7 @@ static unsigned ntt_direct_log() {       // PANDA_NTT_DIRECT_LOG overrides (tuni
     return v;
 }
 
-static NttTableLayout ntt_table_layout(const NttShape &s) {
+static NttTableLayout ntt_table_layout(const NttShape &s, unsigned direct_log = ntt_direct_log()) {
     NttTableLayout t{};
     t.lo_bits = (s.log_n + 1) / 2;
     t.hi_bits = s.log_n - t.lo_bits;
@@ -95,7 +109,7 @@ static NttTableLayout ntt_table_layout(const NttShape &s) {
     unsigned log_O = 0;
     for (unsigned p = 0; p + 1 < s.passes; p++) {
         const unsigned size_log = s.log_n - log_O;
-        if (size_log <= ntt_direct_log()) t.off_direct[p] = add(1u << size_log, log_O);
+        if (size_log <= direct_log) t.off_direct[p] = add(1u << size_log, log_O);
         log_O += s.r[p];
     }
     t.words = off;
@@ -251,7 +265,7 @@ struct NttPassArgs {
 
 // pass p < P
 template <class P>
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const NttPassArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_CTAS) k_ntt_cols(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const NttPassArgs a) {
     using F = Fe<P>;
     extern __shared__ uint32_t sm[];
     const uint32_t N = 1u << a.r, C = 1u << a.logC, CP = C > 1 ? C + 1 : 1, LS = N * CP;
@@ -280,7 +294,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(const uint32_t *__rest
 
 // pass P (last): contiguous runs in, digit-reversed positions out
 template <class P>
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_last(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const NttPassArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_CTAS) k_ntt_last(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, const NttPassArgs a) {
     using F = Fe<P>;
     extern __shared__ uint32_t sm[];
     const uint32_t N = 1u << a.r, C = 1u << a.logC, CP = C > 1 ? C + 1 : 1, LS = N * CP;
@@ -478,6 +492,11 @@ static cudaError_t ntt_get_tables(const NttShape &shape, const void *omega_host,
         e->layout.words = e->layout.off_sa;
     }
     cudaError_t err = cudaMalloc((void **)&e->d_tab, e->layout.words * 4);
+    if (err == cudaErrorMemoryAllocation && kind == 0 && ntt_direct_log() > 20) {      // the big direct tables are an optimisation, not a requirement
+        cudaGetLastError();
+        e->layout = ntt_table_layout(shape, 20);
+        err = cudaMalloc((void **)&e->d_tab, e->layout.words * 4);
+    }
     if (err != cudaSuccess) { e->d_tab = nullptr; return err; }
     // e->omega lives as long as the cache entry, so the async copy's source stays valid
     err = cudaMemcpyAsync(e->d_tab, e->omega.data(), 32, cudaMemcpyHostToDevice, stream);
@@ -543,7 +562,7 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
     static bool attr_done[64] = {};
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
-    const size_t max_smem = (size_t)8 * (256 * 9) * 4;                 // r = 8, C = 8; shorter transforms with more columns stay below it
+    const size_t max_smem = (size_t)8 * (256 * ((1u << NTT_MIN_LOGC) + 1)) * 4;   // r = 8 with the fewest columns; shorter transforms with more columns stay below it
     if (dev < 64 && !attr_done[dev]) {
         PB_CUDA(cudaFuncSetAttribute(k_ntt_cols<Bn254Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         PB_CUDA(cudaFuncSetAttribute(k_ntt_last<Bn254Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -569,14 +588,14 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
             if (t.off_direct[p]) a.t_direct = tab->d_tab + t.off_direct[p];
             // C adjacent columns per CTA: at least 8 (256-byte runs), more for short transforms so that a tile holds 2048 elements
             // (one radix-8 unit per thread)
-            a.logC = std::min<unsigned>(a.log_M, std::max<unsigned>(3, 11 - std::min<unsigned>(a.r, 11)));
+            a.logC = std::min<unsigned>(a.log_M, std::max<unsigned>(NTT_MIN_LOGC, NTT_TILE_LOG - std::min<unsigned>(a.r, NTT_TILE_LOG)));
             const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
             const size_t smem = a.r > 3 ? (size_t)8 * ((size_t)(1u << a.r) * CP) * 4 : 0;   // a single stage group never touches smem
             const uint32_t blocks = batch << (log_O + a.log_M - a.logC);   // batch rows extend the outer index: (t * 2^log_O + o)
             k_ntt_cols<Bn254Fr><<<blocks, NTT_THREADS, smem, stream>>>(src, dst, a);
         } else {
             const unsigned r1 = shape.passes > 1 ? shape.r[0] : 0;
-            a.logC = std::min<unsigned>(r1, std::max<unsigned>(3, 11 - std::min<unsigned>(a.r, 11)));
+            a.logC = std::min<unsigned>(r1, std::max<unsigned>(NTT_MIN_LOGC, NTT_TILE_LOG - std::min<unsigned>(a.r, NTT_TILE_LOG)));
             if (inverse) a.scale = tab->d_tab + t.off_scale;
             const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
             const size_t smem = a.r > 3 ? (size_t)8 * ((size_t)(1u << a.r) * CP) * 4 : 0;

@@ -100,6 +100,14 @@ static panda_error msm_execute(pb::CurveId curve, const panda_msm_configuration 
     return perr(pb::msm_run(curve, cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, coord, cu(cfg.mem_pool), cu(cfg.stream)));
 }
 
+// One bucket class of a sharded MSM (msm.cuh): the Jacobian partial of the buckets congruent to class_index modulo class_count.
+static panda_error msm_execute_class(pb::CurveId curve, const panda_msm_configuration &cfg, size_t n, unsigned class_count, unsigned class_index) {
+    if (!cfg.results || (n && (!cfg.bases || !cfg.scalars))) return perr(cudaErrorInvalidValue);
+    if (n > (size_t)1 << 30) return perr(cudaErrorInvalidValue);
+    return perr(pb::msm_run(curve, cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, pb::COORD_JACOBIAN, cu(cfg.mem_pool), cu(cfg.stream), 0, 0, nullptr,
+                            pb::MSM_TABLE_DEFAULT, class_count, class_index));
+}
+
 // Host-pointer variant: stage through the device on cfg.stream, synchronous like the reference's CPU path.
 static panda_error msm_execute_host(pb::CurveId curve, const panda_msm_configuration &cfg) {
     if (!cfg.results || !cfg.bases || !cfg.scalars || cfg.log_scalars_count > 30) return perr(cudaErrorInvalidValue);   // before anything is queued
@@ -170,6 +178,15 @@ panda_error panda_msm_execute_bn254(const panda_msm_configuration cfg) {
     return msm_execute(pb::CURVE_BN254, cfg, (size_t)1 << cfg.log_scalars_count);
 }
 panda_error panda_msm_execute_bn254_n(const panda_msm_configuration cfg, size_t n) { return msm_execute(pb::CURVE_BN254, cfg, n); }
+panda_error panda_msm_execute_bn254_class(const panda_msm_configuration cfg, size_t n, unsigned class_count, unsigned class_index) {
+    return msm_execute_class(pb::CURVE_BN254, cfg, n, class_count, class_index);
+}
+panda_error panda_msm_execute_bls12_377_class(const panda_msm_configuration cfg, size_t n, unsigned class_count, unsigned class_index) {
+    return msm_execute_class(pb::CURVE_BLS12_377, cfg, n, class_count, class_index);
+}
+panda_error panda_msm_execute_bls12_381_class(const panda_msm_configuration cfg, size_t n, unsigned class_count, unsigned class_index) {
+    return msm_execute_class(pb::CURVE_BLS12_381, cfg, n, class_count, class_index);
+}
 panda_error panda_msm_execute_bn254_host(const panda_msm_configuration cfg) { return msm_execute_host(pb::CURVE_BN254, cfg); }
 panda_error panda_msm_execute_bls12_377_host(const panda_msm_configuration cfg) { return msm_execute_host(pb::CURVE_BLS12_377, cfg); }
 panda_error panda_msm_execute_bls12_377(const panda_msm_configuration cfg) {
@@ -298,6 +315,19 @@ panda_error panda_debug_msm_timed(int curve, const panda_msm_configuration cfg, 
     pb::CoordType coord = cfg.msm_result_coordinate_type == PROJECTIVE ? pb::COORD_PROJECTIVE : pb::COORD_JACOBIAN;
     cudaError_t e = pb::msm_run(pb::curve_from_id(curve), cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, coord,
                                 cu(cfg.mem_pool), cu(cfg.stream), c_override, seg_override, (stage_ms || info) ? &t : nullptr, table_mode);
+    if (stage_ms) {
+        stage_ms[0] = t.digits; stage_ms[1] = t.scan; stage_ms[2] = t.scatter; stage_ms[3] = t.accumulate;
+        stage_ms[4] = t.bucket_reduce; stage_ms[5] = t.window_reduce; stage_ms[6] = t.final;
+    }
+    if (info) { info[0] = (unsigned)t.folded; info[1] = t.c; info[2] = t.windows; }
+    return perr(e);
+}
+
+panda_error panda_debug_msm_timed_class(int curve, const panda_msm_configuration cfg, size_t n, unsigned class_count, unsigned class_index,
+                                        float *stage_ms, unsigned *info) {
+    pb::MsmStageTimes t{};
+    cudaError_t e = pb::msm_run(pb::curve_from_id(curve), cfg.bases, cfg.scalars, (uint32_t)n, cfg.results, pb::COORD_JACOBIAN,
+                                cu(cfg.mem_pool), cu(cfg.stream), 0, 0, (stage_ms || info) ? &t : nullptr, pb::MSM_TABLE_DEFAULT, class_count, class_index);
     if (stage_ms) {
         stage_ms[0] = t.digits; stage_ms[1] = t.scan; stage_ms[2] = t.scatter; stage_ms[3] = t.accumulate;
         stage_ms[4] = t.bucket_reduce; stage_ms[5] = t.window_reduce; stage_ms[6] = t.final;
