@@ -100,15 +100,34 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     // chunks (folded only): every chunk is a physical bucket set of its own (counts, sorted list, partial slots); the bucket
     // reduction merges the chunks of a logical set
     p.chunks = folded ? std::max<uint32_t>(1, std::min<uint32_t>(chunks, std::max<uint32_t>(1, n / 4096))) : 1;
-    // the first chunk is short (its upload is exposed), the others are four times as long (their upload hides behind the chunk before)
+    // Chunk sizes grow geometrically.  The first chunk is short (its upload is exposed); chunk q+1 is uploaded (0.58 us per 1000 scalars over
+    // PCIe 5) and sorted (0.26) while the chunks before it accumulate (1.78), so it can be as long as n_{q+1} <= 1.43 * (n_0 + .. + n_q) without
+    // leaving the integer pipe idle: sizes 1 : 1.43 : 3.5 : 8.4 : 20.5 (every chunk is (growth - 1) = 1.43 times the sum of its predecessors).
+    // PANDA_MSM_CHUNK_GROWTH overrides growth = 2.43.
+    p.chunk_begin[0] = 0;
     if (p.chunks > 1) {
-        p.chunk_first = std::max<uint32_t>(4, (n / (1 + 4 * (p.chunks - 1)) + 3) & ~3u);
-        p.chunk_n = ((n - p.chunk_first + (p.chunks - 1) - 1) / (p.chunks - 1) + 3) & ~3u;
-        p.chunks = 1 + (n - p.chunk_first + p.chunk_n - 1) / p.chunk_n;
+        static const double growth = [] { const char *e = getenv("PANDA_MSM_CHUNK_GROWTH"); const double v = e ? atof(e) : 0.0; return v >= 1.0 ? v : 2.43; }();
+        p.chunks = std::min<uint32_t>(p.chunks, MSM_MAX_CHUNKS);
+        double total = 0, wq = 1.0, acc = 0;
+        for (uint32_t q = 0; q < p.chunks; q++) { total += q == 0 ? 1.0 : wq; if (q == 0) wq = growth - 1.0; else wq *= growth; }
+        wq = 1.0;
+        uint32_t used = 0;
+        for (uint32_t q = 0; q < p.chunks; q++) {
+            acc += q == 0 ? 1.0 : wq;
+            if (q == 0) wq = growth - 1.0; else wq *= growth;
+            uint32_t end = q + 1 == p.chunks ? n : (uint32_t)std::min<double>((double)n, (double)n * acc / total);
+            end = std::min<uint32_t>(n, (end + 255) & ~255u);
+            if (end <= p.chunk_begin[used]) continue;              // (tiny jobs: empty chunks are dropped)
+            p.chunk_begin[++used] = end;
+            if (end == n) break;
+        }
+        p.chunks = used;
     } else {
-        p.chunk_first = p.chunk_n = n;
+        p.chunk_begin[1] = n;
     }
-    p.stride = folded ? std::max(p.chunk_first, p.chunk_n) * p.windows : n;
+    uint32_t max_chunk = 0;
+    for (uint32_t q = 0; q < p.chunks; q++) max_chunk = std::max(max_chunk, p.chunk_begin[q + 1] - p.chunk_begin[q]);
+    p.stride = folded ? max_chunk * p.windows : n;
     p.table_bytes = folded ? (size_t)n * p.windows * 2 * fq_bytes : 0;
     // segment length: about one average bucket, so that most buckets end up with one or two partial sums, but
     // never so long that the accumulation kernel has fewer than ~4 waves of threads (148 SMs x 384 threads)
@@ -131,14 +150,27 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     // at most one stitching CTA per SM over all sets (128 for one set): with 256 two of them share an SM and the latency-bound chains slow each other down
     // (measured at 2^24: 0.84 ms for 256 CTAs of 1024 chunk sums, against 0.42 ms for the single CTA of the next level)
     p.groups = std::min<uint32_t>(pow2_floor(std::max<uint32_t>(1, 148 / p.sets)), std::max<uint32_t>(1, p.chunks_ps / 1024));
-    // folded scatter passes: the slice of the sorted list written by one pass should stay in L2 (126 MB); measured on B200 at
-    // 2^24 (768 MiB list): 8 passes 4.1 ms, 16 passes 5.5 ms, 32 passes 8.3 ms, 1 pass 7.1 ms -- each pass re-reads the codes
+    // folded scatter ranges: the slice of the sorted list written for one bucket range should stay in L2 (126 MB) while its 4-byte writes land
+    // (<= 128 MiB, up to 32 ranges), and the scatter of range r+1 hides behind the accumulation of range r, so only the first range's scatter
+    // is exposed: slices of ~50 MiB, up to 16 ranges.  Measured at 2^24 (768 MiB list): 8 / 16 / 32 ranges 35.7 / 35.2 / 36.0 ms per MSM
+    // against 36.6 unpipelined; 2^22: 10.46 (1) / 10.42 (4) / 10.19 (8); 2^20: 3.47 (1) / 3.36 (4).  Lists below 8 MiB stay in one range
+    // (and so do bucket-class shards, whose scatter passes each recode all the scalars).
     p.phases = 1;
     if (folded) {
         static const uint32_t forced = [] { const char *e = getenv("PANDA_MSM_PHASES"); return e ? (uint32_t)atoi(e) : 0u; }();
-        while (p.phases < p.nb && (((uint64_t)p.stride * 4) >> class_log2) / p.phases > ((uint64_t)128 << 20)) p.phases *= 2;
+        const uint64_t list_bytes = ((uint64_t)p.stride * 4) >> class_log2;
+        while (!class_log2 && p.phases < 16 && p.phases < p.nb && list_bytes >= ((uint64_t)8 << 20) && list_bytes / p.phases > ((uint64_t)12 << 20)) p.phases *= 2;
+        while (p.phases < p.nb && list_bytes / p.phases > ((uint64_t)128 << 20)) p.phases *= 2;
         if (forced) p.phases = std::min<uint32_t>(pow2_floor(forced), p.nb);
+        if (!class_log2) {
+            // tile codes keep 18 bits of the bucket index (the rest is the range) and the tile headers one lane per range
+            p.phases = std::min<uint32_t>(p.phases, 32);
+            while ((p.nb / p.phases) > (1u << 18)) p.phases *= 2;
+        }
     }
+    const uint32_t chunk_tiles = (max_chunk + 255) / 256;
+    p.codes_stride = folded && !class_log2 ? chunk_tiles * 256 * p.windows : 0;
+    p.heads_stride = folded && !class_log2 ? chunk_tiles * (p.phases + 1) : 0;
 
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
@@ -148,7 +180,8 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.off_cursor = off;  off = align(off + phys * p.nb * 4);
     p.off_biglist = off; off = align(off + phys * p.nb * 4);
     p.off_tiles = off;   off = align(off + phys * ((p.nb + 4095) / 4096) * 4);
-    p.off_digits = off;  off = align(off + (class_log2 ? 0 : folded ? (size_t)p.chunks * p.stride * 4 : (size_t)p.windows * n * 2));   // class shards recode the scalars in both passes
+    p.off_digits = off;  off = align(off + (class_log2 ? 0 : folded ? (size_t)p.chunks * p.codes_stride * 4 : (size_t)p.windows * n * 2));   // class shards recode the scalars in both passes
+    p.off_heads = off;   off = align(off + (size_t)p.chunks * p.heads_stride * 2);
     p.off_sorted = off;  off = align(off + phys * p.stride * 4);
     p.off_slots = off;   off = align(off + phys * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);
     p.off_chunks = off;  off = align(off + (size_t)p.sets * p.chunks_ps * 2 * 4 * fq_bytes);
@@ -377,6 +410,7 @@ static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, c
 }
 
 static cudaError_t aux_stream_for_current_device(cudaStream_t *out);
+static cudaError_t aux2_stream_for_current_device(cudaStream_t *out);
 static uint32_t resident_chunks(uint32_t n);
 
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
@@ -403,9 +437,18 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
         p.table_n = table_n;
         p.class_index = class_index;
         if (p.chunks > 1) {
-            MsmFeed feed{nullptr, nullptr, nullptr, nullptr};
+            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr};
             PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
+            PB_CUDA(aux2_stream_for_current_device(&feed.aux2_stream));
             return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, nullptr, &feed);
+        }
+        // one chunk, several scatter ranges: range r+1 is scattered while range r is accumulated (PANDA_MSM_PIPELINE=0: one launch each)
+        static const bool pipeline_on = [] { const char *v = getenv("PANDA_MSM_PIPELINE"); return !v || atoi(v) != 0; }();
+        if (pipeline_on && p.phases > 1 && !class_log2) {
+            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr};
+            PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
+            PB_CUDA(aux2_stream_for_current_device(&feed.aux2_stream));
+            return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings, &feed);
         }
         return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings);
     }
@@ -415,10 +458,11 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
     return run_pipeline(curve, p, bases, scalars, result, coord, pool, stream, timings);
 }
 
-// per device: one copy stream (streamed scalars) and one auxiliary compute stream (chunk overlap), created on first use
+// per device: one copy stream (streamed scalars), one high-priority auxiliary compute stream (chunk / range overlap) and one more at the
+// caller's priority, created on first use
 static cudaError_t side_stream_for_current_device(int which, cudaStream_t *out) {
     static std::mutex m;
-    static cudaStream_t streams[2][64] = {};
+    static cudaStream_t streams[3][64] = {};
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
@@ -433,6 +477,7 @@ static cudaError_t side_stream_for_current_device(int which, cudaStream_t *out) 
 }
 static cudaError_t copy_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(0, out); }
 static cudaError_t aux_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(1, out); }
+static cudaError_t aux2_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(2, out); }   // second accumulation stream of the pipelined plan
 
 // chunks of a device-resident table-plan MSM: chunk q+1 sorts on the higher-priority auxiliary stream while chunk q accumulates, and every chunk's
 // scatter passes re-read only its own codes.  Measured (profiles/r2_sweep.md, product entry point): 2^24 38.4 vs 37.6 ms and 2^25 74.3 vs 73.6 ms
@@ -462,12 +507,13 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
     cudaError_t e;
     if (table) {
         static const uint32_t forced = [] { const char *v = getenv("PANDA_MSM_CHUNKS"); return v ? (uint32_t)atoi(v) : 0u; }();
-        uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 23) ? 3 : n >= (1u << 19) ? 2 : 1);
+        uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 23) ? 5 : n >= (1u << 21) ? 4 : n >= (1u << 19) ? 3 : 1);
         MsmPlan p = msm_make_plan(curve, n, true, tc, 0, ~(size_t)0, chunks);
         p.table_n = table_n;
-        MsmFeed feed{host_scalars, d_scal, nullptr, nullptr};
+        MsmFeed feed{host_scalars, d_scal, nullptr, nullptr, nullptr};
         e = copy_stream_for_current_device(&feed.copy_stream);
         if (e == cudaSuccess) e = aux_stream_for_current_device(&feed.aux_stream);
+        if (e == cudaSuccess) e = aux2_stream_for_current_device(&feed.aux2_stream);
         if (e == cudaSuccess) e = run_pipeline(curve, p, table, d_scal, result, coord, pool, stream, nullptr, &feed);
     } else {
         e = cudaMemcpyAsync(d_scal, host_scalars, (size_t)n * 32, cudaMemcpyHostToDevice, stream);

@@ -17,6 +17,8 @@ inline uint32_t curve_scalar_bits(CurveId c) { return c == CURVE_BLS12_377 ? 253
 inline CurveId curve_from_id(int id) { return id == 1 ? CURVE_BLS12_377 : id == 2 ? CURVE_BLS12_381 : CURVE_BN254; }
 enum CoordType { COORD_JACOBIAN = 0, COORD_PROJECTIVE = 1 };   // curve.cuh:23-27
 
+static constexpr uint32_t MSM_MAX_CHUNKS = 8;
+
 struct MsmPlan {
     uint32_t n;            // points
     uint32_t table_n;      // folded: row length of the table (>= n: an MSM may use a prefix of a registered base set)
@@ -34,13 +36,15 @@ struct MsmPlan {
     uint32_t groups;       // CTAs per set in the group-reduce stage (<= 256, divides chunks_ps)
     uint32_t chunks;       // Q: point-range chunks that are sorted and accumulated separately and share the bucket reduction
                            //    (Q > 1 only for streamed scalars: chunk q computes while chunk q+1 is still being uploaded)
-    uint32_t chunk_first;  // points in chunk 0
-    uint32_t chunk_n;      // points in every later chunk (the last one may be shorter)
-    uint32_t phases;       // folded scatter: passes over the codes, one bucket range each (L2-resident output slice)
+    uint32_t chunk_begin[MSM_MAX_CHUNKS + 1];   // chunk q covers points [chunk_begin[q], chunk_begin[q + 1]): sizes grow geometrically
+    uint32_t phases;       // folded scatter: bucket ranges (a power of two <= 32, each at most 2^18 buckets): the codes are grouped by range tile by tile
+                           //    and scattered one range at a time (L2-resident output slice; pipelined with the accumulation of the range before)
+    uint32_t codes_stride; // folded: code capacity per chunk (whole 256-scalar tiles of W codes)
+    uint32_t heads_stride; // folded: u16 header entries per chunk (tiles * (phases + 1))
     uint32_t class_log2;   // bucket-class shard (multi-GPU): this run only takes the digits whose bucket index is congruent to class_index
     uint32_t class_index;  //    modulo 2^class_log2; nb counts the buckets of that class.  0 / 0: the whole MSM
     // workspace layout (byte offsets into one arena)
-    size_t off_counts, off_offsets, off_cursor, off_biglist, off_tiles, off_digits, off_sorted, off_slots, off_chunks, off_gsums, bytes;
+    size_t off_counts, off_offsets, off_cursor, off_biglist, off_tiles, off_digits, off_heads, off_sorted, off_slots, off_chunks, off_gsums, bytes;
     size_t table_bytes;    // folded: size of the precomputed table (W * n affine points)
 };
 
@@ -50,7 +54,9 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
 
 // How a chunked pipeline is fed: host_scalars != nullptr: chunk q is uploaded on copy_stream right before its kernels are queued;
 // aux_stream != nullptr: odd chunks run on it, so that one chunk's sort overlaps the previous chunk's accumulation.
-struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; cudaStream_t aux_stream; };
+// aux2_stream (with aux_stream, one resident chunk, several scatter ranges): the scatter of bucket range r+1 runs on aux_stream while range r
+// is accumulated; the accumulation launches alternate between the caller's stream and aux2_stream.
+struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; cudaStream_t aux_stream; cudaStream_t aux2_stream; };
 
 // Per-stage device timings (ms) filled when msm_run is called with timings != nullptr (adds event syncs;
 // the benchmark harness uses it to attribute time to kernels -- never set on the product path).

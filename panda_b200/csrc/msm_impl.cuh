@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <type_traits>
+#include <vector>
 
 namespace pb {
 
@@ -201,47 +202,103 @@ static __global__ void __launch_bounds__(256) k_scatter(const uint16_t *__restri
     }
 }
 
-// K3 (folded): one bucket set of up to 2^22 buckets; the sorted list (4*W*n bytes) is far larger than L2, so the scatter
-// runs in `phases` passes over the codes (blockIdx.y = phase): pass p only places the entries of bucket range p, whose
-// slice of the sorted list (<= 128 MiB) stays in L2 while its 4-byte writes land, and reaches HBM as full lines.
-// entry = table index w*n + i = the code's own position.
-static __global__ void __launch_bounds__(256) k_scatter_folded(const uint32_t *__restrict__ codes, uint32_t nq, uint32_t W, uint32_t n_total,
-                                                               uint32_t point0, uint32_t log2_span, uint32_t *__restrict__ cursor,
-                                                               uint32_t *__restrict__ sorted) {
-    // codes[w * nq + i] belongs to point point0 + i (a chunk of the job); its table entry is w * n_total + point0 + i
-    const uint32_t phase = blockIdx.y;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    for (uint32_t w = 0; w < W; w++) {
-        const uint32_t *cw = codes + (size_t)w * nq;
-        const uint32_t entry0 = w * n_total + point0;
-        auto place = [&](uint32_t code, uint32_t i) {
-            if (code == CODE_SKIP32) return;
-            const uint32_t b = code & 0x7FFFFFFFu;
-            if ((b >> log2_span) != phase) return;
-            const uint32_t pos = atomicAdd(&cursor[b], 1u);
-            sorted[pos] = (entry0 + i) | (code & 0x80000000u);
-        };
-        if ((nq & 3u) == 0) {
-            const uint4 *c4 = reinterpret_cast<const uint4 *>(cw);
-            const uint32_t nv = nq / 4;
-            uint32_t q = tid;
-            // four independent 16-byte loads in flight per thread: a pass is a stream of the codes with a returning atomic and a
-            // dependent store on one code in `phases`, so it is bound by memory latency, not by bandwidth
-            for (; q + 3 * nthreads < nv; q += 4 * nthreads) {
-                const uint4 v0 = __ldg(c4 + q), v1 = __ldg(c4 + q + nthreads), v2 = __ldg(c4 + q + 2 * nthreads), v3 = __ldg(c4 + q + 3 * nthreads);
-                place(v0.x, 4 * q); place(v0.y, 4 * q + 1); place(v0.z, 4 * q + 2); place(v0.w, 4 * q + 3);
-                const uint32_t q1 = q + nthreads, q2 = q + 2 * nthreads, q3 = q + 3 * nthreads;
-                place(v1.x, 4 * q1); place(v1.y, 4 * q1 + 1); place(v1.z, 4 * q1 + 2); place(v1.w, 4 * q1 + 3);
-                place(v2.x, 4 * q2); place(v2.y, 4 * q2 + 1); place(v2.z, 4 * q2 + 2); place(v2.w, 4 * q2 + 3);
-                place(v3.x, 4 * q3); place(v3.y, 4 * q3 + 1); place(v3.z, 4 * q3 + 2); place(v3.w, 4 * q3 + 3);
-            }
-            for (; q < nv; q += nthreads) {
-                const uint4 v = __ldg(c4 + q);
-                place(v.x, 4 * q); place(v.y, 4 * q + 1); place(v.z, 4 * q + 2); place(v.w, 4 * q + 3);
-            }
-        } else {
-            for (uint32_t q = tid; q < nq; q += nthreads) place(__ldg(cw + q), q);
+// K1 / K3 of the table plan (one bucket set, `ranges` bucket ranges of 2^log2_span buckets).  The scatter used to be a filter: every range pass
+// read ALL codes and kept one in `ranges` -- 8 x 201 M code inspections at 2^24, which cost the overlapped accumulation kernel 3-12 % of its issue
+// slots once the two were pipelined.  Now K1 writes the codes of each 256-scalar tile already GROUPED BY RANGE (a counting sort of at most
+// 256 * W codes in shared memory, no atomics: per-thread counts in a conflict-free [range][thread] matrix, one row scan per range), with the
+// group boundaries in a small header, so the scatter of range r reads exactly its own codes: contiguous slices, every code a hit.
+//   code = sign << 31 | (w * 256 + scalar's index in the tile) << 18 | (bucket & (2^log2_span - 1)),  log2_span <= 18, W <= 32
+static constexpr uint32_t TILE_PTS = 256;
+static constexpr uint32_t TILE_ID_SHIFT = 18;
+template <class C>
+__global__ void __launch_bounds__(TILE_PTS) k_digits_tiled(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide,
+                                                           uint32_t log2_span, uint32_t ranges, uint32_t *__restrict__ codes,
+                                                           uint16_t *__restrict__ heads, uint32_t *__restrict__ counts) {
+    using Fr = typename C::Fr;
+    extern __shared__ __align__(16) uint32_t sh_dyn[];
+    uint32_t *cnt = sh_dyn;                               // [ranges][256]: bank = thread index, so every access is conflict-free
+    uint32_t *base = cnt + ranges * TILE_PTS;             // [ranges + 1]
+    uint32_t *out = base + 40;                            // [256 * W]
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t span_mask = (1u << log2_span) - 1;
+    const uint32_t tiles = (n + TILE_PTS - 1) / TILE_PTS;
+    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t i = tile * TILE_PTS + tid;
+        for (uint32_t r = 0; r < ranges; r++) cnt[r * TILE_PTS + tid] = 0;
+        Fr s = Fr::zero();
+        if (i < n) s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; the input is left untouched (zero: no digits)
+        for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t mag, uint32_t neg) {
+            const uint32_t b = mag - 1;
+            atomicAdd(&counts[b], 1u);
+            cnt[(b >> log2_span) * TILE_PTS + tid]++;
+        });
+        __syncthreads();
+        // exclusive scan of every range's row over the 256 threads: a warp per row, 8 cells per lane
+        for (uint32_t r = warp; r < ranges; r += TILE_PTS / 32) {
+            uint4 *row = reinterpret_cast<uint4 *>(cnt + r * TILE_PTS) + lane * 2;
+            uint4 a = row[0], b4 = row[1];
+            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+            uint32_t sum = 0, ex[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { ex[k] = sum; sum += v[k]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            const uint32_t pre = incl - sum;
+            row[0] = make_uint4(ex[0] + pre, ex[1] + pre, ex[2] + pre, ex[3] + pre);
+            row[1] = make_uint4(ex[4] + pre, ex[5] + pre, ex[6] + pre, ex[7] + pre);
+            if (lane == 31) base[r + 1] = incl;           // the row's total for now
         }
+        __syncthreads();
+        if (warp == 0) {                                   // range starts within the tile (ranges <= 32)
+            const uint32_t v = lane < ranges ? base[lane + 1] : 0;
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            if (lane < ranges) base[lane + 1] = incl;
+            if (lane == 0) base[0] = 0;
+        }
+        __syncthreads();
+        for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t mag, uint32_t neg) {
+            const uint32_t b = mag - 1, r = b >> log2_span;
+            const uint32_t pos = base[r] + cnt[r * TILE_PTS + tid]++;
+            out[pos] = (neg << 31) | ((w * TILE_PTS + tid) << TILE_ID_SHIFT) | (b & span_mask);
+        });
+        __syncthreads();
+        const uint32_t total = base[ranges];
+        uint32_t *dst = codes + (size_t)tile * TILE_PTS * W;
+        for (uint32_t k = tid; k < total; k += TILE_PTS) dst[k] = out[k];
+        if (tid <= ranges) heads[(size_t)tile * (ranges + 1) + tid] = (uint16_t)base[tid];
+        __syncthreads();
+    }
+}
+
+// K3 (table plan): bucket range(s) first_range + blockIdx.y; a warp per tile walks the tile's slice for the range -- every code is placed.
+static __global__ void __launch_bounds__(256) k_scatter_tiled(const uint32_t *__restrict__ codes, const uint16_t *__restrict__ heads, uint32_t nq, uint32_t W,
+                                                              uint32_t n_total, uint32_t point0, uint32_t log2_span, uint32_t ranges, uint32_t first_range,
+                                                              uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+    const uint32_t r = first_range + blockIdx.y;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t tiles = (nq + TILE_PTS - 1) / TILE_PTS;
+    const uint32_t span_mask = (1u << log2_span) - 1, bucket0 = r << log2_span;
+    for (uint32_t tile = warp_g; tile < tiles; tile += nwarps) {
+        const uint16_t *h = heads + (size_t)tile * (ranges + 1) + r;
+        const uint32_t h0 = h[0], h1 = h[1];
+        const uint32_t *src = codes + (size_t)tile * TILE_PTS * W;
+        const uint32_t entry0 = point0 + tile * TILE_PTS;
+        auto place = [&](uint32_t code) {
+            const uint32_t id = (code >> TILE_ID_SHIFT) & 0x1FFFu;
+            const uint32_t entry = (id >> 8) * n_total + entry0 + (id & 255u);
+            const uint32_t pos = atomicAdd(&cursor[bucket0 | (code & span_mask)], 1u);
+            sorted[pos] = entry | (code & 0x80000000u);
+        };
+        uint32_t k = h0 + lane;
+        for (; k + 96 < h1; k += 128) {                    // four independent returning atomics in flight per lane
+            const uint32_t c0 = __ldg(src + k), c1 = __ldg(src + k + 32), c2 = __ldg(src + k + 64), c3 = __ldg(src + k + 96);
+            place(c0); place(c1); place(c2); place(c3);
+        }
+        for (; k < h1; k += 32) place(__ldg(src + k));
     }
 }
 
@@ -275,24 +332,12 @@ __global__ void __launch_bounds__(256) k_class_pass(const uint32_t *__restrict__
 // (s + bucket), which is unique and makes a bucket's partials contiguous.
 // IMAD-bound: 8 products + 2 squares = 1314 IMAD-class instructions per entry (8 limbs); 4 B index + 64 B (96 B) gathered point per entry.
 template <class C>
-PB_DEV void accumulate_body(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
-                            const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
-                            uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
+PB_DEV void accumulate_segment(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sw, const uint32_t *__restrict__ ow,
+                               uint32_t b_lo, uint32_t b_hi, uint32_t start, uint32_t end, uint8_t *__restrict__ slot_s) {
     using Fq = typename C::Fq;
     using Pt = Xyzz<Fq>;
     using Af = Affine<Fq>;
-    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (uint64_t)W * segs_pw) return;
-    const uint32_t w = (uint32_t)(gid / segs_pw), s = (uint32_t)(gid % segs_pw);
-    const uint32_t *ow = offsets + (size_t)w * (nb + 1);
-    const uint32_t cnt = __ldg(ow + nb);
-    const uint32_t start = s * L;
-    if (start >= cnt) return;
-    const uint32_t end = min(start + L, cnt);
-    const uint32_t *sw = sorted + (size_t)w * stride;
-    uint8_t *slot_w = slots + ((size_t)w * ((size_t)segs_pw + nb) + s) * Pt::BYTES;
-
-    uint32_t lo = 0, hi = nb;          // largest b with offsets[b] <= start
+    uint32_t lo = b_lo, hi = b_hi;     // largest b in [b_lo, b_hi) with offsets[b] <= start
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (__ldg(ow + mid) <= start) lo = mid; else hi = mid;
@@ -312,7 +357,7 @@ PB_DEV void accumulate_body(const uint8_t *__restrict__ bases, const uint32_t *_
             p_next = Af::load_gather(bases + (size_t)(e_next & 0x7FFFFFFFu) * Af::BYTES);
         }
         if (pos >= next_bd) {          // bucket boundary: emit the finished partial, skip empty buckets
-            acc.store(slot_w + (size_t)b * Pt::BYTES);
+            acc.store(slot_s + (size_t)b * Pt::BYTES);
             acc = Pt::identity();
             do { b++; next_bd = __ldg(ow + b + 1); } while (pos >= next_bd);
         }
@@ -320,7 +365,44 @@ PB_DEV void accumulate_body(const uint8_t *__restrict__ bases, const uint32_t *_
         if (e >> 31) p.y = p.y.neg();
         acc.madd(p.x, p.y);
     }
-    acc.store(slot_w + (size_t)b * Pt::BYTES);
+    acc.store(slot_s + (size_t)b * Pt::BYTES);
+}
+
+template <class C>
+PB_DEV void accumulate_body(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                            const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
+                            uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
+    using Pt = Xyzz<typename C::Fq>;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (uint64_t)W * segs_pw) return;
+    const uint32_t w = (uint32_t)(gid / segs_pw), s = (uint32_t)(gid % segs_pw);
+    const uint32_t *ow = offsets + (size_t)w * (nb + 1);
+    const uint32_t cnt = __ldg(ow + nb);
+    const uint32_t start = s * L;
+    if (start >= cnt) return;
+    accumulate_segment<C>(bases, sorted + (size_t)w * stride, ow, 0, nb, start, min(start + L, cnt),
+                          slots + ((size_t)w * ((size_t)segs_pw + nb) + s) * Pt::BYTES);
+}
+
+// K4, one bucket range of a single (folded) bucket set at a time -- the pipelined driver scatters range r+1 (L2-atomic bound, few
+// registers, higher-priority stream) while range r is being accumulated (integer-pipe bound).  Range [b_lo, b_hi) owns the segments whose
+// LAST entry lies in it (a segment that straddles a range boundary waits for the later range); grid-stride, so the grid is only a hint.
+template <class C>
+PB_DEV void accumulate_range_body(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ offsets,
+                                  uint32_t nb, uint32_t L, uint32_t segs_ps, uint32_t b_lo, uint32_t b_hi, uint8_t *__restrict__ slots) {
+    using Pt = Xyzz<typename C::Fq>;
+    const uint32_t cnt = __ldg(offsets + nb);
+    const uint32_t lo = __ldg(offsets + b_lo), hi = __ldg(offsets + b_hi);
+    // a straddling segment starts in an earlier range: widen the bucket search downwards for it (b_lo_search = 0 costs ~3 more probes)
+#pragma unroll 1
+    for (uint64_t s = (uint64_t)(lo / L) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < segs_ps; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t start = (uint32_t)s * L;
+        if (start >= cnt) break;
+        const uint32_t end = min(start + L, cnt);
+        if (end > hi) break;
+        if (end <= lo) continue;
+        accumulate_segment<C>(bases, sorted, offsets, start >= lo ? b_lo : 0, b_hi, start, end, slots + (size_t)s * Pt::BYTES);
+    }
 }
 
 template <class C>
@@ -335,6 +417,19 @@ __global__ void __launch_bounds__(64, 5) k_accumulate_wide(const uint8_t *__rest
                                                           const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
                                                           uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
     accumulate_body<C>(bases, sorted, offsets, stride, nb, L, segs_pw, W, slots);
+}
+
+template <class C>
+__global__ void __maxnreg__(136) k_accumulate_range(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                                                                 const uint32_t *__restrict__ offsets, uint32_t nb, uint32_t L, uint32_t segs_ps,
+                                                                 uint32_t b_lo, uint32_t b_hi, uint8_t *__restrict__ slots) {
+    accumulate_range_body<C>(bases, sorted, offsets, nb, L, segs_ps, b_lo, b_hi, slots);
+}
+template <class C>
+__global__ void __launch_bounds__(64, 5) k_accumulate_range_wide(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                                                                const uint32_t *__restrict__ offsets, uint32_t nb, uint32_t L, uint32_t segs_ps,
+                                                                uint32_t b_lo, uint32_t b_hi, uint8_t *__restrict__ slots) {
+    accumulate_range_body<C>(bases, sorted, offsets, nb, L, segs_ps, b_lo, b_hi, slots);
 }
 
 template <class F>
@@ -727,6 +822,29 @@ struct StageTimer {
     float ms(int i) { float t = 0; cudaEventElapsedTime(&t, ev[i], ev[i + 1]); return t; }
 };
 
+// PANDA_MSM_TRACE=1: timeline of a chunked / pipelined run (events on every stream involved, printed relative to the start of the call; the
+// call then synchronises -- a diagnostic, never set on a measured path)
+struct TraceLog {
+    struct Mark { const char *what; uint32_t q; cudaEvent_t ev; };
+    std::vector<Mark> marks;
+    bool on;
+    TraceLog() { static const bool enabled = [] { const char *e = getenv("PANDA_MSM_TRACE"); return e && atoi(e) != 0; }(); on = enabled; }
+    void mark(const char *what, uint32_t q, cudaStream_t s) {
+        if (!on) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, s);
+        marks.push_back({what, q, ev});
+    }
+    void report(cudaStream_t s) {
+        if (!on || marks.empty()) return;
+        cudaStreamSynchronize(s);
+        for (auto &m : marks) { cudaEventSynchronize(m.ev); float t = 0; cudaEventElapsedTime(&t, marks[0].ev, m.ev); fprintf(stderr, "[trace] %-14s %u  %8.3f ms\n", m.what, m.q, t); }
+        for (auto &m : marks) cudaEventDestroy(m.ev);
+        marks.clear();
+    }
+};
+
 // Runs the pipeline described by `p`.  `points` is the caller's bases (windowed) or the precomputed table (folded).
 // feed != nullptr: chunked run.  With feed->host_scalars the scalars are still in host memory and chunk q is uploaded on
 // feed->copy_stream right before chunk q's kernels are queued (the upload of chunk q+1 overlaps the work on chunk q); with
@@ -750,81 +868,141 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
     const size_t slot_stride = ((size_t)p.segs_ps + p.nb) * Pt::BYTES;       // per physical set
 
     StageTimer tm(timings != nullptr && p.chunks == 1, stream);
-    // events: `fed` orders the copy stream against the compute streams; `sorted_ev` staggers the chunks (chunk q+1 starts sorting when
-    // chunk q starts accumulating, on the other stream, so that its atomics-bound sort hides behind integer-bound additions);
-    // `aux_done` joins the auxiliary stream back into `stream`
+    TraceLog trace;
+    trace.mark("start", 0, stream);
+    // Streams by role.  Several chunks: every chunk's sort (digits, scan, scatter -- L2-atomic bound) runs on the high-priority stream `aux` as soon
+    // as its scalars are there, the accumulations (integer-pipe bound) alternate between the caller's stream and `aux2`, so that one chunk's tail
+    // overlaps the next one's head and a sort never queues behind an accumulation.  One resident chunk with several scatter ranges: the same
+    // roles range by range (`pipelined`).
+    // events: `fed` orders the copy stream and the side streams against `stream`; `sorted_ev` hands a sorted chunk / range to its accumulation;
+    // `aux_done` joins `aux2` back into `stream`
     cudaEvent_t fed = nullptr, sorted_ev = nullptr, aux_done = nullptr;
     const bool uploading = feed && feed->host_scalars;
-    cudaStream_t aux = (feed && p.chunks > 1) ? feed->aux_stream : nullptr;
+    cudaStream_t aux = (feed && p.chunks > 1 && feed->aux_stream && feed->aux2_stream) ? feed->aux_stream : nullptr;
+    cudaStream_t aux2 = aux ? feed->aux2_stream : nullptr;
+    // one resident chunk, several scatter ranges: scatter and accumulation are pipelined range by range over two side streams
+    cudaStream_t pipe = nullptr, pipe2 = nullptr;
+    if (feed && p.chunks == 1 && p.folded && !p.class_log2 && p.phases > 1 && !uploading) { pipe = feed->aux_stream; pipe2 = feed->aux2_stream; }
+    const bool pipelined = pipe && pipe2;
     cudaError_t err = cudaSuccess;
     do {
         if ((err = cudaMemsetAsync(counts, 0, (phys * p.nb + p.chunks) * 4, stream)) != cudaSuccess) break;
-        if (uploading || aux) {
+        if (pipelined || uploading || aux) {
             if ((err = cudaEventCreateWithFlags(&fed, cudaEventDisableTiming)) != cudaSuccess) break;
+            if ((err = cudaEventCreateWithFlags(&sorted_ev, cudaEventDisableTiming)) != cudaSuccess) break;
+            if ((err = cudaEventCreateWithFlags(&aux_done, cudaEventDisableTiming)) != cudaSuccess) break;
+        }
+        if (uploading || aux) {
             // the workspace / staging buffer were allocated in stream order on `stream`: other streams may only touch them from here on
             if ((err = cudaEventRecord(fed, stream)) != cudaSuccess) break;
             if (uploading && (err = cudaStreamWaitEvent(feed->copy_stream, fed, 0)) != cudaSuccess) break;
             if (aux && (err = cudaStreamWaitEvent(aux, fed, 0)) != cudaSuccess) break;
-        }
-        if (aux) {
-            if ((err = cudaEventCreateWithFlags(&sorted_ev, cudaEventDisableTiming)) != cudaSuccess) break;
-            if ((err = cudaEventCreateWithFlags(&aux_done, cudaEventDisableTiming)) != cudaSuccess) break;
+            if (aux2 && (err = cudaStreamWaitEvent(aux2, fed, 0)) != cudaSuccess) break;
         }
         for (uint32_t q = 0; q < p.chunks && err == cudaSuccess; q++) {
-            cudaStream_t sq = (aux && (q & 1)) ? aux : stream;               // chunks alternate between the two streams
-            const uint32_t point0 = q == 0 ? 0 : p.chunk_first + (q - 1) * p.chunk_n;
-            const uint32_t nq = q == 0 ? p.chunk_first : std::min<uint32_t>(p.chunk_n, n - point0);
+            cudaStream_t sq = aux ? aux : stream;                             // this chunk's sort ...
+            cudaStream_t sa = aux ? ((q & 1) ? aux2 : stream) : stream;       // ... and its accumulation
+            const uint32_t point0 = p.chunk_begin[q], nq = p.chunk_begin[q + 1] - point0;
             const size_t set0 = (size_t)q * p.sets;                           // first physical set of this chunk
             const uint32_t *sc = (const uint32_t *)scalars + (size_t)point0 * 8;
             if (uploading) {
                 if ((err = cudaMemcpyAsync((uint8_t *)feed->dev_scalars + (size_t)point0 * 32, (const uint8_t *)feed->host_scalars + (size_t)point0 * 32,
                                            (size_t)nq * 32, cudaMemcpyHostToDevice, feed->copy_stream)) != cudaSuccess) break;
                 if ((err = cudaEventRecord(fed, feed->copy_stream)) != cudaSuccess) break;
+                trace.mark("uploaded", q, feed->copy_stream);
                 if ((err = cudaStreamWaitEvent(sq, fed, 0)) != cudaSuccess) break;
             }
-            if (aux && q > 0 && (err = cudaStreamWaitEvent(sq, sorted_ev, 0)) != cudaSuccess) break;   // previous chunk is sorted
             uint32_t *counts_q = counts + set0 * p.nb, *offsets_q = offsets + set0 * (p.nb + 1), *cursor_q = cursor + set0 * p.nb;
             uint32_t *big_count_q = big_counts + q, *big_list_q = big_list + set0 * p.nb, *tiles_q = tile_sums + set0 * tiles_ps;
-            uint8_t *codes_q = digits + (size_t)q * p.stride * 4;            // folded: 32-bit codes of this chunk (chunks == 1 otherwise)
+            uint8_t *codes_q = digits + (size_t)q * p.codes_stride * 4;      // folded: 32-bit codes of this chunk, tile by tile (chunks == 1 otherwise)
+            uint16_t *heads_q = (uint16_t *)(ws + p.off_heads) + (size_t)q * p.heads_stride;
+            uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;        // table plan: buckets per scatter range
+            // kernels that run beside an accumulation (every chunk but the first; every scatter range but the first) get small grids: their
+            // warps mostly wait for L2 atomics, and each CTA that becomes resident displaces accumulation warps that would keep the integer pipe
+            // busy.  Too few, and the sort of the next chunk is late (a CTA beside three accumulation CTAs gets a small share of the issue
+            // slots).  Measured at 2^24 (profiles/r2_e2e_pipeline.md): scatter 2 CTAs per SM, digits 4; the range pipeline's scatters 1.
+            static const uint32_t side_ctas = [] { const char *e = getenv("PANDA_MSM_SIDE_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 296u; }();
+            static const uint32_t side_digit_ctas = [] { const char *e = getenv("PANDA_MSM_SIDE_DIGITS"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 592u; }();
+            const uint32_t cta_cap = (aux && q > 0) ? side_ctas : 148 * 8;
+            const uint32_t digit_cap = (aux && q > 0) ? side_digit_ctas : 148 * 8;
+            const uint32_t scat_blocks = std::min<uint32_t>(((nq + TILE_PTS - 1) / TILE_PTS + 7) / 8, cta_cap);
             uint32_t *sorted_q = sorted + set0 * p.stride;
             uint8_t *slots_q = slots + set0 * slot_stride;
             tm.mark();
-            const uint32_t sblocks = std::min<uint32_t>((nq + 255) / 256, 148 * 8);
+            trace.mark("sort begins", q, sq);
+            const uint32_t sblocks = std::min<uint32_t>((nq + 255) / 256, cta_cap);
             if (p.class_log2) {
                 if (p.folded) k_class_pass<C, true, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, p.table_n, point0, p.stride, 0, counts_q, nullptr);
                 else k_class_pass<C, false, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, nq, 0, p.stride, 0, counts_q, nullptr);
-            } else if (p.folded) k_digits<C, true><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, codes_q, counts_q);
+            } else if (p.folded) {
+                const size_t sh_bytes = ((size_t)p.phases * TILE_PTS + 40 + (size_t)TILE_PTS * p.windows) * 4;
+                if (sh_bytes > 48 * 1024 && (err = cudaFuncSetAttribute(k_digits_tiled<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes)) != cudaSuccess) break;
+                const uint32_t tblocks = std::min<uint32_t>((nq + TILE_PTS - 1) / TILE_PTS, digit_cap);
+                k_digits_tiled<C><<<tblocks, TILE_PTS, sh_bytes, sq>>>(sc, nq, p.c, p.windows, p.wide, log2_span, p.phases, (uint32_t *)codes_q, heads_q, counts_q);
+            }
             else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, codes_q, counts_q);
             tm.mark();
+            trace.mark("digits done", q, sq);
             k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, p.nb, tiles_ps, tiles_q);
             k_scan_tops<<<p.sets, 1024, 0, sq>>>(tiles_q, tiles_ps, p.nb, offsets_q);
             k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q, big_count_q, big_list_q);
             tm.mark();
+            trace.mark("scanned", q, sq);
             if (p.class_log2) {
                 uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
                 if (p.folded) k_class_pass<C, true, true><<<dim3(sblocks, p.phases), 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, p.table_n, point0, p.stride, log2_span, cursor_q, sorted_q);
                 else k_class_pass<C, false, true><<<dim3(sblocks, 1), 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, nq, 0, p.stride, 31, cursor_q, sorted_q);
+            } else if (pipelined) {
+                // bucket range r is scattered on the high-priority stream `pipe` while the ranges before it are being accumulated; the accumulation
+                // launches alternate between `sq` and `pipe2` so that the tail of one overlaps the head of the next (they are independent)
+                const uint32_t span = 1u << log2_span, ranges = p.phases;
+                if ((err = cudaEventRecord(fed, sq)) != cudaSuccess) break;                    // scan done (and workspace allocated)
+                if ((err = cudaStreamWaitEvent(pipe, fed, 0)) != cudaSuccess) break;
+                if ((err = cudaStreamWaitEvent(pipe2, fed, 0)) != cudaSuccess) break;
+                const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
+                const uint32_t all_blocks = (p.segs_ps + acc_threads - 1) / acc_threads;
+                const uint32_t blocks = std::min<uint32_t>(all_blocks, all_blocks / ranges + all_blocks / (4 * ranges) + 8);
+                for (uint32_t r = 0; r < ranges && err == cudaSuccess; r++) {
+                    k_scatter_tiled<<<dim3(r ? std::min(scat_blocks, side_ctas / 2) : scat_blocks, 1), 256, 0, pipe>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, r, cursor_q, sorted_q);
+                    if ((err = cudaEventRecord(sorted_ev, pipe)) != cudaSuccess) break;
+                    cudaStream_t sa = (r & 1) ? pipe2 : sq;
+                    if ((err = cudaStreamWaitEvent(sa, sorted_ev, 0)) != cudaSuccess) break;
+                    if (r == 0) tm.mark();                                                     // "scatter" = the exposed first range
+                    if (C::Fq::N > 8) k_accumulate_range_wide<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.nb, p.seg_len, p.segs_ps, r * span, (r + 1) * span, slots_q);
+                    else k_accumulate_range<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.nb, p.seg_len, p.segs_ps, r * span, (r + 1) * span, slots_q);
+                }
+                if (err != cudaSuccess) break;
+                if ((err = cudaEventRecord(aux_done, pipe2)) != cudaSuccess) break;
+                if ((err = cudaStreamWaitEvent(sq, aux_done, 0)) != cudaSuccess) break;
+                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
+                tm.mark();
+                err = cudaGetLastError();
+                continue;
             } else if (p.folded) {
-                uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
-                k_scatter_folded<<<dim3(148 * 8, p.phases), 256, 0, sq>>>((const uint32_t *)codes_q, nq, p.windows, p.table_n, point0, log2_span, cursor_q, sorted_q);
+                k_scatter_tiled<<<dim3(cta_cap < 148 * 8 ? std::max<uint32_t>(1, scat_blocks / p.phases) : scat_blocks, p.phases), 256, 0, sq>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, 0, cursor_q, sorted_q);
             } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, sq>>>((const uint16_t *)codes_q, nq, p.nb, cursor_q, sorted_q);
-            if (aux && (err = cudaEventRecord(sorted_ev, sq)) != cudaSuccess) break;
             tm.mark();
+            trace.mark("sorted", q, sq);
+            if (aux) {
+                if ((err = cudaEventRecord(sorted_ev, sq)) != cudaSuccess) break;
+                if ((err = cudaStreamWaitEvent(sa, sorted_ev, 0)) != cudaSuccess) break;
+            }
             {
                 // 12-limb fields (186 registers per thread): 64-thread CTAs fit 5 per SM (10 warps) where 128-thread ones fit 2 (8 warps)
                 const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
                 const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
                 const uint32_t blocks = (uint32_t)((threads + acc_threads - 1) / acc_threads);
-                if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
-                else k_accumulate<C><<<blocks, acc_threads, 0, sq>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
-                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
+                if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                else k_accumulate<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sa>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
             }
             tm.mark();
+            trace.mark("accumulated", q, sa);
             err = cudaGetLastError();
         }
         if (err != cudaSuccess) break;
-        if (aux) {
-            if ((err = cudaEventRecord(aux_done, aux)) != cudaSuccess) break;
+        if (aux) {      // (every sort was waited for by its accumulation, so joining aux2 joins aux as well)
+            if ((err = cudaEventRecord(aux_done, aux2)) != cudaSuccess) break;
             if ((err = cudaStreamWaitEvent(stream, aux_done, 0)) != cudaSuccess) break;
         }
         uint32_t log2m = 0; while ((1u << log2m) < p.chunk) log2m++;
@@ -834,6 +1012,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                                                                                                    p.sets, p.chunks, p.chunk, p.chunks_ps, chunks);
         }
         tm.mark();
+        trace.mark("buckets done", 0, stream);
         const uint32_t cpg = p.chunks_ps / p.groups;
         uint32_t log2cpg = 0; while ((1u << log2cpg) < cpg) log2cpg++;
         k_group_reduce<C><<<dim3(p.groups, p.sets), WIN_THREADS, 0, stream>>>(chunks, p.chunks_ps, cpg, log2m, gsums);
@@ -850,8 +1029,19 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         tm.mark();
         k_final<C><<<1, 32, 0, stream>>>(final_in, p.sets, final_groups, final_unit, p.c, p.class_log2, p.class_index, (int)coord, (uint8_t *)result);
         tm.mark();
+        trace.mark("end", 0, stream);
         err = cudaGetLastError();
     } while (0);
+    if (err == cudaSuccess) trace.report(stream);
+    if (err != cudaSuccess && pipelined) {
+        cudaGetLastError();
+        cudaEvent_t join = nullptr;
+        if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess) {
+            if (cudaEventRecord(join, pipe) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            if (cudaEventRecord(join, pipe2) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            cudaEventDestroy(join);
+        }
+    }
     if (err != cudaSuccess && (aux || uploading)) {
         // error after work was queued on the side streams: they may still touch the workspace / the staged scalars, so `stream` (on which
         // both are freed in stream order) has to wait for them first.  On the success path aux_done and the consumers of `fed` did that.
@@ -859,6 +1049,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         cudaEvent_t join = nullptr;
         if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess) {
             if (aux && cudaEventRecord(join, aux) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            if (aux2 && cudaEventRecord(join, aux2) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
             if (uploading && cudaEventRecord(join, feed->copy_stream) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
             cudaEventDestroy(join);
         }

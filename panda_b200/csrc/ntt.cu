@@ -590,7 +590,7 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
             // (one radix-8 unit per thread)
             a.logC = std::min<unsigned>(a.log_M, std::max<unsigned>(NTT_MIN_LOGC, NTT_TILE_LOG - std::min<unsigned>(a.r, NTT_TILE_LOG)));
             const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
-            const size_t smem = a.r > 3 ? (size_t)8 * ((size_t)(1u << a.r) * CP) * 4 : 0;   // a single stage group never touches smem
+            const size_t smem = a.r > NTT_GROUP ? (size_t)8 * ((size_t)(1u << a.r) * CP) * 4 : 0;   // a single stage group never touches smem
             const uint32_t blocks = batch << (log_O + a.log_M - a.logC);   // batch rows extend the outer index: (t * 2^log_O + o)
             k_ntt_cols<Bn254Fr><<<blocks, NTT_THREADS, smem, stream>>>(src, dst, a);
         } else {
@@ -598,7 +598,7 @@ cudaError_t ntt_run(NttField field, void *d_src, void *d_dst, unsigned log_n, co
             a.logC = std::min<unsigned>(r1, std::max<unsigned>(NTT_MIN_LOGC, NTT_TILE_LOG - std::min<unsigned>(a.r, NTT_TILE_LOG)));
             if (inverse) a.scale = tab->d_tab + t.off_scale;
             const uint32_t C = 1u << a.logC, CP = C > 1 ? C + 1 : 1;
-            const size_t smem = a.r > 3 ? (size_t)8 * ((size_t)(1u << a.r) * CP) * 4 : 0;
+            const size_t smem = a.r > NTT_GROUP ? (size_t)8 * ((size_t)(1u << a.r) * CP) * 4 : 0;
             a.log_bpt = log_O - a.logC;
             const uint32_t blocks = batch << a.log_bpt;
             k_ntt_last<Bn254Fr><<<blocks, NTT_THREADS, smem, stream>>>(src, dst, a);
