@@ -30,21 +30,22 @@ LOG_N = 24
 MODMUL_MACS = 136            # 2*8^2 + 8 32x32->64 multiply-adds per BN254 Montgomery product
 MADD_MODMULS = 10            # XYZZ mixed addition: 8M + 2S
 ACC_MODMULS = MADD_MODMULS
-ACC_KERNEL = "k_accumulate<Bn254> (bucket accumulation, XYZZ mixed additions)"
-ACC_KERNEL_BLS = "k_accumulate_wide<Bls377> (bucket accumulation, XYZZ mixed additions, 12-limb Fq)"
+ACC_KERNEL = "k_accumulate_range<Bn254> (bucket accumulation, XYZZ mixed additions; one launch per scatter range, pipelined with k_scatter_tiled)"
+ACC_KERNEL_BLS = "k_accumulate_range_wide<Bls377> (bucket accumulation, XYZZ mixed additions, 12-limb Fq; one launch per scatter range)"
 NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram__bytes_{read,write}.sum per launch, written by profiles/summarize.py
                                                                         # from the tracked ncu --set full captures
 
 
 def ncu_traffic(kernel_prefix: str, log_n: int):
-    """(bytes per launch, source) of the dominant kernel from the tracked ncu summary, or (None, why)"""
+    """(bytes over the kernel's launches of ONE MSM, source) of the dominant kernel from the tracked ncu summary, or (None, why)"""
     try:
         data = json.load(open(NCU_TRAFFIC_FILE))
     except Exception as exc:
         return None, f"{os.path.relpath(NCU_TRAFFIC_FILE, ROOT)} unreadable: {exc!r}"
     for entry in data.get("kernels", []):
         if entry["kernel"].startswith(kernel_prefix) and entry.get("log_n") == log_n:
-            return float(entry["dram_bytes_read"]) + float(entry["dram_bytes_write"]), f"{data.get('source', '?')} ({entry['kernel']})"
+            return (float(entry["dram_bytes_read"]) + float(entry["dram_bytes_write"]),
+                    f"{data.get('source', '?')} ({entry['kernel']}, {entry.get('launches', 1)} launches of one MSM summed)")
     return None, f"no capture of {kernel_prefix} at 2^{log_n} in {os.path.relpath(NCU_TRAFFIC_FILE, ROOT)}"
 
 
@@ -53,9 +54,9 @@ def ntt_passes_count(k: int) -> int:
 
 
 def kernels_per_msm(plan) -> int:
-    """our launches in one device-resident MSM on registered bases: digits, scan x3, scatter, accumulate, reduce_big, bucket_reduce,
-    group_reduce (x2 when there are more than 32 groups), final"""
-    return 1 + 3 + 1 + 1 + 1 + 1 + (2 if plan.groups > 32 else 1) + 1
+    """our launches in one device-resident MSM on registered bases: digits, scan x3, (scatter, accumulate) per bucket range, reduce_big,
+    bucket_reduce, group_reduce (x2 when there are more than 32 groups), final"""
+    return 1 + 3 + 2 * max(1, plan.phases) + 1 + 1 + (2 if plan.groups > 32 else 1) + 1
 
 
 def log(*a):
@@ -610,8 +611,9 @@ def run_own_arm(args):
     achieved_macs = macs / (acc_ms * 1e-3)
     acc_bytes = entries * (4 + 64)                          # 4 B sorted index + 64 B gathered affine point per mixed addition
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    digits_bytes = n_local * (32 + 2 * W)                   # scalar read + W 16-bit digits written
-    scatter_bytes = n_local * W * (2 + 4)                   # digit read + index written
+    ranges = max(1, plan.phases)
+    digits_bytes = n_local * (32 + 4 * W)                   # scalar read + W 32-bit codes written (grouped by bucket range, tile by tile)
+    scatter_bytes = n_local * W * (4 + 4) // ranges         # code read + index written, for the ONE range whose scatter is exposed (stage `scatter`)
 
     # ---- NTT 2^24 (the second half of BASELINE.json's metric), device-timed
     k = LOG_N
@@ -737,6 +739,8 @@ def run_own_arm(args):
                          "hbm_stages": {"k_digits": {"GB/s": digits_bytes / (float(stages[0]) * 1e-3) / 1e9, "frac": digits_bytes / (float(stages[0]) * 1e-3) / 1e9 / hbm_peak},
                                         "k_scatter": {"GB/s": scatter_bytes / (float(stages[2]) * 1e-3) / 1e9, "frac": scatter_bytes / (float(stages[2]) * 1e-3) / 1e9 / hbm_peak}}},
         "stage_ms": {nm: float(v) for nm, v in zip(names, stages)},
+        "stage_note": f"{ranges} bucket ranges: `scatter` is the exposed scatter of the first range, the others run beside the accumulation of the range before "
+                      "them and are inside `accumulate` (events on the caller's stream around all range launches)",
         "step_ms_rank0": [round(x, 3) for x in per_step],
         "ntt": {"metric": "bn254_fr_ntt_2^24_latency", "ms": ntt_ms, "passes": ntt_passes, "modmul_per_s": ntt_modmuls / (ntt_ms * 1e-3),
                 "frac_of_modmul_peak": ntt_modmuls / (ntt_ms * 1e-3) / modmul_peak, "hbm_GBps": ntt_passes * 64 * (1 << k) / (ntt_ms * 1e-3) / 1e9,

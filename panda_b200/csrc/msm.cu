@@ -151,15 +151,17 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     // (measured at 2^24: 0.84 ms for 256 CTAs of 1024 chunk sums, against 0.42 ms for the single CTA of the next level)
     p.groups = std::min<uint32_t>(pow2_floor(std::max<uint32_t>(1, 148 / p.sets)), std::max<uint32_t>(1, p.chunks_ps / 1024));
     // folded scatter ranges: the slice of the sorted list written for one bucket range should stay in L2 (126 MB) while its 4-byte writes land
-    // (<= 128 MiB, up to 32 ranges), and the scatter of range r+1 hides behind the accumulation of range r, so only the first range's scatter
-    // is exposed: slices of ~50 MiB, up to 16 ranges.  Measured at 2^24 (768 MiB list): 8 / 16 / 32 ranges 35.7 / 35.2 / 36.0 ms per MSM
-    // against 36.6 unpipelined; 2^22: 10.46 (1) / 10.42 (4) / 10.19 (8); 2^20: 3.47 (1) / 3.36 (4).  Lists below 8 MiB stay in one range
-    // (and so do bucket-class shards, whose scatter passes each recode all the scalars).
+    // (<= 128 MiB, up to 32 ranges), and the scatter of one range hides behind the accumulation of the range before it, so only the first
+    // scatter is exposed.  A range should still be a good part of a wave of accumulation segments (56 832 resident threads x L = 64 entries; up
+    // to four range launches run side by side), hence >= 3 M entries per range and at most 8 ranges (16 from 512 MiB lists).  Measured
+    // (profiles/r2_msm_pipeline.md): 2^24 (768 MiB list) 8 / 16 / 32 ranges 35.7 / 35.2 / 36.0 ms per MSM against 36.6 unpipelined; 2^22 1 / 4 / 8 / 16
+    // ranges 10.10 / 10.01 / 9.99 / 10.12; 2^21 6.11 / 5.78 / 5.80 / 5.98; 2^20 (1 / 2 / 4 / 8) 3.46 / 3.39 / 3.33 / 3.45.  Bucket-class shards keep the 128 MiB rule (their scatter passes each recode all scalars).
     p.phases = 1;
     if (folded) {
         static const uint32_t forced = [] { const char *e = getenv("PANDA_MSM_PHASES"); return e ? (uint32_t)atoi(e) : 0u; }();
         const uint64_t list_bytes = ((uint64_t)p.stride * 4) >> class_log2;
-        while (!class_log2 && p.phases < 16 && p.phases < p.nb && list_bytes >= ((uint64_t)8 << 20) && list_bytes / p.phases > ((uint64_t)12 << 20)) p.phases *= 2;
+        const uint32_t max_ranges = list_bytes >= ((uint64_t)512 << 20) ? 16 : 8;
+        while (!class_log2 && p.phases < max_ranges && p.phases < p.nb && list_bytes / (p.phases * 2) >= ((uint64_t)12 << 20)) p.phases *= 2;   // >= 3 M entries per range
         while (p.phases < p.nb && list_bytes / p.phases > ((uint64_t)128 << 20)) p.phases *= 2;
         if (forced) p.phases = std::min<uint32_t>(pow2_floor(forced), p.nb);
         if (!class_log2) {
@@ -411,6 +413,7 @@ static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, c
 
 static cudaError_t aux_stream_for_current_device(cudaStream_t *out);
 static cudaError_t aux2_stream_for_current_device(cudaStream_t *out);
+static cudaError_t side_stream_for_current_device(int which, cudaStream_t *out);
 static uint32_t resident_chunks(uint32_t n);
 
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
@@ -437,7 +440,7 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
         p.table_n = table_n;
         p.class_index = class_index;
         if (p.chunks > 1) {
-            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr};
+            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
             PB_CUDA(aux2_stream_for_current_device(&feed.aux2_stream));
             return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, nullptr, &feed);
@@ -445,9 +448,11 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
         // one chunk, several scatter ranges: range r+1 is scattered while range r is accumulated (PANDA_MSM_PIPELINE=0: one launch each)
         static const bool pipeline_on = [] { const char *v = getenv("PANDA_MSM_PIPELINE"); return !v || atoi(v) != 0; }();
         if (pipeline_on && p.phases > 1 && !class_log2) {
-            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr};
+            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
             PB_CUDA(aux2_stream_for_current_device(&feed.aux2_stream));
+            PB_CUDA(side_stream_for_current_device(3, &feed.aux3_stream));
+            PB_CUDA(side_stream_for_current_device(4, &feed.aux4_stream));
             return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings, &feed);
         }
         return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings);
@@ -462,7 +467,7 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
 // caller's priority, created on first use
 static cudaError_t side_stream_for_current_device(int which, cudaStream_t *out) {
     static std::mutex m;
-    static cudaStream_t streams[3][64] = {};
+    static cudaStream_t streams[5][64] = {};
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
@@ -507,10 +512,10 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
     cudaError_t e;
     if (table) {
         static const uint32_t forced = [] { const char *v = getenv("PANDA_MSM_CHUNKS"); return v ? (uint32_t)atoi(v) : 0u; }();
-        uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 23) ? 5 : n >= (1u << 21) ? 4 : n >= (1u << 19) ? 3 : 1);
+        uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 23) ? 4 : n >= (1u << 19) ? 3 : 1);
         MsmPlan p = msm_make_plan(curve, n, true, tc, 0, ~(size_t)0, chunks);
         p.table_n = table_n;
-        MsmFeed feed{host_scalars, d_scal, nullptr, nullptr, nullptr};
+        MsmFeed feed{host_scalars, d_scal, nullptr, nullptr, nullptr, nullptr, nullptr};
         e = copy_stream_for_current_device(&feed.copy_stream);
         if (e == cudaSuccess) e = aux_stream_for_current_device(&feed.aux_stream);
         if (e == cudaSuccess) e = aux2_stream_for_current_device(&feed.aux2_stream);

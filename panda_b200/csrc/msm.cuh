@@ -55,8 +55,8 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
 // How a chunked pipeline is fed: host_scalars != nullptr: chunk q is uploaded on copy_stream right before its kernels are queued;
 // aux_stream != nullptr: odd chunks run on it, so that one chunk's sort overlaps the previous chunk's accumulation.
 // aux2_stream (with aux_stream, one resident chunk, several scatter ranges): the scatter of bucket range r+1 runs on aux_stream while range r
-// is accumulated; the accumulation launches alternate between the caller's stream and aux2_stream.
-struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; cudaStream_t aux_stream; cudaStream_t aux2_stream; };
+// is accumulated; the accumulation launches rotate over the caller's stream and aux2 .. aux4_stream.
+struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; cudaStream_t aux_stream; cudaStream_t aux2_stream; cudaStream_t aux3_stream; cudaStream_t aux4_stream; };
 
 // Per-stage device timings (ms) filled when msm_run is called with timings != nullptr (adds event syncs;
 // the benchmark harness uses it to attribute time to kernels -- never set on the product path).

@@ -384,24 +384,21 @@ PB_DEV void accumulate_body(const uint8_t *__restrict__ bases, const uint32_t *_
                           slots + ((size_t)w * ((size_t)segs_pw + nb) + s) * Pt::BYTES);
 }
 
-// K4, one bucket range of a single (folded) bucket set at a time -- the pipelined driver scatters range r+1 (L2-atomic bound, few
-// registers, higher-priority stream) while range r is being accumulated (integer-pipe bound).  Range [b_lo, b_hi) owns the segments whose
-// LAST entry lies in it (a segment that straddles a range boundary waits for the later range); grid-stride, so the grid is only a hint.
+// K4, one bucket range of a single (folded) bucket set at a time -- the pipelined driver scatters the next range (L2-atomic bound, few
+// registers, higher-priority stream) while this one is being accumulated (integer-pipe bound).  The ranges are processed from the TOP bucket
+// range downwards and range [b_lo, b_hi) owns the segments whose FIRST entry lies in it: a segment that runs on into higher ranges finds them
+// scattered already.  Grid-stride, so the grid is only a hint.
 template <class C>
 PB_DEV void accumulate_range_body(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ offsets,
                                   uint32_t nb, uint32_t L, uint32_t segs_ps, uint32_t b_lo, uint32_t b_hi, uint8_t *__restrict__ slots) {
     using Pt = Xyzz<typename C::Fq>;
     const uint32_t cnt = __ldg(offsets + nb);
-    const uint32_t lo = __ldg(offsets + b_lo), hi = __ldg(offsets + b_hi);
-    // a straddling segment starts in an earlier range: widen the bucket search downwards for it (b_lo_search = 0 costs ~3 more probes)
+    const uint32_t lo = __ldg(offsets + b_lo), hi = min(__ldg(offsets + b_hi), cnt);
 #pragma unroll 1
-    for (uint64_t s = (uint64_t)(lo / L) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < segs_ps; s += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t s = (uint64_t)((lo + L - 1) / L) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < segs_ps; s += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t start = (uint32_t)s * L;
-        if (start >= cnt) break;
-        const uint32_t end = min(start + L, cnt);
-        if (end > hi) break;
-        if (end <= lo) continue;
-        accumulate_segment<C>(bases, sorted, offsets, start >= lo ? b_lo : 0, b_hi, start, end, slots + (size_t)s * Pt::BYTES);
+        if (start >= hi) break;
+        accumulate_segment<C>(bases, sorted, offsets, b_lo, nb, start, min(start + L, cnt), slots + (size_t)s * Pt::BYTES);
     }
 }
 
@@ -439,6 +436,11 @@ __device__ __noinline__ void add_cold(Xyzz<F> &a, const Xyzz<F> &b);      // def
 // [t*m, (t+1)*m) of logical set w from the top: B_j = sum of its partial slots over all `merge` chunks (physical set
 // q * W + w holds chunk q's partials), run += B_j, tri += run.
 // Emits Lc = sum_i (i+1) * B_{t*m+i} and Rc = sum_i B_{t*m+i}.
+// The chain per thread is: two offsets -> the bucket's partial slots (128 B each, DRAM) -> a point addition.  With 8 warps per SM (200+ registers)
+// nothing hides those dependent loads, so the walk is software-pipelined without spending registers on it: the offsets of the next
+// (bucket, chunk) pair are loaded while the current pair is being added, and the next slot is pulled into L2 / L1 with a prefetch.
+PB_DEV void prefetch_line(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <class C>
 __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const uint8_t *__restrict__ slots, const uint32_t *__restrict__ offsets,
                                                               uint32_t nb, uint32_t L, uint32_t segs_pw, uint32_t W, uint32_t merge, uint32_t m,
@@ -448,28 +450,42 @@ __global__ void __launch_bounds__(RED_THREADS) k_bucket_reduce(const uint8_t *__
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= W * chunks_pw) return;
     const uint32_t w = gid / chunks_pw, t = gid % chunks_pw;
-    Pt run = Pt::identity(), tri = Pt::identity();
-#pragma unroll 1
-    for (uint32_t i = m; i-- > 0;) {
+    const size_t set_stride = ((size_t)segs_pw + nb) * Pt::BYTES;
+    // (bucket, chunk) pair -> its slots [s0, s1] (s0 > s1: none) and the address of slot 0 of that bucket
+    auto bounds = [&](uint32_t i, uint32_t q, uint32_t &s0, uint32_t &s1, const uint8_t *&base) {
         const uint32_t j = t * m + i;
+        const size_t set = (size_t)q * W + w;
+        const uint32_t *ow = offsets + set * (nb + 1);
+        const uint32_t o0 = __ldg(ow + j), o1 = __ldg(ow + j + 1);
+        base = slots + set * set_stride + (size_t)j * Pt::BYTES;
+        if (o1 > o0) {
+            s0 = o0 / L;
+            s1 = (o1 - 1) / L;
+            if (s1 - s0 + 1 > BIG_SPAN) s1 = s0;           // already folded into its first slot by k_reduce_big
+        } else { s0 = 1; s1 = 0; }
+    };
+    Pt run = Pt::identity(), tri = Pt::identity();
+    uint32_t i = m - 1, q = 0, s0, s1;
+    const uint8_t *base;
+    bounds(i, q, s0, s1, base);
+    if (s0 <= s1) prefetch_line(base + (size_t)s0 * Pt::BYTES);
 #pragma unroll 1
-        for (uint32_t q = 0; q < merge; q++) {
-            const size_t set = (size_t)q * W + w;
-            const uint32_t *ow = offsets + set * (nb + 1);
-            const uint8_t *slot_w = slots + set * ((size_t)segs_pw + nb) * Pt::BYTES;
-            const uint32_t o0 = __ldg(ow + j), o1 = __ldg(ow + j + 1);
-            if (o1 > o0) {
-                const uint32_t s0 = o0 / L;
-                uint32_t s1 = (o1 - 1) / L;
-                if (s1 - s0 + 1 > BIG_SPAN) s1 = s0;       // already folded into its first slot by k_reduce_big
+    for (uint32_t step = m * merge; step-- > 0;) {
+        // the pair after this one (its offsets travel while this pair is being added)
+        uint32_t ni = i, nq = q + 1, ns0 = 1, ns1 = 0;
+        const uint8_t *nbase = base;
+        if (nq == merge) { nq = 0; ni = i - 1; }
+        if (step) bounds(ni, nq, ns0, ns1, nbase);
 #pragma unroll 1
-                for (uint32_t sg = s0; sg <= s1; sg++) {
-                    Pt part = Pt::load(slot_w + ((size_t)sg + j) * Pt::BYTES);
-                    if constexpr (Fq::N > 8) add_cold(run, part); else run.add(part);   // 12 limbs: out of line (255 registers + spills otherwise)
-                }
-            }
+        for (uint32_t sg = s0; sg <= s1; sg++) {
+            if (sg < s1) prefetch_line(base + (size_t)(sg + 1) * Pt::BYTES);
+            else if (ns0 <= ns1) prefetch_line(nbase + (size_t)ns0 * Pt::BYTES);
+            Pt part = Pt::load(base + (size_t)sg * Pt::BYTES);
+            if constexpr (Fq::N > 8) add_cold(run, part); else run.add(part);   // 12 limbs: out of line (255 registers + spills otherwise)
         }
-        if constexpr (Fq::N > 8) add_cold(tri, run); else tri.add(run);
+        if (s0 > s1 && ns0 <= ns1) prefetch_line(nbase + (size_t)ns0 * Pt::BYTES);
+        if (q + 1 == merge) { if constexpr (Fq::N > 8) add_cold(tri, run); else tri.add(run); }
+        i = ni; q = nq; s0 = ns0; s1 = ns1; base = nbase;
     }
     uint8_t *out = chunks + (size_t)gid * 2 * Pt::BYTES;
     tri.store(out);
@@ -881,9 +897,11 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
     cudaStream_t aux = (feed && p.chunks > 1 && feed->aux_stream && feed->aux2_stream) ? feed->aux_stream : nullptr;
     cudaStream_t aux2 = aux ? feed->aux2_stream : nullptr;
     // one resident chunk, several scatter ranges: scatter and accumulation are pipelined range by range over two side streams
-    cudaStream_t pipe = nullptr, pipe2 = nullptr;
-    if (feed && p.chunks == 1 && p.folded && !p.class_log2 && p.phases > 1 && !uploading) { pipe = feed->aux_stream; pipe2 = feed->aux2_stream; }
-    const bool pipelined = pipe && pipe2;
+    cudaStream_t pipe = nullptr, pipe2 = nullptr, pipe3 = nullptr, pipe4 = nullptr;
+    if (feed && p.chunks == 1 && p.folded && !p.class_log2 && p.phases > 1 && !uploading) {
+        pipe = feed->aux_stream; pipe2 = feed->aux2_stream; pipe3 = feed->aux3_stream; pipe4 = feed->aux4_stream;
+    }
+    const bool pipelined = pipe && pipe2 && pipe3 && pipe4;
     cudaError_t err = cudaSuccess;
     do {
         if ((err = cudaMemsetAsync(counts, 0, (phys * p.nb + p.chunks) * 4, stream)) != cudaSuccess) break;
@@ -920,7 +938,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             // kernels that run beside an accumulation (every chunk but the first; every scatter range but the first) get small grids: their
             // warps mostly wait for L2 atomics, and each CTA that becomes resident displaces accumulation warps that would keep the integer pipe
             // busy.  Too few, and the sort of the next chunk is late (a CTA beside three accumulation CTAs gets a small share of the issue
-            // slots).  Measured at 2^24 (profiles/r2_e2e_pipeline.md): scatter 2 CTAs per SM, digits 4; the range pipeline's scatters 1.
+            // slots).  Measured at 2^24 (profiles/r2_msm_pipeline.md): scatter 2 CTAs per SM, digits 4; the range pipeline's scatters 1.
             static const uint32_t side_ctas = [] { const char *e = getenv("PANDA_MSM_SIDE_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 296u; }();
             static const uint32_t side_digit_ctas = [] { const char *e = getenv("PANDA_MSM_SIDE_DIGITS"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 592u; }();
             const uint32_t cta_cap = (aux && q > 0) ? side_ctas : 148 * 8;
@@ -954,26 +972,39 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                 else k_class_pass<C, false, true><<<dim3(sblocks, 1), 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, nq, 0, p.stride, 31, cursor_q, sorted_q);
             } else if (pipelined) {
                 // bucket range r is scattered on the high-priority stream `pipe` while the ranges before it are being accumulated; the accumulation
-                // launches alternate between `sq` and `pipe2` so that the tail of one overlaps the head of the next (they are independent)
+                // launches rotate over four streams so that the tail of one overlaps the head of the next ones (they are independent)
                 const uint32_t span = 1u << log2_span, ranges = p.phases;
                 if ((err = cudaEventRecord(fed, sq)) != cudaSuccess) break;                    // scan done (and workspace allocated)
                 if ((err = cudaStreamWaitEvent(pipe, fed, 0)) != cudaSuccess) break;
                 if ((err = cudaStreamWaitEvent(pipe2, fed, 0)) != cudaSuccess) break;
+                if ((err = cudaStreamWaitEvent(pipe3, fed, 0)) != cudaSuccess) break;
+                if ((err = cudaStreamWaitEvent(pipe4, fed, 0)) != cudaSuccess) break;
+                cudaStream_t acc_streams[4] = {sq, pipe2, pipe3, pipe4};      // small ranges are a fraction of a wave each: up to four run side by side
                 const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
                 const uint32_t all_blocks = (p.segs_ps + acc_threads - 1) / acc_threads;
-                const uint32_t blocks = std::min<uint32_t>(all_blocks, all_blocks / ranges + all_blocks / (4 * ranges) + 8);
-                for (uint32_t r = 0; r < ranges && err == cudaSuccess; r++) {
-                    k_scatter_tiled<<<dim3(r ? std::min(scat_blocks, side_ctas / 2) : scat_blocks, 1), 256, 0, pipe>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, r, cursor_q, sorted_q);
+                // The balanced windows make the ranges uneven: the (W - wide) narrow windows only reach the lower half of the buckets, so with
+                // uniform scalars a lower-half range holds (2 W - wide) / wide times the entries of an upper-half one (7 x at 2^24).  The ranges
+                // are processed from the top one downwards (k_accumulate_range's ownership rule): the small ones go first, the exposed scatter is
+                // a small one, and every launch gets the grid its expected share asks for -- the kernel is grid-stride, so other digit
+                // distributions only cost balance, not correctness.
+                for (uint32_t k = 0; k < ranges && err == cudaSuccess; k++) {
+                    const uint32_t r = ranges - 1 - k;
+                    const double share = ((double)p.wide + (r < ranges / 2 || ranges == 1 ? 2.0 * (p.windows - p.wide) : 0.0)) / ((double)p.windows * ranges);
+                    const uint32_t blocks = std::min<uint32_t>(all_blocks, (uint32_t)((double)all_blocks * share * 1.03) + 8);
+                    k_scatter_tiled<<<dim3(k ? std::min(scat_blocks, side_ctas / 2) : scat_blocks, 1), 256, 0, pipe>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, r, cursor_q, sorted_q);
                     if ((err = cudaEventRecord(sorted_ev, pipe)) != cudaSuccess) break;
-                    cudaStream_t sa = (r & 1) ? pipe2 : sq;
+                    cudaStream_t sa = acc_streams[k & 3];
                     if ((err = cudaStreamWaitEvent(sa, sorted_ev, 0)) != cudaSuccess) break;
-                    if (r == 0) tm.mark();                                                     // "scatter" = the exposed first range
+                    if (k == 0) tm.mark();                                                     // "scatter" = the exposed first range
                     if (C::Fq::N > 8) k_accumulate_range_wide<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.nb, p.seg_len, p.segs_ps, r * span, (r + 1) * span, slots_q);
                     else k_accumulate_range<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.nb, p.seg_len, p.segs_ps, r * span, (r + 1) * span, slots_q);
                 }
                 if (err != cudaSuccess) break;
-                if ((err = cudaEventRecord(aux_done, pipe2)) != cudaSuccess) break;
-                if ((err = cudaStreamWaitEvent(sq, aux_done, 0)) != cudaSuccess) break;
+                for (int j = 1; j < 4 && err == cudaSuccess; j++) {
+                    if ((err = cudaEventRecord(aux_done, acc_streams[j])) != cudaSuccess) break;
+                    err = cudaStreamWaitEvent(sq, aux_done, 0);
+                }
+                if (err != cudaSuccess) break;
                 k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
                 tm.mark();
                 err = cudaGetLastError();
@@ -1039,6 +1070,8 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess) {
             if (cudaEventRecord(join, pipe) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
             if (cudaEventRecord(join, pipe2) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            if (cudaEventRecord(join, pipe3) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            if (cudaEventRecord(join, pipe4) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
             cudaEventDestroy(join);
         }
     }

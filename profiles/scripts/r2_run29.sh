@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+( python -m pytest tests/test_gpu_msm.py -m gpu -x -q ) > gpurun_out/r2_pytest29.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest29.log
+for k in 20 22 24; do python profiles/scripts/stage_times.py $k; done
+python profiles/scripts/stage_times.py 24 1
+python profiles/scripts/streamed_times.py 24 0,3
+PANDA_MSM_TRACE=1 python profiles/scripts/streamed_times.py 24 0 2>&1 | grep -E "buckets done|accumulated    3|end " | tail -3

@@ -82,13 +82,16 @@ def traffic(args):
         rows = list(csv.reader(txt.splitlines()))
         h, units = rows[0], rows[1]
         ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
-        seen = set()
+        # the capture covers the launches of ONE MSM: a kernel that is launched once per scatter range is summed over its launches
+        seen = {}
         for r in rows[2:]:
             name = re.sub(r"^void ", "", r[ki]).split("(")[0]
-            if name in seen:
-                continue
-            seen.add(name)
-            out["kernels"].append({"kernel": name, "log_n": int(log_n), "dram_bytes_read": to_bytes(r[ri], units[ri]), "dram_bytes_write": to_bytes(r[wi], units[wi])})
+            if name not in seen:
+                seen[name] = {"kernel": name, "log_n": int(log_n), "launches": 0, "dram_bytes_read": 0.0, "dram_bytes_write": 0.0}
+                out["kernels"].append(seen[name])
+            seen[name]["launches"] += 1
+            seen[name]["dram_bytes_read"] += to_bytes(r[ri], units[ri])
+            seen[name]["dram_bytes_write"] += to_bytes(r[wi], units[wi])
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json"), "w") as f:
         json.dump(out, f, indent=1)
 
