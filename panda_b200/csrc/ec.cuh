@@ -102,7 +102,7 @@ struct Xyzz {
         F ppp = p * pp;
         F q = x * pp;
         F x3 = r.sqr() - ppp - q.dbl();
-        y = r * (q - x3) - y * ppp;
+        y = F::mul_add2((q - x3).canon(), r, y.neg().canon(), ppp);      // r (q - x3) - y ppp with one reduction (field.cuh)
         x = x3;
         zz = zz * pp;
         zzz = zzz * ppp;
@@ -125,7 +125,7 @@ struct Xyzz {
         F ppp = p * pp;
         F q = u1 * pp;
         F x3 = r.sqr() - ppp - q.dbl();
-        y = r * (q - x3) - s1 * ppp;
+        y = F::mul_add2((q - x3).canon(), r, s1.neg().canon(), ppp);
         x = x3;
         zz = zz * o.zz * pp;
         zzz = zzz * o.zzz * ppp;

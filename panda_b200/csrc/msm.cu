@@ -155,24 +155,22 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     // scatter is exposed.  A range should still be a good part of a wave of accumulation segments (56 832 resident threads x L = 64 entries; up
     // to four range launches run side by side), hence >= 3 M entries per range and at most 8 ranges (16 from 512 MiB lists).  Measured
     // (profiles/r2_msm_pipeline.md): 2^24 (768 MiB list) 8 / 16 / 32 ranges 35.7 / 35.2 / 36.0 ms per MSM against 36.6 unpipelined; 2^22 1 / 4 / 8 / 16
-    // ranges 10.10 / 10.01 / 9.99 / 10.12; 2^21 6.11 / 5.78 / 5.80 / 5.98; 2^20 (1 / 2 / 4 / 8) 3.46 / 3.39 / 3.33 / 3.45.  Bucket-class shards keep the 128 MiB rule (their scatter passes each recode all scalars).
+    // ranges 10.10 / 10.01 / 9.99 / 10.12; 2^21 6.11 / 5.78 / 5.80 / 5.98; 2^20 (1 / 2 / 4 / 8) 3.46 / 3.39 / 3.33 / 3.45.
     p.phases = 1;
     if (folded) {
         static const uint32_t forced = [] { const char *e = getenv("PANDA_MSM_PHASES"); return e ? (uint32_t)atoi(e) : 0u; }();
         const uint64_t list_bytes = ((uint64_t)p.stride * 4) >> class_log2;
         const uint32_t max_ranges = list_bytes >= ((uint64_t)512 << 20) ? 16 : 8;
-        while (!class_log2 && p.phases < max_ranges && p.phases < p.nb && list_bytes / (p.phases * 2) >= ((uint64_t)12 << 20)) p.phases *= 2;   // >= 3 M entries per range
+        while (p.phases < max_ranges && p.phases < p.nb && list_bytes / (p.phases * 2) >= ((uint64_t)12 << 20)) p.phases *= 2;   // >= 3 M entries per range
         while (p.phases < p.nb && list_bytes / p.phases > ((uint64_t)128 << 20)) p.phases *= 2;
         if (forced) p.phases = std::min<uint32_t>(pow2_floor(forced), p.nb);
-        if (!class_log2) {
-            // tile codes keep 18 bits of the bucket index (the rest is the range) and the tile headers one lane per range
-            p.phases = std::min<uint32_t>(p.phases, 32);
-            while ((p.nb / p.phases) > (1u << 18)) p.phases *= 2;
-        }
+        // tile codes keep 18 bits of the bucket index (the rest is the range) and the tile headers one lane per range
+        p.phases = std::min<uint32_t>(p.phases, 32);
+        while ((p.nb / p.phases) > (1u << 18)) p.phases *= 2;
     }
     const uint32_t chunk_tiles = (max_chunk + 255) / 256;
-    p.codes_stride = folded && !class_log2 ? chunk_tiles * 256 * p.windows : 0;
-    p.heads_stride = folded && !class_log2 ? chunk_tiles * (p.phases + 1) : 0;
+    p.codes_stride = folded ? chunk_tiles * 256 * p.windows : 0;
+    p.heads_stride = folded ? chunk_tiles * (p.phases + 1) : 0;
 
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
@@ -182,7 +180,7 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.off_cursor = off;  off = align(off + phys * p.nb * 4);
     p.off_biglist = off; off = align(off + phys * p.nb * 4);
     p.off_tiles = off;   off = align(off + phys * ((p.nb + 4095) / 4096) * 4);
-    p.off_digits = off;  off = align(off + (class_log2 ? 0 : folded ? (size_t)p.chunks * p.codes_stride * 4 : (size_t)p.windows * n * 2));   // class shards recode the scalars in both passes
+    p.off_digits = off;  off = align(off + (folded ? (size_t)p.chunks * p.codes_stride * 4 : (size_t)p.windows * n * 2));
     p.off_heads = off;   off = align(off + (size_t)p.chunks * p.heads_stride * 2);
     p.off_sorted = off;  off = align(off + phys * p.stride * 4);
     p.off_slots = off;   off = align(off + phys * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);
@@ -447,7 +445,7 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
         }
         // one chunk, several scatter ranges: range r+1 is scattered while range r is accumulated (PANDA_MSM_PIPELINE=0: one launch each)
         static const bool pipeline_on = [] { const char *v = getenv("PANDA_MSM_PIPELINE"); return !v || atoi(v) != 0; }();
-        if (pipeline_on && p.phases > 1 && !class_log2) {
+        if (pipeline_on && p.phases > 1) {
             MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
             PB_CUDA(aux2_stream_for_current_device(&feed.aux2_stream));

@@ -212,26 +212,50 @@ static constexpr uint32_t TILE_PTS = 256;
 static constexpr uint32_t TILE_ID_SHIFT = 18;
 template <class C>
 __global__ void __launch_bounds__(TILE_PTS) k_digits_tiled(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide,
-                                                           uint32_t log2_span, uint32_t ranges, uint32_t *__restrict__ codes,
-                                                           uint16_t *__restrict__ heads, uint32_t *__restrict__ counts) {
+                                                           uint32_t log2_span, uint32_t ranges, uint32_t class_log2, uint32_t class_index,
+                                                           uint32_t *__restrict__ codes, uint16_t *__restrict__ heads, uint32_t *__restrict__ counts) {
     using Fr = typename C::Fr;
     extern __shared__ __align__(16) uint32_t sh_dyn[];
-    uint32_t *cnt = sh_dyn;                               // [ranges][256]: bank = thread index, so every access is conflict-free
-    uint32_t *base = cnt + ranges * TILE_PTS;             // [ranges + 1]
-    uint32_t *out = base + 40;                            // [256 * W]
+    // every array is [row][thread]: bank = thread index, so all accesses but the final placement are conflict-free
+    uint32_t *cnt = sh_dyn;                               // [ranges][256] digits per range and thread, then their exclusive scan
+    uint32_t *base = cnt + ranges * TILE_PTS;             // [ranges + 1] range starts within the tile
+    uint32_t *stage = base + 40;                          // [W][256] sign << 31 | bucket, or all-ones: the digits, extracted once
+    uint32_t *out = stage + W * TILE_PTS;                 // [256 * W] the tile's codes grouped by range
+    uint32_t *limbs = out;                                // [9][256] canonical scalar + a zero row (dead before `out` is written; W >= 9 for these curves)
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t span_mask = (1u << log2_span) - 1;
+    const uint32_t span_mask = (1u << log2_span) - 1, class_mask = (1u << class_log2) - 1;
     const uint32_t tiles = (n + TILE_PTS - 1) / TILE_PTS;
     for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const uint32_t i = tile * TILE_PTS + tid;
         for (uint32_t r = 0; r < ranges; r++) cnt[r * TILE_PTS + tid] = 0;
-        Fr s = Fr::zero();
-        if (i < n) s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; the input is left untouched (zero: no digits)
-        for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t mag, uint32_t neg) {
-            const uint32_t b = mag - 1;
-            atomicAdd(&counts[b], 1u);
-            cnt[(b >> log2_span) * TILE_PTS + tid]++;
-        });
+        {
+            Fr s = Fr::zero();
+            if (i < n) s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; the input is left untouched (zero: no digits)
+#pragma unroll
+            for (int l = 0; l < Fr::N; l++) limbs[l * TILE_PTS + tid] = s.l[l];
+            limbs[Fr::N * TILE_PTS + tid] = 0;
+        }
+        // signed-digit recoding (see for_each_digit): the window is cut out of two adjacent limbs read back from shared memory -- a dynamic limb
+        // index without local memory, ~25 instructions per digit where the bit-buffer loop took ~75 (ncu: the kernel was issue-bound)
+        uint32_t o = 0, carry = 0;
+#pragma unroll 1
+        for (uint32_t w = 0; w < W; w++) {
+            const uint32_t cw = w < wide ? c : c - 1, limb = o >> 5;
+            const uint32_t bits = __funnelshift_r(limbs[limb * TILE_PTS + tid], limbs[(limb + 1) * TILE_PTS + tid], o & 31) & ((1u << cw) - 1);
+            o += cw;
+            const uint32_t v = bits + carry;
+            uint32_t mag = v, neg = 0;
+            carry = 0;
+            if (w + 1 < W && v > (1u << (cw - 1))) { mag = (1u << cw) - v; neg = 1; carry = 1; }   // the top window is never recoded
+            uint32_t code = CODE_SKIP32;
+            if (mag && ((mag - 1) & class_mask) == class_index) {      // bucket-class shard: only the buckets congruent to class_index survive, renumbered
+                const uint32_t b = (mag - 1) >> class_log2;
+                atomicAdd(&counts[b], 1u);
+                cnt[(b >> log2_span) * TILE_PTS + tid]++;
+                code = (neg << 31) | b;
+            }
+            stage[w * TILE_PTS + tid] = code;
+        }
         __syncthreads();
         // exclusive scan of every range's row over the 256 threads: a warp per row, 8 cells per lane
         for (uint32_t r = warp; r < ranges; r += TILE_PTS / 32) {
@@ -243,7 +267,7 @@ __global__ void __launch_bounds__(TILE_PTS) k_digits_tiled(const uint32_t *__res
             for (int k = 0; k < 8; k++) { ex[k] = sum; sum += v[k]; }
             uint32_t incl = sum;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            for (int o2 = 1; o2 < 32; o2 <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o2); if ((int)lane >= o2) incl += t; }
             const uint32_t pre = incl - sum;
             row[0] = make_uint4(ex[0] + pre, ex[1] + pre, ex[2] + pre, ex[3] + pre);
             row[1] = make_uint4(ex[4] + pre, ex[5] + pre, ex[6] + pre, ex[7] + pre);
@@ -254,16 +278,19 @@ __global__ void __launch_bounds__(TILE_PTS) k_digits_tiled(const uint32_t *__res
             const uint32_t v = lane < ranges ? base[lane + 1] : 0;
             uint32_t incl = v;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+            for (int o2 = 1; o2 < 32; o2 <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o2); if ((int)lane >= o2) incl += t; }
             if (lane < ranges) base[lane + 1] = incl;
             if (lane == 0) base[0] = 0;
         }
         __syncthreads();
-        for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t mag, uint32_t neg) {
-            const uint32_t b = mag - 1, r = b >> log2_span;
+#pragma unroll 1
+        for (uint32_t w = 0; w < W; w++) {
+            const uint32_t code = stage[w * TILE_PTS + tid];
+            if (code == CODE_SKIP32) continue;
+            const uint32_t b = code & 0x7FFFFFFFu, r = b >> log2_span;
             const uint32_t pos = base[r] + cnt[r * TILE_PTS + tid]++;
-            out[pos] = (neg << 31) | ((w * TILE_PTS + tid) << TILE_ID_SHIFT) | (b & span_mask);
-        });
+            out[pos] = (code & 0x80000000u) | ((w * TILE_PTS + tid) << TILE_ID_SHIFT) | (b & span_mask);
+        }
         __syncthreads();
         const uint32_t total = base[ranges];
         uint32_t *dst = codes + (size_t)tile * TILE_PTS * W;
@@ -299,31 +326,6 @@ static __global__ void __launch_bounds__(256) k_scatter_tiled(const uint32_t *__
             place(c0); place(c1); place(c2); place(c3);
         }
         for (; k < h1; k += 32) place(__ldg(src + k));
-    }
-}
-
-// K1 / K3 of a bucket-class shard (msm.cuh): 1 / 2^class_log2 of the digits survive, so a dense code array would be mostly "skip" words
-// written and re-read for nothing (measured on one class of eight at 2^24: 1.40 ms against 0.19 ms for the digits of a 2^21-point slice).
-// Both passes recode the scalars instead -- 32 B read per scalar and pass, no code array: the first counts the surviving digits per bucket,
-// the second (SCATTER) places them, one bucket range per launch row (blockIdx.y) like k_scatter_folded.
-template <class C, bool FOLDED, bool SCATTER>
-__global__ void __launch_bounds__(256) k_class_pass(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, uint32_t nb,
-                                                    uint32_t class_log2, uint32_t class_index, uint32_t n_total, uint32_t point0, uint32_t stride,
-                                                    uint32_t log2_span, uint32_t *__restrict__ counters, uint32_t *__restrict__ sorted) {
-    using Fr = typename C::Fr;
-    const uint32_t class_mask = (1u << class_log2) - 1, phase = blockIdx.y;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();
-        for_each_digit(s, c, W, wide, [&](uint32_t w, uint32_t mag, uint32_t neg) {
-            if (((mag - 1) & class_mask) != class_index) return;
-            const uint32_t local = (mag - 1) >> class_log2;
-            uint32_t *ctr = counters + (FOLDED ? (size_t)0 : (size_t)w * nb) + local;      // counts (first pass) / cursor (second pass)
-            if (!SCATTER) { atomicAdd(ctr, 1u); return; }
-            if ((local >> log2_span) != phase) return;
-            const uint32_t pos = atomicAdd(ctr, 1u);
-            const uint32_t entry = FOLDED ? w * n_total + point0 + i : i;
-            sorted[(FOLDED ? (size_t)0 : (size_t)w * stride) + pos] = entry | (neg << 31);
-        });
     }
 }
 
@@ -898,7 +900,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
     cudaStream_t aux2 = aux ? feed->aux2_stream : nullptr;
     // one resident chunk, several scatter ranges: scatter and accumulation are pipelined range by range over two side streams
     cudaStream_t pipe = nullptr, pipe2 = nullptr, pipe3 = nullptr, pipe4 = nullptr;
-    if (feed && p.chunks == 1 && p.folded && !p.class_log2 && p.phases > 1 && !uploading) {
+    if (feed && p.chunks == 1 && p.folded && p.phases > 1 && !uploading) {
         pipe = feed->aux_stream; pipe2 = feed->aux2_stream; pipe3 = feed->aux3_stream; pipe4 = feed->aux4_stream;
     }
     const bool pipelined = pipe && pipe2 && pipe3 && pipe4;
@@ -949,14 +951,12 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             tm.mark();
             trace.mark("sort begins", q, sq);
             const uint32_t sblocks = std::min<uint32_t>((nq + 255) / 256, cta_cap);
-            if (p.class_log2) {
-                if (p.folded) k_class_pass<C, true, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, p.table_n, point0, p.stride, 0, counts_q, nullptr);
-                else k_class_pass<C, false, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, nq, 0, p.stride, 0, counts_q, nullptr);
-            } else if (p.folded) {
-                const size_t sh_bytes = ((size_t)p.phases * TILE_PTS + 40 + (size_t)TILE_PTS * p.windows) * 4;
+            if (p.folded) {
+                const size_t sh_bytes = ((size_t)(p.phases + 2 * p.windows) * TILE_PTS + 40) * 4;
                 if (sh_bytes > 48 * 1024 && (err = cudaFuncSetAttribute(k_digits_tiled<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes)) != cudaSuccess) break;
                 const uint32_t tblocks = std::min<uint32_t>((nq + TILE_PTS - 1) / TILE_PTS, digit_cap);
-                k_digits_tiled<C><<<tblocks, TILE_PTS, sh_bytes, sq>>>(sc, nq, p.c, p.windows, p.wide, log2_span, p.phases, (uint32_t *)codes_q, heads_q, counts_q);
+                k_digits_tiled<C><<<tblocks, TILE_PTS, sh_bytes, sq>>>(sc, nq, p.c, p.windows, p.wide, log2_span, p.phases, p.class_log2, p.class_index,
+                                                                      (uint32_t *)codes_q, heads_q, counts_q);
             }
             else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, codes_q, counts_q);
             tm.mark();
@@ -966,11 +966,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
             k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q, big_count_q, big_list_q);
             tm.mark();
             trace.mark("scanned", q, sq);
-            if (p.class_log2) {
-                uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;
-                if (p.folded) k_class_pass<C, true, true><<<dim3(sblocks, p.phases), 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, p.table_n, point0, p.stride, log2_span, cursor_q, sorted_q);
-                else k_class_pass<C, false, true><<<dim3(sblocks, 1), 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, nq, 0, p.stride, 31, cursor_q, sorted_q);
-            } else if (pipelined) {
+            if (pipelined) {
                 // bucket range r is scattered on the high-priority stream `pipe` while the ranges before it are being accumulated; the accumulation
                 // launches rotate over four streams so that the tail of one overlaps the head of the next ones (they are independent)
                 const uint32_t span = 1u << log2_span, ranges = p.phases;
@@ -981,7 +977,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                 if ((err = cudaStreamWaitEvent(pipe4, fed, 0)) != cudaSuccess) break;
                 cudaStream_t acc_streams[4] = {sq, pipe2, pipe3, pipe4};      // small ranges are a fraction of a wave each: up to four run side by side
                 const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
-                const uint32_t all_blocks = (p.segs_ps + acc_threads - 1) / acc_threads;
+                const uint32_t all_blocks = ((p.segs_ps >> p.class_log2) + acc_threads - 1) / acc_threads + 1;   // expected segments (a class shard keeps 1 / 2^class_log2 of the entries)
                 // The balanced windows make the ranges uneven: the (W - wide) narrow windows only reach the lower half of the buckets, so with
                 // uniform scalars a lower-half range holds (2 W - wide) / wide times the entries of an upper-half one (7 x at 2^24).  The ranges
                 // are processed from the top one downwards (k_accumulate_range's ownership rule): the small ones go first, the exposed scatter is
