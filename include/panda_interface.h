@@ -158,6 +158,15 @@ panda_error panda_msm_combine_bls12_381(const void *partials, unsigned count, vo
 panda_error panda_msm_execute_bn254_n(const panda_msm_configuration exec_cfg, size_t n);
 panda_error panda_msm_execute_bls12_377_n(const panda_msm_configuration exec_cfg, size_t n);
 
+/* One bucket class of an MSM sharded over class_count GPUs (a power of two <= 64) that all hold ALL n points and scalars: the call adds up only
+ * the digits whose bucket index is congruent to class_index modulo class_count and returns their weighted sum as a Jacobian point; the
+ * class_count partials add up to the MSM (panda_msm_combine_*).  Every GPU does 1 / class_count of the additions AND of the bucket reduction at the
+ * window width of the whole job, where a shard by point range (panda_msm_execute_*_n on n / class_count points) repeats the reduction per GPU and
+ * narrows its windows.  Adjacent buckets belong to different classes, so skewed digit distributions stay balanced.  No reference precedent. */
+panda_error panda_msm_execute_bn254_class(const panda_msm_configuration exec_cfg, size_t n, unsigned class_count, unsigned class_index);
+panda_error panda_msm_execute_bls12_377_class(const panda_msm_configuration exec_cfg, size_t n, unsigned class_count, unsigned class_index);
+panda_error panda_msm_execute_bls12_381_class(const panda_msm_configuration exec_cfg, size_t n, unsigned class_count, unsigned class_index);
+
 /* init_msm for cached bases (wrapper.rs:122-152 keeps the device pointer and reuses it across calls): announces that the n
  * affine points at d_bases stay unchanged until panda_msm_unregister_bases / panda_msm_tear_down.  The library builds its
  * table of 2^(c*j) * P multiples right away (asynchronous on `stream`; W * n * 64 bytes of HBM, capped by PANDA_MSM_TABLE_BUDGET

@@ -510,7 +510,7 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
     cudaError_t e;
     if (table) {
         static const uint32_t forced = [] { const char *v = getenv("PANDA_MSM_CHUNKS"); return v ? (uint32_t)atoi(v) : 0u; }();
-        uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 23) ? 4 : n >= (1u << 19) ? 3 : 1);
+        uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 19) ? 3 : 1);
         MsmPlan p = msm_make_plan(curve, n, true, tc, 0, ~(size_t)0, chunks);
         p.table_n = table_n;
         MsmFeed feed{host_scalars, d_scal, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -256,6 +256,9 @@ SIGNATURES: dict[str, list] = {
     "panda_msm_execute_bls12_377": [MSMConfiguration],
     "panda_msm_execute_bn254_n": [MSMConfiguration, SizeT],
     "panda_msm_execute_bls12_377_n": [MSMConfiguration, SizeT],
+    "panda_msm_execute_bn254_class": [MSMConfiguration, SizeT, _uint, _uint],
+    "panda_msm_execute_bls12_377_class": [MSMConfiguration, SizeT, _uint, _uint],
+    "panda_msm_execute_bls12_381_class": [MSMConfiguration, SizeT, _uint, _uint],
     "panda_msm_register_bases_bn254": [_vp, SizeT, PandaStream],
     "panda_msm_register_bases_bls12_377": [_vp, SizeT, PandaStream],
     "panda_msm_unregister_bases": [_vp],

@@ -98,3 +98,32 @@ class ShardedMsm:
             out = torch.empty(nb, dtype=torch.uint8, device=dev)
             self.combine(gathered.data_ptr(), self.world, out.data_ptr(), coord, stream)
         return out
+
+
+def _cuda_class_msm(curve: int):
+    import ctypes as C
+    from . import gpu_ffi as ffi
+
+    def run(d_bases: int, d_scalars: int, n: int, class_count: int, class_index: int, d_out: int, stream: int, pool: int) -> None:
+        cfg = ffi.MSMConfiguration(ffi.PandaMemPool(pool or None), ffi.PandaStream(stream or None), d_bases, d_scalars, d_out, 0,
+                                   ffi.PandaMSMResultCoordinateType.Jacobian)
+        fn = ffi.lib.panda_msm_execute_bls12_377_class if curve == 1 else ffi.lib.panda_msm_execute_bn254_class
+        rc = fn(cfg, C.c_size_t(n), class_count, class_index)
+        if rc != 0:
+            raise ffi.PandaGpuError("SchedulingErr", rc)
+
+    return run
+
+
+class ClassShardedMsm(ShardedMsm):
+    """MSM sharded by BUCKET CLASS: every rank holds all n points and scalars (and the whole table of the cached bases) and adds up the digits
+    whose bucket index is congruent to its rank modulo the world size (panda_msm_execute_*_class); the 96-byte partials are all-gathered and
+    summed like ShardedMsm's.  For device-resident scalars on a box whose GPUs each have room for the whole job: the window width stays the
+    single-GPU one and the bucket reduction is split, not repeated.  The world size must be a power of two."""
+
+    def __init__(self, curve: int = 0, group=None, class_msm: Optional[Callable] = None, combine: Optional[Callable] = None):
+        super().__init__(curve, group, local_msm=lambda *a: None, combine=combine)
+        if self.world & (self.world - 1):
+            raise ValueError("bucket-class shards need a power-of-two world size")
+        self.class_msm = class_msm or _cuda_class_msm(curve)
+        self.local_msm = lambda d_b, d_s, n, d_out, stream, pool: self.class_msm(d_b, d_s, n, self.world, self.rank, d_out, stream, pool)

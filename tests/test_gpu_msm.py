@@ -475,6 +475,62 @@ def test_split_pipeline_small(split):
     assert "product path (panda_msm_execute_*) closed-form match: True" in out.stdout, out.stdout[-2000:]
 
 
+@pytest.mark.parametrize("ranges", [1, 4, 32])
+def test_range_pipeline_forced(ranges):
+    """PANDA_MSM_PHASES forces the number of bucket ranges of the table plan (1: one scatter and one accumulation launch; more: the scatter of a
+    range overlaps the accumulation of the range before it on the library's side streams); PANDA_MSM_PIPELINE=0 runs the ranges without the overlap"""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for pipeline in ("1", "0"):
+        env = dict(os.environ, PANDA_MSM_PHASES=str(ranges), PANDA_MSM_PIPELINE=pipeline)
+        out = subprocess.run([sys.executable, os.path.join(root, "tests", "run_msm.py"), "17", "1", "0", "0", "0", "2"], env=env, capture_output=True,
+                             text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert f"P={ranges} " in out.stdout, out.stdout[-2000:]
+        assert "closed-form match: True" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("curve,k,mode", [(0, 16, "uniform"), (0, 14, "all_equal"), (0, 14, "small"), (1, 13, "uniform")])
+def test_bucket_class_shards(oracle, dev, curve, k, mode):
+    """panda_msm_execute_*_class: the class_count partials (each the buckets of one residue class) add up to the MSM, on registered bases
+    (table plan) and on unannounced ones (windowed plan), for uniform and for skewed scalars"""
+    ffi, gu = dev
+    n = 1 << k
+    fq = oracle.FQ_BYTES[curve]
+    bases = oracle.gen_bases(curve, 900 + k, n)
+    scal = oracle.gen_scalars(oracle.FR_OF[curve], 901 + k, n)
+    if mode == "all_equal":
+        scal = np.tile(scal[:32], n)
+    elif mode == "small":
+        small = np.zeros((n, 32), np.uint8); small[:, 0] = np.arange(n) % 5
+        scal = oracle.f_to_mont(1, small.reshape(-1))
+    exp = oracle.jac_to_affine(curve, oracle.msm(curve, bases, scal, n, c=10))
+    d_b, d_s = gu.DevBuf.from_numpy(bases), gu.DevBuf.from_numpy(scal)
+    stream, pool = ffi.PandaStream.new(), ffi.PandaMemPool.new(0)
+    execute = ffi.lib.panda_msm_execute_bls12_377_class if curve else ffi.lib.panda_msm_execute_bn254_class
+    combine = ffi.lib.panda_msm_combine_bls12_377 if curve else ffi.lib.panda_msm_combine_bn254
+    register = ffi.lib.panda_msm_register_bases_bls12_377 if curve else ffi.lib.panda_msm_register_bases_bn254
+    try:
+        for registered in (False, True):
+            if registered:
+                assert register(d_b.ptr, n, stream) == 0
+            for count in (1, 2, 8):
+                d_p, d_r = gu.DevBuf(3 * fq * count), gu.DevBuf(3 * fq)
+                for g in range(count):
+                    cfg = ffi.MSMConfiguration(pool, stream, d_b.ptr, d_s.ptr, d_p.ptr.value + 3 * fq * g, k, 0)
+                    assert execute(cfg, n, count, g) == 0
+                assert combine(d_p.ptr, count, d_r.ptr, 0, stream) == 0
+                stream.sync()
+                assert (oracle.jac_to_affine(curve, d_r.to_numpy()) == exp).all(), (registered, count)
+        cfg = ffi.MSMConfiguration(pool, stream, d_b.ptr, d_s.ptr, d_r.ptr, k, 0)
+        assert execute(cfg, n, 3, 0) != 0 and execute(cfg, n, 4, 4) != 0        # class count must be a power of two, index below it
+    finally:
+        assert ffi.lib.panda_msm_tear_down() == 0
+
+
 def test_randomised_differential(oracle, dev):
     """40 seeded random cases against the oracle: ragged sizes, scalars mixing 0 / 1 / r-1 / small / random, bases with identities,
     duplicates and negated pairs, windowed and table plans, both output coordinates, device-resident and host (streamed) scalars"""
