@@ -458,6 +458,16 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
     MsmPlan p = msm_make_plan(curve, n, false, c_override <= 16 ? c_override : 0, seg_override, ~(size_t)0, 1, class_log2);
     if (!p.c) return cudaErrorInvalidValue;
     p.class_index = class_index;
+    // windowed plan: window w+1 is scattered while window w is accumulated, from 2^22 sorted entries (a window is then a wave of segments or more)
+    static const bool pipeline_on = [] { const char *v = getenv("PANDA_MSM_PIPELINE"); return !v || atoi(v) != 0; }();
+    if (pipeline_on && ((uint64_t)n * p.windows >> class_log2) >= ((uint64_t)1 << 22)) {
+        MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
+        PB_CUDA(aux2_stream_for_current_device(&feed.aux2_stream));
+        PB_CUDA(side_stream_for_current_device(3, &feed.aux3_stream));
+        PB_CUDA(side_stream_for_current_device(4, &feed.aux4_stream));
+        return run_pipeline(curve, p, bases, scalars, result, coord, pool, stream, timings, &feed);
+    }
     return run_pipeline(curve, p, bases, scalars, result, coord, pool, stream, timings);
 }
 

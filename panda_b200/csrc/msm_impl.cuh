@@ -188,9 +188,9 @@ static __global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *__re
 
 // K3 (windowed): scatter point indices (digit sign in bit 31) into their bucket's range.  blockIdx.y = window, so one window's
 // 4n-byte output range is being filled at a time and stays in L2 while it is written.
-static __global__ void __launch_bounds__(256) k_scatter(const uint16_t *__restrict__ digits, uint32_t n, uint32_t nb,
+static __global__ void __launch_bounds__(256) k_scatter(const uint16_t *__restrict__ digits, uint32_t n, uint32_t nb, uint32_t w0,
                                                         uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
-    const uint32_t w = blockIdx.y;
+    const uint32_t w = w0 + blockIdx.y;             // the pipelined driver launches one window at a time (gridDim.y = 1)
     const uint16_t *dw = digits + (size_t)w * n;
     uint32_t *kw = cursor + (size_t)w * nb;
     uint32_t *sw = sorted + (size_t)w * n;
@@ -373,11 +373,11 @@ PB_DEV void accumulate_segment(const uint8_t *__restrict__ bases, const uint32_t
 template <class C>
 PB_DEV void accumulate_body(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
                             const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
-                            uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
+                            uint32_t segs_pw, uint32_t W, uint32_t w0, uint8_t *__restrict__ slots) {
     using Pt = Xyzz<typename C::Fq>;
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (uint64_t)W * segs_pw) return;
-    const uint32_t w = (uint32_t)(gid / segs_pw), s = (uint32_t)(gid % segs_pw);
+    const uint32_t w = w0 + (uint32_t)(gid / segs_pw), s = (uint32_t)(gid % segs_pw);      // bucket sets w0 .. w0 + W - 1
     const uint32_t *ow = offsets + (size_t)w * (nb + 1);
     const uint32_t cnt = __ldg(ow + nb);
     const uint32_t start = s * L;
@@ -407,15 +407,15 @@ PB_DEV void accumulate_range_body(const uint8_t *__restrict__ bases, const uint3
 template <class C>
 __global__ void __launch_bounds__(ACC_THREADS) k_accumulate(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                            const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
-                                                           uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
-    accumulate_body<C>(bases, sorted, offsets, stride, nb, L, segs_pw, W, slots);
+                                                           uint32_t segs_pw, uint32_t W, uint32_t w0, uint8_t *__restrict__ slots) {
+    accumulate_body<C>(bases, sorted, offsets, stride, nb, L, segs_pw, W, w0, slots);
 }
 // 12-limb fields: 64-thread CTAs, five per SM (204 registers) -- ten warps per SM instead of the eight that 222 registers allow
 template <class C>
 __global__ void __launch_bounds__(64, 5) k_accumulate_wide(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                           const uint32_t *__restrict__ offsets, uint32_t stride, uint32_t nb, uint32_t L,
-                                                          uint32_t segs_pw, uint32_t W, uint8_t *__restrict__ slots) {
-    accumulate_body<C>(bases, sorted, offsets, stride, nb, L, segs_pw, W, slots);
+                                                          uint32_t segs_pw, uint32_t W, uint32_t w0, uint8_t *__restrict__ slots) {
+    accumulate_body<C>(bases, sorted, offsets, stride, nb, L, segs_pw, W, w0, slots);
 }
 
 template <class C>
@@ -904,10 +904,14 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         pipe = feed->aux_stream; pipe2 = feed->aux2_stream; pipe3 = feed->aux3_stream; pipe4 = feed->aux4_stream;
     }
     const bool pipelined = pipe && pipe2 && pipe3 && pipe4;
+    // windowed plan (one bucket set per window): the same pipeline window by window
+    const bool pipelined_w = feed && !pipelined && p.chunks == 1 && !p.folded && p.windows > 1 && !uploading && feed->aux_stream && feed->aux2_stream &&
+                             feed->aux3_stream && feed->aux4_stream;
+    if (pipelined_w) { pipe = feed->aux_stream; pipe2 = feed->aux2_stream; pipe3 = feed->aux3_stream; pipe4 = feed->aux4_stream; }
     cudaError_t err = cudaSuccess;
     do {
         if ((err = cudaMemsetAsync(counts, 0, (phys * p.nb + p.chunks) * 4, stream)) != cudaSuccess) break;
-        if (pipelined || uploading || aux) {
+        if (pipelined || pipelined_w || uploading || aux) {
             if ((err = cudaEventCreateWithFlags(&fed, cudaEventDisableTiming)) != cudaSuccess) break;
             if ((err = cudaEventCreateWithFlags(&sorted_ev, cudaEventDisableTiming)) != cudaSuccess) break;
             if ((err = cudaEventCreateWithFlags(&aux_done, cudaEventDisableTiming)) != cudaSuccess) break;
@@ -1005,9 +1009,37 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                 tm.mark();
                 err = cudaGetLastError();
                 continue;
+            } else if (pipelined_w) {
+                // windowed plan: window w+1 is scattered on `pipe` while window w is accumulated; accumulations rotate over four streams
+                if ((err = cudaEventRecord(fed, sq)) != cudaSuccess) break;
+                cudaStream_t acc_streams[4] = {sq, pipe2, pipe3, pipe4};
+                if ((err = cudaStreamWaitEvent(pipe, fed, 0)) != cudaSuccess) break;
+                for (int j = 1; j < 4 && err == cudaSuccess; j++) err = cudaStreamWaitEvent(acc_streams[j], fed, 0);
+                if (err != cudaSuccess) break;
+                const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
+                const uint32_t blocks = (p.segs_ps + acc_threads - 1) / acc_threads;
+                for (uint32_t w = 0; w < p.windows && err == cudaSuccess; w++) {
+                    k_scatter<<<dim3(w ? std::min(sblocks, side_ctas / 2) : sblocks, 1), 256, 0, pipe>>>((const uint16_t *)codes_q, nq, p.nb, w, cursor_q, sorted_q);
+                    if ((err = cudaEventRecord(sorted_ev, pipe)) != cudaSuccess) break;
+                    cudaStream_t sa = acc_streams[w & 3];
+                    if ((err = cudaStreamWaitEvent(sa, sorted_ev, 0)) != cudaSuccess) break;
+                    if (w == 0) tm.mark();
+                    if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, 1, w, slots_q);
+                    else k_accumulate<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, 1, w, slots_q);
+                }
+                if (err != cudaSuccess) break;
+                for (int j = 1; j < 4 && err == cudaSuccess; j++) {
+                    if ((err = cudaEventRecord(aux_done, acc_streams[j])) != cudaSuccess) break;
+                    err = cudaStreamWaitEvent(sq, aux_done, 0);
+                }
+                if (err != cudaSuccess) break;
+                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
+                tm.mark();
+                err = cudaGetLastError();
+                continue;
             } else if (p.folded) {
                 k_scatter_tiled<<<dim3(cta_cap < 148 * 8 ? std::max<uint32_t>(1, scat_blocks / p.phases) : scat_blocks, p.phases), 256, 0, sq>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, 0, cursor_q, sorted_q);
-            } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, sq>>>((const uint16_t *)codes_q, nq, p.nb, cursor_q, sorted_q);
+            } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, sq>>>((const uint16_t *)codes_q, nq, p.nb, 0, cursor_q, sorted_q);
             tm.mark();
             trace.mark("sorted", q, sq);
             if (aux) {
@@ -1019,8 +1051,8 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                 const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
                 const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
                 const uint32_t blocks = (uint32_t)((threads + acc_threads - 1) / acc_threads);
-                if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
-                else k_accumulate<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, slots_q);
+                if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, 0, slots_q);
+                else k_accumulate<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, 0, slots_q);
                 k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sa>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
             }
             tm.mark();
@@ -1060,7 +1092,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         err = cudaGetLastError();
     } while (0);
     if (err == cudaSuccess) trace.report(stream);
-    if (err != cudaSuccess && pipelined) {
+    if (err != cudaSuccess && (pipelined || pipelined_w)) {
         cudaGetLastError();
         cudaEvent_t join = nullptr;
         if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess) {
