@@ -321,6 +321,7 @@ def run_own_arm(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")      # host-side barrier for the legs in which ONE rank drives the other ranks' GPUs
     from panda_b200 import gpu_ffi as ffi          # raises if libpanda-cuda.so is missing
     from panda_b200 import gpu_manager as gm
     from panda_b200.sharded import ShardedMsm, shard_range
@@ -566,12 +567,14 @@ def run_own_arm(args):
                 del bases_d, scal_d
                 torch.cuda.empty_cache()
             barrier()
+            # the waiting ranks must not sit in an NCCL barrier: its kernel spins on THEIR GPU, which rank 0 is driving here (the two
+            # processes' contexts would be time-sliced: measured 39.6 ms per MSM at N = 2 against 18.1 ms for the shards themselves)
             if rank == 0:
                 multi_capi = run_multi_capi(ffi, O, np, torch, n, world)
-            barrier()
+            dist.barrier(group=cpu_group)
         except Exception as exc:
             multi_capi = {"error": repr(exc)[:300]}
-            barrier()
+            dist.barrier(group=cpu_group)
         if rank == 0:
             assert ffi.lib.panda_set_device(local_rank) == 0
             assert ffi.lib.panda_msm_register_bases_bn254(bases_d.data_ptr(), n_local, ffi.PandaStream(stream)) == 0

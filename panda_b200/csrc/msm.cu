@@ -431,7 +431,6 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
     PB_CUDA(acquire_table(curve, bases, n, stream, table_mode, c_override, &table_ref, &tc, &table_n));
     const void *table = table_ref ? table_ref->ptr : nullptr;
     if (table) {
-        // per-stage timings are an attribution pass over the unsplit pipeline; the product path splits large jobs in two chunks
         const uint32_t chunks = (timings || class_log2) ? 1 : resident_chunks(n);
         MsmPlan p = msm_make_plan(curve, n, true, tc, seg_override, ~(size_t)0, chunks, class_log2);
         if (!p.c) return cudaErrorInvalidValue;
@@ -492,14 +491,15 @@ static cudaError_t copy_stream_for_current_device(cudaStream_t *out) { return si
 static cudaError_t aux_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(1, out); }
 static cudaError_t aux2_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(2, out); }   // second accumulation stream of the pipelined plan
 
-// chunks of a device-resident table-plan MSM: chunk q+1 sorts on the higher-priority auxiliary stream while chunk q accumulates, and every chunk's
-// scatter passes re-read only its own codes.  Measured (profiles/r2_sweep.md, product entry point): 2^24 38.4 vs 37.6 ms and 2^25 74.3 vs 73.6 ms
-// for 2 chunks vs 1 -- the second set of partial sums costs more than the overlap wins; 2^26 (where the scatter makes 32 passes over 3.2 GB of codes,
-// 16 % of the step) 143.8 ms with 4 chunks against 151.8 with 1 and 147.1 with 8.  PANDA_MSM_SPLIT = q forces q chunks (tests, tuning).
+// Point-range chunks of a device-resident table-plan MSM (chunk q+1 sorts while chunk q accumulates).  Round-2 history: 2 chunks lost at 2^24 / 2^25 (the
+// second set of partial sums costs more than the overlap wins) and 4 chunks won at 2^26 (143.8 ms against 151.8: 32 filter passes over 3.2 GB of codes);
+// the range pipeline now overlaps the sort WITHOUT a second set of partial sums (2^26: 125.5 ms), so resident jobs run as one chunk.
+// PANDA_MSM_SPLIT = q forces q chunks (tests, tuning).
 static uint32_t resident_chunks(uint32_t n) {
     static const int forced = [] { const char *v = getenv("PANDA_MSM_SPLIT"); return v ? atoi(v) : 0; }();
     if (forced > 0) return (uint32_t)forced;
-    return n >= (1u << 26) ? 4 : 1;
+    (void)n;
+    return 1;
 }
 
 cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_scalars, uint32_t n, void *result, CoordType coord,
