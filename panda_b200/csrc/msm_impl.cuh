@@ -30,6 +30,9 @@ struct Bls381 {
 
 static constexpr uint32_t DIGIT_SKIP = 0xFFFFu;     // digit 0: contributes nothing
 static constexpr int ACC_THREADS = 128;
+#ifndef PANDA_ACC_MAXNREG
+#define PANDA_ACC_MAXNREG 128     // k_accumulate_range: 4 CTAs per SM (16 warps); 136 (3 CTAs, room for a side-stream CTA beside them) measured 29.15 vs 28.38 ms at 2^24
+#endif
 static constexpr int RED_THREADS = 128;
 static constexpr int WIN_THREADS = 256;
 static constexpr int BIG_THREADS = 256;
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(64, 5) k_accumulate_wide(const uint8_t *__rest
 }
 
 template <class C>
-__global__ void __maxnreg__(136) k_accumulate_range(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
+__global__ void __maxnreg__(PANDA_ACC_MAXNREG) k_accumulate_range(const uint8_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                                  const uint32_t *__restrict__ offsets, uint32_t nb, uint32_t L, uint32_t segs_ps,
                                                                  uint32_t b_lo, uint32_t b_hi, uint8_t *__restrict__ slots) {
     accumulate_range_body<C>(bases, sorted, offsets, nb, L, segs_ps, b_lo, b_hi, slots);
@@ -871,7 +874,6 @@ template <class C>
 cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
                            cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed) {
     using Pt = Xyzz<typename C::Fq>;
-    const uint32_t n = p.n;
     uint8_t *ws = nullptr;
     if (pool) PB_CUDA(cudaMallocFromPoolAsync((void **)&ws, p.bytes, pool, stream));
     else PB_CUDA(cudaMallocAsync((void **)&ws, p.bytes, stream));

@@ -493,6 +493,24 @@ def test_range_pipeline_forced(ranges):
         assert "closed-form match: True" in out.stdout, out.stdout[-2000:]
 
 
+@pytest.mark.skipif(bool(__import__("os").environ.get("PANDA_TEST_NESTED")), reason="already inside the nested run")
+def test_table_plan_pipeline_on_edge_and_skew_cases():
+    """the edge-case, skew, arbitrary-count and oracle-sweep tests once more in a child process whose library builds a table at first sight
+    (PANDA_MSM_PRECOMPUTE=2) and cuts it into 8 bucket ranges (PANDA_MSM_PHASES=8): empty ranges, buckets whose segments straddle range
+    boundaries, oversized buckets and tiny jobs all go through the pipelined scatter / accumulation"""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PANDA_MSM_PRECOMPUTE="2", PANDA_MSM_PHASES="8", PANDA_TEST_NESTED="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_msm.py"), "-m", "gpu", "-x", "-q", "-k",
+                          "edge_cases or skewed_scalars or arbitrary_point_count or sweep_against_oracle or streamed_skew"],
+                         env=env, capture_output=True, text=True, timeout=1200, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-1000:]
+
+
 @pytest.mark.parametrize("curve,k,mode", [(0, 16, "uniform"), (0, 14, "all_equal"), (0, 14, "small"), (1, 13, "uniform")])
 def test_bucket_class_shards(oracle, dev, curve, k, mode):
     """panda_msm_execute_*_class: the class_count partials (each the buckets of one residue class) add up to the MSM, on registered bases
