@@ -1,7 +1,9 @@
 // msm.cu -- Pippenger MSM for sm_100a: signed-digit windows, counting sort of point indices by bucket,
 // load-balanced bucket accumulation (XYZZ mixed additions), parallel running-sum bucket reduction with
 // warp-shuffle stitching, on-device window combination; for bases that are reused across calls, a table of
-// 2^(c*j) * P multiples folds all windows into one bucket set.  See msm.cuh / DESIGN.md.
+// 2^(c*j) * P multiples folds all windows into one bucket set.  The sort is off the critical path: the digit codes leave the first
+// kernel grouped by bucket range, and the scatter of one range (L2-atomic bound) runs on a side stream beside the accumulation of
+// another (integer-pipe bound); the windowed plan pipelines window by window the same way.  See msm.cuh / DESIGN.md.
 //
 // Replaces src/cuda/core/unit/msm/msm_cuda.cuh:552-769 of the reference (kernels :148-282, :373-497 and
 // the host-side Horner :59-77).  Written from scratch for B200; nothing here is derived from that code.
