@@ -102,13 +102,14 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     // chunks (folded only): every chunk is a physical bucket set of its own (counts, sorted list, partial slots); the bucket
     // reduction merges the chunks of a logical set
     p.chunks = folded ? std::max<uint32_t>(1, std::min<uint32_t>(chunks, std::max<uint32_t>(1, n / 4096))) : 1;
-    // Chunk sizes grow geometrically.  The first chunk is short (its upload is exposed); chunk q+1 is uploaded (0.58 us per 1000 scalars over
-    // PCIe 5) and sorted (0.26) while the chunks before it accumulate (1.78), so it can be as long as n_{q+1} <= 1.43 * (n_0 + .. + n_q) without
-    // leaving the integer pipe idle: sizes 1 : 1.43 : 3.5 : 8.4 : 20.5 (every chunk is (growth - 1) = 1.43 times the sum of its predecessors).
-    // PANDA_MSM_CHUNK_GROWTH overrides growth = 2.43.
+    // Chunk sizes grow geometrically: every chunk is (growth - 1) times the sum of its predecessors (1 : 3 : 12 for three chunks).  The first
+    // chunk is short (its upload is exposed: 0.58 us per 1000 scalars over PCIe 5); a later chunk is uploaded and recoded in sub-chunks while
+    // its predecessors accumulate (1.7 us per 1000 points), so it may be about three times as long as everything before it before the
+    // integer pipe would have to wait for it.  Measured at 2^24 (profiles/r2_msm_pipeline.md): growth 2.43 / 3.2 / 4.0 37.1 / 37.0 / 36.6 ms
+    // end to end with three chunks.  PANDA_MSM_CHUNK_GROWTH overrides growth = 4.
     p.chunk_begin[0] = 0;
     if (p.chunks > 1) {
-        static const double growth = [] { const char *e = getenv("PANDA_MSM_CHUNK_GROWTH"); const double v = e ? atof(e) : 0.0; return v >= 1.0 ? v : 2.43; }();
+        static const double growth = [] { const char *e = getenv("PANDA_MSM_CHUNK_GROWTH"); const double v = e ? atof(e) : 0.0; return v >= 1.0 ? v : 4.0; }();
         p.chunks = std::min<uint32_t>(p.chunks, MSM_MAX_CHUNKS);
         double total = 0, wq = 1.0, acc = 0;
         for (uint32_t q = 0; q < p.chunks; q++) { total += q == 0 ? 1.0 : wq; if (q == 0) wq = growth - 1.0; else wq *= growth; }
@@ -411,10 +412,9 @@ static cudaError_t acquire_table(CurveId curve, const void *bases, uint32_t n, c
     return cudaSuccess;
 }
 
-static cudaError_t aux_stream_for_current_device(cudaStream_t *out);
-static cudaError_t aux2_stream_for_current_device(cudaStream_t *out);
 static cudaError_t side_stream_for_current_device(int which, cudaStream_t *out);
 static uint32_t resident_chunks(uint32_t n);
+static cudaError_t side_streams(MsmFeed *feed);      // the current device's four side streams into feed->aux*_stream
 
 cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint32_t n, void *result, CoordType coord,
                     cudaMemPool_t pool, cudaStream_t stream, uint32_t c_override, uint32_t seg_override, MsmStageTimes *timings, int table_mode,
@@ -439,19 +439,15 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
         p.table_n = table_n;
         p.class_index = class_index;
         if (p.chunks > 1) {
-            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-            PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
-            PB_CUDA(aux2_stream_for_current_device(&feed.aux2_stream));
+            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            PB_CUDA(side_streams(&feed));
             return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, nullptr, &feed);
         }
         // one chunk, several scatter ranges: range r+1 is scattered while range r is accumulated (PANDA_MSM_PIPELINE=0: one launch each)
         static const bool pipeline_on = [] { const char *v = getenv("PANDA_MSM_PIPELINE"); return !v || atoi(v) != 0; }();
         if (pipeline_on && p.phases > 1) {
-            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-            PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
-            PB_CUDA(aux2_stream_for_current_device(&feed.aux2_stream));
-            PB_CUDA(side_stream_for_current_device(3, &feed.aux3_stream));
-            PB_CUDA(side_stream_for_current_device(4, &feed.aux4_stream));
+            MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            PB_CUDA(side_streams(&feed));
             return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings, &feed);
         }
         return run_pipeline(curve, p, table, scalars, result, coord, pool, stream, timings);
@@ -462,11 +458,8 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
     // windowed plan: window w+1 is scattered while window w is accumulated, from 2^22 sorted entries (a window is then a wave of segments or more)
     static const bool pipeline_on = [] { const char *v = getenv("PANDA_MSM_PIPELINE"); return !v || atoi(v) != 0; }();
     if (pipeline_on && ((uint64_t)n * p.windows >> class_log2) >= ((uint64_t)1 << 22)) {
-        MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-        PB_CUDA(aux_stream_for_current_device(&feed.aux_stream));
-        PB_CUDA(aux2_stream_for_current_device(&feed.aux2_stream));
-        PB_CUDA(side_stream_for_current_device(3, &feed.aux3_stream));
-        PB_CUDA(side_stream_for_current_device(4, &feed.aux4_stream));
+        MsmFeed feed{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        PB_CUDA(side_streams(&feed));
         return run_pipeline(curve, p, bases, scalars, result, coord, pool, stream, timings, &feed);
     }
     return run_pipeline(curve, p, bases, scalars, result, coord, pool, stream, timings);
@@ -476,7 +469,7 @@ cudaError_t msm_run(CurveId curve, const void *bases, const void *scalars, uint3
 // caller's priority, created on first use
 static cudaError_t side_stream_for_current_device(int which, cudaStream_t *out) {
     static std::mutex m;
-    static cudaStream_t streams[5][64] = {};
+    static cudaStream_t streams[6][64] = {};
     int dev = 0;
     PB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
@@ -484,14 +477,20 @@ static cudaError_t side_stream_for_current_device(int which, cudaStream_t *out) 
     if (!streams[which][dev]) {
         int least = 0, greatest = 0;                       // the auxiliary compute stream outranks the caller's stream, so that its
         PB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));   // (small) sort CTAs slot in between the accumulation CTAs
-        PB_CUDA(cudaStreamCreateWithPriority(&streams[which][dev], cudaStreamNonBlocking, which == 1 ? greatest : least));
+        PB_CUDA(cudaStreamCreateWithPriority(&streams[which][dev], cudaStreamNonBlocking, (which == 1 || which == 5) ? greatest : least));
     }
     *out = streams[which][dev];
     return cudaSuccess;
 }
 static cudaError_t copy_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(0, out); }
-static cudaError_t aux_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(1, out); }
-static cudaError_t aux2_stream_for_current_device(cudaStream_t *out) { return side_stream_for_current_device(2, out); }   // second accumulation stream of the pipelined plan
+static cudaError_t side_streams(MsmFeed *feed) {
+    PB_CUDA(side_stream_for_current_device(1, &feed->aux_stream));
+    PB_CUDA(side_stream_for_current_device(2, &feed->aux2_stream));
+    PB_CUDA(side_stream_for_current_device(3, &feed->aux3_stream));
+    PB_CUDA(side_stream_for_current_device(4, &feed->aux4_stream));
+    PB_CUDA(side_stream_for_current_device(5, &feed->dig_stream));
+    return cudaSuccess;
+}
 
 // Point-range chunks of a device-resident table-plan MSM (chunk q+1 sorts while chunk q accumulates).  Round-2 history: 2 chunks lost at 2^24 / 2^25 (the
 // second set of partial sums costs more than the overlap wins) and 4 chunks won at 2^26 (143.8 ms against 151.8: 32 filter passes over 3.2 GB of codes);
@@ -525,10 +524,9 @@ cudaError_t msm_run_streamed(CurveId curve, const void *bases, const void *host_
         uint32_t chunks = chunks_override ? chunks_override : forced ? forced : (n >= (1u << 19) ? 3 : 1);
         MsmPlan p = msm_make_plan(curve, n, true, tc, 0, ~(size_t)0, chunks);
         p.table_n = table_n;
-        MsmFeed feed{host_scalars, d_scal, nullptr, nullptr, nullptr, nullptr, nullptr};
+        MsmFeed feed{host_scalars, d_scal, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         e = copy_stream_for_current_device(&feed.copy_stream);
-        if (e == cudaSuccess) e = aux_stream_for_current_device(&feed.aux_stream);
-        if (e == cudaSuccess) e = aux2_stream_for_current_device(&feed.aux2_stream);
+        if (e == cudaSuccess) e = side_streams(&feed);
         if (e == cudaSuccess) e = run_pipeline(curve, p, table, d_scal, result, coord, pool, stream, nullptr, &feed);
     } else {
         e = cudaMemcpyAsync(d_scal, host_scalars, (size_t)n * 32, cudaMemcpyHostToDevice, stream);

@@ -56,7 +56,9 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
 // aux_stream != nullptr: odd chunks run on it, so that one chunk's sort overlaps the previous chunk's accumulation.
 // aux2_stream (with aux_stream, one resident chunk, several scatter ranges): the scatter of bucket range r+1 runs on aux_stream while range r
 // is accumulated; the accumulation launches rotate over the caller's stream and aux2 .. aux4_stream.
-struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; cudaStream_t aux_stream; cudaStream_t aux2_stream; cudaStream_t aux3_stream; cudaStream_t aux4_stream; };
+// dig_stream (high priority like aux_stream): digits and scan of the chunks of a streamed MSM, so that chunk q+1 is recoded as it arrives while chunk q's
+// ranges are still being scattered on aux_stream.
+struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; cudaStream_t aux_stream; cudaStream_t aux2_stream; cudaStream_t aux3_stream; cudaStream_t aux4_stream; cudaStream_t dig_stream; };
 
 // Per-stage device timings (ms) filled when msm_run is called with timings != nullptr (adds event syncs;
 // the benchmark harness uses it to attribute time to kernels -- never set on the product path).

@@ -106,86 +106,85 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
 // K2a/b/c: exclusive scan of the bucket counts of every bucket set -> offsets[set][0..nb], cursor[set][0..nb-1].
 // Three small launches (tile sums, scan of the tile sums, apply) so that a 2^21-bucket set is scanned by 512 CTAs.
 // Buckets whose entries span more than BIG_SPAN accumulation segments are appended to big_list.
-static constexpr uint32_t SCAN_TILE = 4096;
+// 256-thread CTAs: in a streamed MSM these kernels start while an earlier chunk's accumulation fills every SM's register file, and a CTA
+// of 1024 threads had to wait for two accumulation CTAs of one SM to retire (traced: 0.5 ms for a 30-microsecond scan).
+static constexpr uint32_t SCAN_TILE = 4096, SCAN_THREADS = 256, SCAN_PER = SCAN_TILE / SCAN_THREADS;
 
-static __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t tiles_ps, uint32_t *__restrict__ tile_sums) {
+// block-wide inclusive scan of one value per thread (SCAN_THREADS threads); returns the inclusive prefix, *total the block sum
+PB_DEV uint32_t scan_block_incl(uint32_t v, uint32_t *warp_tot, uint32_t *total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t t = lane < SCAN_THREADS / 32 ? warp_tot[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, t, o); if ((int)lane >= o) t += u; }
+        warp_tot[lane] = t;
+    }
+    __syncthreads();
+    *total = warp_tot[SCAN_THREADS / 32 - 1];
+    return incl + (warp ? warp_tot[warp - 1] : 0);
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t tiles_ps, uint32_t *__restrict__ tile_sums) {
     __shared__ uint32_t warp_tot[32];
     const uint32_t set = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const uint32_t *cw = counts + (size_t)set * nb;
     uint32_t v = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { const uint32_t idx = tile * SCAN_TILE + k * 1024 + tid; if (idx < nb) v += cw[idx]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((tid & 31) == 0) warp_tot[tid >> 5] = v;
-    __syncthreads();
-    if (tid < 32) {
-        v = warp_tot[tid];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (tid == 0) tile_sums[(size_t)set * tiles_ps + tile] = v;
-    }
+    for (uint32_t k = 0; k < SCAN_PER; k++) { const uint32_t idx = tile * SCAN_TILE + k * SCAN_THREADS + tid; if (idx < nb) v += cw[idx]; }
+    uint32_t total;
+    scan_block_incl(v, warp_tot, &total);
+    if (tid == 0) tile_sums[(size_t)set * tiles_ps + tile] = total;
 }
 
 // one CTA per set: exclusive scan of its (<= 1024) tile sums in place; the set total goes to offsets[set][nb]
-static __global__ void __launch_bounds__(1024) k_scan_tops(uint32_t *__restrict__ tile_sums, uint32_t tiles_ps, uint32_t nb, uint32_t *__restrict__ offsets) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tops(uint32_t *__restrict__ tile_sums, uint32_t tiles_ps, uint32_t nb, uint32_t *__restrict__ offsets) {
     __shared__ uint32_t warp_tot[32];
-    const uint32_t set = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t set = blockIdx.x, tid = threadIdx.x;
     uint32_t *ts = tile_sums + (size_t)set * tiles_ps;
-    const uint32_t v = tid < tiles_ps ? ts[tid] : 0;
-    uint32_t incl = v;
+    uint32_t v4[4], v = 0;                                      // thread owns 4 consecutive tile sums
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t t = warp_tot[lane];
+    for (int k = 0; k < 4; k++) { const uint32_t idx = tid * 4 + k; v4[k] = idx < tiles_ps ? ts[idx] : 0; v += v4[k]; }
+    uint32_t total;
+    uint32_t excl = scan_block_incl(v, warp_tot, &total) - v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, t, o); if ((int)lane >= o) t += u; }
-        warp_tot[lane] = t;
-    }
-    __syncthreads();
-    const uint32_t excl = (warp ? warp_tot[warp - 1] : 0) + incl - v;
-    if (tid < tiles_ps) ts[tid] = excl;
-    if (tid == 0) offsets[(size_t)set * (nb + 1) + nb] = warp_tot[31];
+    for (int k = 0; k < 4; k++) { const uint32_t idx = tid * 4 + k; if (idx < tiles_ps) ts[idx] = excl; excl += v4[k]; }
+    if (tid == 0) offsets[(size_t)set * (nb + 1) + nb] = total;
 }
 
-static __global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ tile_sums, uint32_t nb,
-                                                            uint32_t tiles_ps, uint32_t L, uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
-                                                            uint32_t *__restrict__ big_count, uint32_t *__restrict__ big_list) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ tile_sums, uint32_t nb,
+                                                                    uint32_t tiles_ps, uint32_t L, uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor,
+                                                                    uint32_t *__restrict__ big_count, uint32_t *__restrict__ big_list) {
     __shared__ uint32_t warp_tot[32];
-    const uint32_t set = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t set = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const uint32_t *cw = counts + (size_t)set * nb;
     uint32_t *ow = offsets + (size_t)set * (nb + 1);
     uint32_t *kw = cursor + (size_t)set * nb;
-    // thread owns 4 consecutive counts
-    const uint32_t base = tile * SCAN_TILE + tid * 4;
-    uint32_t c4[4];
+    // thread owns SCAN_PER consecutive counts
+    const uint32_t base = tile * SCAN_TILE + tid * SCAN_PER;
+    uint32_t cN[SCAN_PER], v = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) c4[k] = base + k < nb ? cw[base + k] : 0;
-    const uint32_t v = c4[0] + c4[1] + c4[2] + c4[3];
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t t = warp_tot[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, t, o); if ((int)lane >= o) t += u; }
-        warp_tot[lane] = t;
+    for (uint32_t k = 0; k < SCAN_PER; k += 4) {
+        if (base + k + 3 < nb) { const uint4 q = *reinterpret_cast<const uint4 *>(cw + base + k); cN[k] = q.x; cN[k + 1] = q.y; cN[k + 2] = q.z; cN[k + 3] = q.w; }
+        else { for (uint32_t j = 0; j < 4; j++) cN[k + j] = base + k + j < nb ? cw[base + k + j] : 0; }
     }
-    __syncthreads();
-    uint32_t excl = tile_sums[(size_t)set * tiles_ps + tile] + (warp ? warp_tot[warp - 1] : 0) + incl - v;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (uint32_t k = 0; k < SCAN_PER; k++) v += cN[k];
+    uint32_t total;
+    uint32_t excl = tile_sums[(size_t)set * tiles_ps + tile] + scan_block_incl(v, warp_tot, &total) - v;
+#pragma unroll
+    for (uint32_t k = 0; k < SCAN_PER; k++) {
         const uint32_t idx = base + k;
         if (idx < nb) {
             ow[idx] = excl;
             if (cursor) kw[idx] = excl;
-            if (big_count && c4[k] && (excl + c4[k] - 1) / L - excl / L + 1 > BIG_SPAN) big_list[atomicAdd(big_count, 1u)] = set * nb + idx;
+            if (big_count && cN[k] && (excl + cN[k] - 1) / L - excl / L + 1 > BIG_SPAN) big_list[atomicAdd(big_count, 1u)] = set * nb + idx;
         }
-        excl += c4[k];
+        excl += cN[k];
     }
 }
 
@@ -890,182 +889,171 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
     StageTimer tm(timings != nullptr && p.chunks == 1, stream);
     TraceLog trace;
     trace.mark("start", 0, stream);
-    // Streams by role.  Several chunks: every chunk's sort (digits, scan, scatter -- L2-atomic bound) runs on the high-priority stream `aux` as soon
-    // as its scalars are there, the accumulations (integer-pipe bound) alternate between the caller's stream and `aux2`, so that one chunk's tail
-    // overlaps the next one's head and a sort never queues behind an accumulation.  One resident chunk with several scatter ranges: the same
-    // roles range by range (`pipelined`).
-    // events: `fed` orders the copy stream and the side streams against `stream`; `sorted_ev` hands a sorted chunk / range to its accumulation;
-    // `aux_done` joins `aux2` back into `stream`
+    // Streams by role (feed != nullptr carries the library's per-device side streams).  The sort of a chunk (digits, scan, scatter -- L2-atomic
+    // bound) runs on the high-priority stream `side[0]` (digits and scan of a single resident chunk stay on the caller's stream: nothing could
+    // overlap them), the accumulations (integer-pipe bound) rotate over the caller's stream and side[1..3], so that one launch's tail overlaps
+    // the next one's head and a sort never queues behind an accumulation.  Table plan with several bucket ranges: scatter and accumulation go
+    // range by range (the scatter of one range beside the accumulation of another); windowed plan: window by window; several chunks
+    // (streamed scalars): chunk after chunk, every chunk uploaded and recoded in sub-chunks so that its digits trail its upload closely.
+    // events: `fed` orders the copy stream and the side streams against `stream` / a sub-chunk's upload against its digit kernel; `sorted_ev`
+    // hands a scattered range / window / chunk to its accumulation; `aux_done` joins the accumulation streams back into `stream`
     cudaEvent_t fed = nullptr, sorted_ev = nullptr, aux_done = nullptr;
     const bool uploading = feed && feed->host_scalars;
-    cudaStream_t aux = (feed && p.chunks > 1 && feed->aux_stream && feed->aux2_stream) ? feed->aux_stream : nullptr;
-    cudaStream_t aux2 = aux ? feed->aux2_stream : nullptr;
-    // one resident chunk, several scatter ranges: scatter and accumulation are pipelined range by range over two side streams
-    cudaStream_t pipe = nullptr, pipe2 = nullptr, pipe3 = nullptr, pipe4 = nullptr;
-    if (feed && p.chunks == 1 && p.folded && p.phases > 1 && !uploading) {
-        pipe = feed->aux_stream; pipe2 = feed->aux2_stream; pipe3 = feed->aux3_stream; pipe4 = feed->aux4_stream;
-    }
-    const bool pipelined = pipe && pipe2 && pipe3 && pipe4;
-    // windowed plan (one bucket set per window): the same pipeline window by window
-    const bool pipelined_w = feed && !pipelined && p.chunks == 1 && !p.folded && p.windows > 1 && !uploading && feed->aux_stream && feed->aux2_stream &&
-                             feed->aux3_stream && feed->aux4_stream;
-    if (pipelined_w) { pipe = feed->aux_stream; pipe2 = feed->aux2_stream; pipe3 = feed->aux3_stream; pipe4 = feed->aux4_stream; }
+    const bool have_side = feed && feed->aux_stream && feed->aux2_stream && feed->aux3_stream && feed->aux4_stream;
+    const bool chunked = have_side && p.chunks > 1;
+    const bool ranged = have_side && p.folded && p.phases > 1;                    // range by range
+    const bool windowed_pipe = have_side && !p.folded && p.windows > 1 && p.chunks == 1;   // window by window
+    const bool multi = chunked || ranged || windowed_pipe;                        // more than the caller's stream is in play
+    cudaStream_t side0 = have_side ? feed->aux_stream : nullptr;
+    cudaStream_t sdig = have_side && feed->dig_stream ? feed->dig_stream : side0;   // digits + scan of a chunked run (scatters stay on side0)
+    cudaStream_t acc_streams[4] = {stream, have_side ? feed->aux2_stream : stream, have_side ? feed->aux3_stream : stream, have_side ? feed->aux4_stream : stream};
+    uint32_t acc_launch = 0;                                                      // rotates the accumulation launches over acc_streams
     cudaError_t err = cudaSuccess;
     do {
         if ((err = cudaMemsetAsync(counts, 0, (phys * p.nb + p.chunks) * 4, stream)) != cudaSuccess) break;
-        if (pipelined || pipelined_w || uploading || aux) {
+        if (multi || uploading) {
             if ((err = cudaEventCreateWithFlags(&fed, cudaEventDisableTiming)) != cudaSuccess) break;
             if ((err = cudaEventCreateWithFlags(&sorted_ev, cudaEventDisableTiming)) != cudaSuccess) break;
             if ((err = cudaEventCreateWithFlags(&aux_done, cudaEventDisableTiming)) != cudaSuccess) break;
-        }
-        if (uploading || aux) {
             // the workspace / staging buffer were allocated in stream order on `stream`: other streams may only touch them from here on
             if ((err = cudaEventRecord(fed, stream)) != cudaSuccess) break;
             if (uploading && (err = cudaStreamWaitEvent(feed->copy_stream, fed, 0)) != cudaSuccess) break;
-            if (aux && (err = cudaStreamWaitEvent(aux, fed, 0)) != cudaSuccess) break;
-            if (aux2 && (err = cudaStreamWaitEvent(aux2, fed, 0)) != cudaSuccess) break;
+            if (multi) {
+                if ((err = cudaStreamWaitEvent(side0, fed, 0)) != cudaSuccess) break;
+                if (sdig != side0 && (err = cudaStreamWaitEvent(sdig, fed, 0)) != cudaSuccess) break;
+                for (int j = 1; j < 4 && err == cudaSuccess; j++) err = cudaStreamWaitEvent(acc_streams[j], fed, 0);
+                if (err != cudaSuccess) break;
+            }
         }
+        // kernels that run beside an accumulation (every chunk but the first; every scatter range but the first) get small grids: their
+        // warps mostly wait for L2 atomics, and each CTA that becomes resident displaces accumulation warps that would keep the integer pipe
+        // busy.  Too few, and the sort of the next chunk is late (a CTA beside the accumulation CTAs gets a small share of the issue
+        // slots).  Measured at 2^24 (profiles/r2_msm_pipeline.md): scatter 2 CTAs per SM, digits 4; the range pipeline's scatters 1.
+        static const uint32_t side_ctas = [] { const char *e = getenv("PANDA_MSM_SIDE_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 296u; }();
+        static const uint32_t side_digit_ctas = [] { const char *e = getenv("PANDA_MSM_SIDE_DIGITS"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 592u; }();
+        uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;        // table plan: buckets per scatter range
+        const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
         for (uint32_t q = 0; q < p.chunks && err == cudaSuccess; q++) {
-            cudaStream_t sq = aux ? aux : stream;                             // this chunk's sort ...
-            cudaStream_t sa = aux ? ((q & 1) ? aux2 : stream) : stream;       // ... and its accumulation
+            cudaStream_t sq = chunked ? sdig : stream;                        // digits and scan of this chunk
             const uint32_t point0 = p.chunk_begin[q], nq = p.chunk_begin[q + 1] - point0;
             const size_t set0 = (size_t)q * p.sets;                           // first physical set of this chunk
             const uint32_t *sc = (const uint32_t *)scalars + (size_t)point0 * 8;
-            if (uploading) {
-                if ((err = cudaMemcpyAsync((uint8_t *)feed->dev_scalars + (size_t)point0 * 32, (const uint8_t *)feed->host_scalars + (size_t)point0 * 32,
-                                           (size_t)nq * 32, cudaMemcpyHostToDevice, feed->copy_stream)) != cudaSuccess) break;
-                if ((err = cudaEventRecord(fed, feed->copy_stream)) != cudaSuccess) break;
-                trace.mark("uploaded", q, feed->copy_stream);
-                if ((err = cudaStreamWaitEvent(sq, fed, 0)) != cudaSuccess) break;
-            }
             uint32_t *counts_q = counts + set0 * p.nb, *offsets_q = offsets + set0 * (p.nb + 1), *cursor_q = cursor + set0 * p.nb;
             uint32_t *big_count_q = big_counts + q, *big_list_q = big_list + set0 * p.nb, *tiles_q = tile_sums + set0 * tiles_ps;
             uint8_t *codes_q = digits + (size_t)q * p.codes_stride * 4;      // folded: 32-bit codes of this chunk, tile by tile (chunks == 1 otherwise)
             uint16_t *heads_q = (uint16_t *)(ws + p.off_heads) + (size_t)q * p.heads_stride;
-            uint32_t log2_span = 0; while ((p.nb >> log2_span) > p.phases) log2_span++;        // table plan: buckets per scatter range
-            // kernels that run beside an accumulation (every chunk but the first; every scatter range but the first) get small grids: their
-            // warps mostly wait for L2 atomics, and each CTA that becomes resident displaces accumulation warps that would keep the integer pipe
-            // busy.  Too few, and the sort of the next chunk is late (a CTA beside three accumulation CTAs gets a small share of the issue
-            // slots).  Measured at 2^24 (profiles/r2_msm_pipeline.md): scatter 2 CTAs per SM, digits 4; the range pipeline's scatters 1.
-            static const uint32_t side_ctas = [] { const char *e = getenv("PANDA_MSM_SIDE_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 296u; }();
-            static const uint32_t side_digit_ctas = [] { const char *e = getenv("PANDA_MSM_SIDE_DIGITS"); const int v = e ? atoi(e) : 0; return v > 0 ? (uint32_t)v : 592u; }();
-            const uint32_t cta_cap = (aux && q > 0) ? side_ctas : 148 * 8;
-            const uint32_t digit_cap = (aux && q > 0) ? side_digit_ctas : 148 * 8;
-            const uint32_t scat_blocks = std::min<uint32_t>(((nq + TILE_PTS - 1) / TILE_PTS + 7) / 8, cta_cap);
             uint32_t *sorted_q = sorted + set0 * p.stride;
             uint8_t *slots_q = slots + set0 * slot_stride;
-            tm.mark();
-            trace.mark("sort begins", q, sq);
+            const bool beside = chunked && q > 0;                             // an earlier chunk is accumulating while this one sorts
+            const uint32_t digit_cap = beside ? side_digit_ctas : 148 * 8, cta_cap = beside ? side_ctas : 148 * 8;
             const uint32_t sblocks = std::min<uint32_t>((nq + 255) / 256, cta_cap);
-            if (p.folded) {
-                const size_t sh_bytes = ((size_t)(p.phases + 2 * p.windows) * TILE_PTS + 40) * 4;
-                if (sh_bytes > 48 * 1024 && (err = cudaFuncSetAttribute(k_digits_tiled<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes)) != cudaSuccess) break;
-                const uint32_t tblocks = std::min<uint32_t>((nq + TILE_PTS - 1) / TILE_PTS, digit_cap);
-                k_digits_tiled<C><<<tblocks, TILE_PTS, sh_bytes, sq>>>(sc, nq, p.c, p.windows, p.wide, log2_span, p.phases, p.class_log2, p.class_index,
-                                                                      (uint32_t *)codes_q, heads_q, counts_q);
+            const uint32_t scat_blocks = std::min<uint32_t>(((nq + TILE_PTS - 1) / TILE_PTS + 7) / 8, cta_cap);
+            tm.mark();
+            // ---- digits (+ upload): a streamed chunk arrives in up to eight sub-chunks of whole tiles, each recoded as soon as it is there
+            const uint32_t subs = (uploading && p.folded) ? (nq >= (1u << 23) ? 8 : nq >= (1u << 20) ? 4 : 1) : 1;
+            for (uint32_t j = 0; j < subs && err == cudaSuccess; j++) {
+                const uint32_t t0 = (uint32_t)(((uint64_t)((nq + TILE_PTS - 1) / TILE_PTS) * j / subs) * TILE_PTS);
+                const uint32_t t1 = j + 1 == subs ? nq : (uint32_t)(((uint64_t)((nq + TILE_PTS - 1) / TILE_PTS) * (j + 1) / subs) * TILE_PTS);
+                if (t1 <= t0) continue;
+                if (uploading) {
+                    if ((err = cudaMemcpyAsync((uint8_t *)feed->dev_scalars + (size_t)(point0 + t0) * 32, (const uint8_t *)feed->host_scalars + (size_t)(point0 + t0) * 32,
+                                               (size_t)(t1 - t0) * 32, cudaMemcpyHostToDevice, feed->copy_stream)) != cudaSuccess) break;
+                    if ((err = cudaEventRecord(fed, feed->copy_stream)) != cudaSuccess) break;
+                    trace.mark("uploaded", q, feed->copy_stream);
+                    if ((err = cudaStreamWaitEvent(sq, fed, 0)) != cudaSuccess) break;
+                }
+                if (j == 0) trace.mark("sort begins", q, sq);
+                if (p.folded) {
+                    const size_t sh_bytes = ((size_t)(p.phases + 2 * p.windows) * TILE_PTS + 40) * 4;
+                    if (sh_bytes > 48 * 1024 && (err = cudaFuncSetAttribute(k_digits_tiled<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes)) != cudaSuccess) break;
+                    const uint32_t tile0 = t0 / TILE_PTS;
+                    const uint32_t tblocks = std::min<uint32_t>((t1 - t0 + TILE_PTS - 1) / TILE_PTS, digit_cap);
+                    k_digits_tiled<C><<<tblocks, TILE_PTS, sh_bytes, sq>>>(sc + (size_t)t0 * 8, t1 - t0, p.c, p.windows, p.wide, log2_span, p.phases, p.class_log2, p.class_index,
+                                                                          (uint32_t *)codes_q + (size_t)tile0 * TILE_PTS * p.windows, heads_q + (size_t)tile0 * (p.phases + 1), counts_q);
+                } else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, codes_q, counts_q);
             }
-            else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, codes_q, counts_q);
+            if (err != cudaSuccess) break;
             tm.mark();
             trace.mark("digits done", q, sq);
-            k_scan_tiles<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, p.nb, tiles_ps, tiles_q);
-            k_scan_tops<<<p.sets, 1024, 0, sq>>>(tiles_q, tiles_ps, p.nb, offsets_q);
-            k_scan_apply<<<dim3(tiles_ps, p.sets), 1024, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q, big_count_q, big_list_q);
+            k_scan_tiles<<<dim3(tiles_ps, p.sets), SCAN_THREADS, 0, sq>>>(counts_q, p.nb, tiles_ps, tiles_q);
+            k_scan_tops<<<p.sets, SCAN_THREADS, 0, sq>>>(tiles_q, tiles_ps, p.nb, offsets_q);
+            k_scan_apply<<<dim3(tiles_ps, p.sets), SCAN_THREADS, 0, sq>>>(counts_q, tiles_q, p.nb, tiles_ps, p.seg_len, offsets_q, cursor_q, big_count_q, big_list_q);
             tm.mark();
             trace.mark("scanned", q, sq);
-            if (pipelined) {
-                // bucket range r is scattered on the high-priority stream `pipe` while the ranges before it are being accumulated; the accumulation
-                // launches rotate over four streams so that the tail of one overlaps the head of the next ones (they are independent)
-                const uint32_t span = 1u << log2_span, ranges = p.phases;
-                if ((err = cudaEventRecord(fed, sq)) != cudaSuccess) break;                    // scan done (and workspace allocated)
-                if ((err = cudaStreamWaitEvent(pipe, fed, 0)) != cudaSuccess) break;
-                if ((err = cudaStreamWaitEvent(pipe2, fed, 0)) != cudaSuccess) break;
-                if ((err = cudaStreamWaitEvent(pipe3, fed, 0)) != cudaSuccess) break;
-                if ((err = cudaStreamWaitEvent(pipe4, fed, 0)) != cudaSuccess) break;
-                cudaStream_t acc_streams[4] = {sq, pipe2, pipe3, pipe4};      // small ranges are a fraction of a wave each: up to four run side by side
-                const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
-                const uint32_t all_blocks = ((p.segs_ps >> p.class_log2) + acc_threads - 1) / acc_threads + 1;   // expected segments (a class shard keeps 1 / 2^class_log2 of the entries)
+            // ---- scatter + accumulation
+            cudaStream_t ss = multi ? side0 : stream;                          // scatters
+            if (multi && ss != sq) {                                           // (single resident chunk: digits and scan ran on the caller's stream)
+                if ((err = cudaEventRecord(fed, sq)) != cudaSuccess) break;
+                if ((err = cudaStreamWaitEvent(ss, fed, 0)) != cudaSuccess) break;
+            }
+            auto hand_over = [&](cudaStream_t sa) -> cudaError_t {             // what `ss` has scattered so far may be accumulated on `sa`
+                if (sa == ss) return cudaSuccess;
+                cudaError_t e = cudaEventRecord(sorted_ev, ss);
+                return e != cudaSuccess ? e : cudaStreamWaitEvent(sa, sorted_ev, 0);
+            };
+            if (ranged) {
                 // The balanced windows make the ranges uneven: the (W - wide) narrow windows only reach the lower half of the buckets, so with
                 // uniform scalars a lower-half range holds (2 W - wide) / wide times the entries of an upper-half one (7 x at 2^24).  The ranges
                 // are processed from the top one downwards (k_accumulate_range's ownership rule): the small ones go first, the exposed scatter is
                 // a small one, and every launch gets the grid its expected share asks for -- the kernel is grid-stride, so other digit
                 // distributions only cost balance, not correctness.
+                const uint32_t span = 1u << log2_span, ranges = p.phases;
+                const uint32_t chunk_segs = ((uint32_t)(((uint64_t)nq * p.windows) >> p.class_log2) + p.seg_len - 1) / p.seg_len;   // expected segments of this chunk
+                const uint32_t all_blocks = (chunk_segs + acc_threads - 1) / acc_threads + 1;
                 for (uint32_t k = 0; k < ranges && err == cudaSuccess; k++) {
                     const uint32_t r = ranges - 1 - k;
                     const double share = ((double)p.wide + (r < ranges / 2 || ranges == 1 ? 2.0 * (p.windows - p.wide) : 0.0)) / ((double)p.windows * ranges);
                     const uint32_t blocks = std::min<uint32_t>(all_blocks, (uint32_t)((double)all_blocks * share * 1.03) + 8);
-                    k_scatter_tiled<<<dim3(k ? std::min(scat_blocks, side_ctas / 2) : scat_blocks, 1), 256, 0, pipe>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, r, cursor_q, sorted_q);
-                    if ((err = cudaEventRecord(sorted_ev, pipe)) != cudaSuccess) break;
-                    cudaStream_t sa = acc_streams[k & 3];
-                    if ((err = cudaStreamWaitEvent(sa, sorted_ev, 0)) != cudaSuccess) break;
-                    if (k == 0) tm.mark();                                                     // "scatter" = the exposed first range
+                    const uint32_t grid = (k == 0 && q == 0) ? scat_blocks : std::min(scat_blocks, chunked ? side_ctas : side_ctas / 2);
+                    k_scatter_tiled<<<dim3(grid, 1), 256, 0, ss>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, r, cursor_q, sorted_q);
+                    cudaStream_t sa = acc_streams[acc_launch++ & 3];
+                    if ((err = hand_over(sa)) != cudaSuccess) break;
+                    if (k == 0) { tm.mark(); trace.mark("first range", q, sa); }   // "scatter" = the exposed first range
                     if (C::Fq::N > 8) k_accumulate_range_wide<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.nb, p.seg_len, p.segs_ps, r * span, (r + 1) * span, slots_q);
                     else k_accumulate_range<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.nb, p.seg_len, p.segs_ps, r * span, (r + 1) * span, slots_q);
                 }
-                if (err != cudaSuccess) break;
-                for (int j = 1; j < 4 && err == cudaSuccess; j++) {
-                    if ((err = cudaEventRecord(aux_done, acc_streams[j])) != cudaSuccess) break;
-                    err = cudaStreamWaitEvent(sq, aux_done, 0);
-                }
-                if (err != cudaSuccess) break;
-                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
-                tm.mark();
-                err = cudaGetLastError();
-                continue;
-            } else if (pipelined_w) {
-                // windowed plan: window w+1 is scattered on `pipe` while window w is accumulated; accumulations rotate over four streams
-                if ((err = cudaEventRecord(fed, sq)) != cudaSuccess) break;
-                cudaStream_t acc_streams[4] = {sq, pipe2, pipe3, pipe4};
-                if ((err = cudaStreamWaitEvent(pipe, fed, 0)) != cudaSuccess) break;
-                for (int j = 1; j < 4 && err == cudaSuccess; j++) err = cudaStreamWaitEvent(acc_streams[j], fed, 0);
-                if (err != cudaSuccess) break;
-                const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
+                trace.mark("sorted", q, ss);
+            } else if (windowed_pipe) {
+                // windowed plan: window w+1 is scattered while window w is accumulated
                 const uint32_t blocks = (p.segs_ps + acc_threads - 1) / acc_threads;
                 for (uint32_t w = 0; w < p.windows && err == cudaSuccess; w++) {
-                    k_scatter<<<dim3(w ? std::min(sblocks, side_ctas / 2) : sblocks, 1), 256, 0, pipe>>>((const uint16_t *)codes_q, nq, p.nb, w, cursor_q, sorted_q);
-                    if ((err = cudaEventRecord(sorted_ev, pipe)) != cudaSuccess) break;
-                    cudaStream_t sa = acc_streams[w & 3];
-                    if ((err = cudaStreamWaitEvent(sa, sorted_ev, 0)) != cudaSuccess) break;
+                    k_scatter<<<dim3(w ? std::min(sblocks, side_ctas / 2) : sblocks, 1), 256, 0, ss>>>((const uint16_t *)codes_q, nq, p.nb, w, cursor_q, sorted_q);
+                    cudaStream_t sa = acc_streams[acc_launch++ & 3];
+                    if ((err = hand_over(sa)) != cudaSuccess) break;
                     if (w == 0) tm.mark();
                     if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, 1, w, slots_q);
                     else k_accumulate<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, 1, w, slots_q);
                 }
-                if (err != cudaSuccess) break;
-                for (int j = 1; j < 4 && err == cudaSuccess; j++) {
-                    if ((err = cudaEventRecord(aux_done, acc_streams[j])) != cudaSuccess) break;
-                    err = cudaStreamWaitEvent(sq, aux_done, 0);
-                }
-                if (err != cudaSuccess) break;
-                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sq>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
+            } else {
+                if (p.folded) k_scatter_tiled<<<dim3(beside ? std::max<uint32_t>(1, scat_blocks / p.phases) : scat_blocks, p.phases), 256, 0, ss>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, 0, cursor_q, sorted_q);
+                else k_scatter<<<dim3(sblocks, p.windows), 256, 0, ss>>>((const uint16_t *)codes_q, nq, p.nb, 0, cursor_q, sorted_q);
                 tm.mark();
-                err = cudaGetLastError();
-                continue;
-            } else if (p.folded) {
-                k_scatter_tiled<<<dim3(cta_cap < 148 * 8 ? std::max<uint32_t>(1, scat_blocks / p.phases) : scat_blocks, p.phases), 256, 0, sq>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, 0, cursor_q, sorted_q);
-            } else k_scatter<<<dim3(sblocks, p.windows), 256, 0, sq>>>((const uint16_t *)codes_q, nq, p.nb, 0, cursor_q, sorted_q);
-            tm.mark();
-            trace.mark("sorted", q, sq);
-            if (aux) {
-                if ((err = cudaEventRecord(sorted_ev, sq)) != cudaSuccess) break;
-                if ((err = cudaStreamWaitEvent(sa, sorted_ev, 0)) != cudaSuccess) break;
-            }
-            {
-                // 12-limb fields (186 registers per thread): 64-thread CTAs fit 5 per SM (10 warps) where 128-thread ones fit 2 (8 warps)
-                const uint32_t acc_threads = C::Fq::N > 8 ? 64 : ACC_THREADS;
+                trace.mark("sorted", q, ss);
+                cudaStream_t sa = multi ? acc_streams[acc_launch++ & 3] : stream;
+                if ((err = hand_over(sa)) != cudaSuccess) break;
                 const uint64_t threads = (uint64_t)p.sets * p.segs_ps;
                 const uint32_t blocks = (uint32_t)((threads + acc_threads - 1) / acc_threads);
+                // 12-limb fields: 64-thread CTAs fit 5-6 per SM (10-12 warps) where 128-thread ones fit 2 (8 warps)
                 if (C::Fq::N > 8) k_accumulate_wide<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, 0, slots_q);
                 else k_accumulate<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, p.sets, 0, slots_q);
-                k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, sa>>>(slots_q, offsets_q, big_count_q, big_list_q, p.nb, p.seg_len, p.segs_ps);
+                trace.mark("accumulated", q, sa);
             }
-            tm.mark();
-            trace.mark("accumulated", q, sa);
-            err = cudaGetLastError();
+            if (err == cudaSuccess) err = cudaGetLastError();
         }
         if (err != cudaSuccess) break;
-        if (aux) {      // (every sort was waited for by its accumulation, so joining aux2 joins aux as well)
-            if ((err = cudaEventRecord(aux_done, aux2)) != cudaSuccess) break;
-            if ((err = cudaStreamWaitEvent(stream, aux_done, 0)) != cudaSuccess) break;
+        if (multi) {      // join the accumulation streams (every scatter was waited for by an accumulation, so this joins side0 as well)
+            for (int j = 1; j < 4 && err == cudaSuccess; j++) {
+                if ((err = cudaEventRecord(aux_done, acc_streams[j])) != cudaSuccess) break;
+                err = cudaStreamWaitEvent(stream, aux_done, 0);
+            }
+            if (err != cudaSuccess) break;
         }
+        for (uint32_t q = 0; q < p.chunks; q++) {
+            const size_t set0 = (size_t)q * p.sets;
+            k_reduce_big<C><<<148 * 2, BIG_THREADS, 0, stream>>>(slots + set0 * slot_stride, offsets + set0 * (p.nb + 1), big_counts + q, big_list + set0 * p.nb, p.nb, p.seg_len, p.segs_ps);
+        }
+        tm.mark();
+        trace.mark("accumulated", p.chunks, stream);
         uint32_t log2m = 0; while ((1u << log2m) < p.chunk) log2m++;
         {
             const uint32_t threads = p.sets * p.chunks_ps;
@@ -1094,25 +1082,15 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
         err = cudaGetLastError();
     } while (0);
     if (err == cudaSuccess) trace.report(stream);
-    if (err != cudaSuccess && (pipelined || pipelined_w)) {
-        cudaGetLastError();
-        cudaEvent_t join = nullptr;
-        if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess) {
-            if (cudaEventRecord(join, pipe) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
-            if (cudaEventRecord(join, pipe2) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
-            if (cudaEventRecord(join, pipe3) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
-            if (cudaEventRecord(join, pipe4) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
-            cudaEventDestroy(join);
-        }
-    }
-    if (err != cudaSuccess && (aux || uploading)) {
+    if (err != cudaSuccess && (multi || uploading)) {
         // error after work was queued on the side streams: they may still touch the workspace / the staged scalars, so `stream` (on which
-        // both are freed in stream order) has to wait for them first.  On the success path aux_done and the consumers of `fed` did that.
+        // both are freed in stream order) has to wait for them first.  On the success path the joins above did that.
         cudaGetLastError();
         cudaEvent_t join = nullptr;
         if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess) {
-            if (aux && cudaEventRecord(join, aux) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
-            if (aux2 && cudaEventRecord(join, aux2) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            if (multi && cudaEventRecord(join, side0) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            if (multi && sdig != side0 && cudaEventRecord(join, sdig) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
+            for (int j = 1; j < 4 && multi; j++) if (cudaEventRecord(join, acc_streams[j]) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
             if (uploading && cudaEventRecord(join, feed->copy_stream) == cudaSuccess) cudaStreamWaitEvent(stream, join, 0);
             cudaEventDestroy(join);
         }
