@@ -1,0 +1,8 @@
+#!/bin/bash
+# after the streamed-scalar rework: GPU suite, smoke, bench (N = 1)
+set -u
+OUT=gpurun_out; mkdir -p $OUT
+( time python -m pytest tests -m gpu -x -q ) > $OUT/r2_pytest_final.log 2>&1; echo "pytest rc=$?"; tail -4 $OUT/r2_pytest_final.log
+python -c "import __graft_entry__ as g; g.smoke()" > $OUT/r2_smoke_final.log 2>&1; echo "smoke rc=$?"; tail -1 $OUT/r2_smoke_final.log
+python bench.py > $OUT/r2_bench_final.json 2> $OUT/r2_bench_final.err; echo "bench rc=$?"; cut -c1-300 $OUT/r2_bench_final.json
+python profiles/scripts/streamed_times.py 26 0
