@@ -52,12 +52,12 @@ struct MsmPlan {
 MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_override, uint32_t seg_override, size_t table_budget = ~(size_t)0,
                       uint32_t chunks = 1, uint32_t class_log2 = 0);
 
-// How a chunked pipeline is fed: host_scalars != nullptr: chunk q is uploaded on copy_stream right before its kernels are queued;
-// aux_stream != nullptr: odd chunks run on it, so that one chunk's sort overlaps the previous chunk's accumulation.
-// aux2_stream (with aux_stream, one resident chunk, several scatter ranges): the scatter of bucket range r+1 runs on aux_stream while range r
-// is accumulated; the accumulation launches rotate over the caller's stream and aux2 .. aux4_stream.
-// dig_stream (high priority like aux_stream): digits and scan of the chunks of a streamed MSM, so that chunk q+1 is recoded as it arrives while chunk q's
-// ranges are still being scattered on aux_stream.
+// The library's per-device side streams and, for a streamed MSM, where the scalars come from (msm_impl.cuh: "streams by role").
+//   host_scalars / dev_scalars / copy_stream   scalars still in host memory: uploaded chunk by chunk (sub-chunk by sub-chunk) on copy_stream
+//   aux_stream   (high priority) the scatters: bucket range by bucket range (table plan), window by window (windowed plan)
+//   dig_stream   (high priority) digits + scan of the chunks of a streamed MSM, so that chunk q+1 is recoded as it arrives while chunk q's
+//                ranges are still being scattered
+//   aux2 .. aux4_stream   with the caller's stream, the four streams the accumulation launches rotate over
 struct MsmFeed { const void *host_scalars; void *dev_scalars; cudaStream_t copy_stream; cudaStream_t aux_stream; cudaStream_t aux2_stream; cudaStream_t aux3_stream; cudaStream_t aux4_stream; cudaStream_t dig_stream; };
 
 // Per-stage device timings (ms) filled when msm_run is called with timings != nullptr (adds event syncs;

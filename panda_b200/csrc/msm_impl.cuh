@@ -866,9 +866,9 @@ struct TraceLog {
 };
 
 // Runs the pipeline described by `p`.  `points` is the caller's bases (windowed) or the precomputed table (folded).
-// feed != nullptr: chunked run.  With feed->host_scalars the scalars are still in host memory and chunk q is uploaded on
-// feed->copy_stream right before chunk q's kernels are queued (the upload of chunk q+1 overlaps the work on chunk q); with
-// feed->aux_stream odd chunks run on that stream, staggered so that a chunk sorts while the previous one accumulates.
+// feed == nullptr: everything on `stream`, one launch per stage.  feed != nullptr brings the library's side streams (see the comment on the
+// stream roles below) and, with feed->host_scalars, scalars that are still in host memory: chunk q is uploaded on feed->copy_stream in
+// sub-chunks while the chunks before it are being sorted and accumulated.
 template <class C>
 cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *scalars, void *result, CoordType coord, cudaMemPool_t pool,
                            cudaStream_t stream, MsmStageTimes *timings, const MsmFeed *feed) {
