@@ -70,7 +70,7 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.table_n = n;
     p.folded = folded ? 1 : 0;
     p.class_log2 = class_log2;
-    const uint32_t c_lo = 8, c_hi = folded ? 23 : 16;          // windowed digit codes are 16 bit
+    const uint32_t c_lo = 8, c_hi = folded ? 23 : 20;
     uint32_t best_c = 0;
     double best = 1e300;
     for (uint32_t c = c_lo; c <= c_hi; c++) {
@@ -183,7 +183,7 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     p.off_cursor = off;  off = align(off + phys * p.nb * 4);
     p.off_biglist = off; off = align(off + phys * p.nb * 4);
     p.off_tiles = off;   off = align(off + phys * ((p.nb + 4095) / 4096) * 4);
-    p.off_digits = off;  off = align(off + (folded ? (size_t)p.chunks * p.codes_stride * 4 : (size_t)p.windows * n * 2));
+    p.off_digits = off;  off = align(off + (folded ? (size_t)p.chunks * p.codes_stride * 4 : (size_t)p.windows * n * 4));
     p.off_heads = off;   off = align(off + (size_t)p.chunks * p.heads_stride * 2);
     p.off_sorted = off;  off = align(off + phys * p.stride * 4);
     p.off_slots = off;   off = align(off + phys * ((size_t)p.segs_ps + p.nb) * 4 * fq_bytes);

@@ -28,7 +28,6 @@ struct Bls381 {
     static constexpr int SCALAR_BITS = 255;
 };
 
-static constexpr uint32_t DIGIT_SKIP = 0xFFFFu;     // digit 0: contributes nothing
 static constexpr int ACC_THREADS = 128;
 #ifndef PANDA_ACC_MAXNREG
 #define PANDA_ACC_MAXNREG 128     // k_accumulate_range: 4 CTAs per SM (16 warps); 136 (3 CTAs, room for a side-stream CTA beside them) measured 29.15 vs 28.38 ms at 2^24
@@ -73,19 +72,14 @@ PB_DEV void for_each_digit(const Fr &s, uint32_t c, uint32_t W, uint32_t wide, F
     if (w < W) emit((uint32_t)buf);        // the top window takes whatever is left (W * c covers the scalar width)
 }
 
-// K1: scalars -> per-bucket counts and the digit codes, window-major (code[w*n + i]).
-// Windowed: 16-bit codes (|d|-1, sign in bit 15), 0xFFFF = zero digit.  FOLDED (precomputed 2^(c*j) * P tables, every
-// window feeds the single bucket set, c up to 23): 32-bit codes (|d|-1, sign in bit 31), 0xFFFFFFFF = zero digit.
-// HBM / L2-atomic bound: 32 B read + 2W (4W) B written per scalar, W reductions into an L2-resident histogram.
+// K1 (windowed plan): scalars -> per-bucket counts and the digit codes, window-major (code[w*n + i]): |d|-1 with the sign in bit 31,
+// 0xFFFFFFFF = zero digit.  (32-bit codes since the windows may be wider than 16 bits: at 2^24 c = 17 saves a window.)
+// L2-atomic bound: 32 B read + 4W B written per scalar, W reductions into an L2-resident histogram.
 static constexpr uint32_t CODE_SKIP32 = 0xFFFFFFFFu;
-template <class C, bool FOLDED>
+template <class C>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t wide, uint32_t nb,
-                                                uint32_t class_log2, uint32_t class_index, void *__restrict__ codes_out, uint32_t *__restrict__ counts) {
+                                                uint32_t class_log2, uint32_t class_index, uint32_t *__restrict__ codes, uint32_t *__restrict__ counts) {
     using Fr = typename C::Fr;
-    using Code = typename std::conditional<FOLDED, uint32_t, uint16_t>::type;
-    Code *codes = static_cast<Code *>(codes_out);
-    constexpr Code SKIP = FOLDED ? (Code)CODE_SKIP32 : (Code)DIGIT_SKIP;
-    constexpr int SIGN_BIT = FOLDED ? 31 : 15;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Fr s = Fr::load(scalars + (size_t)i * Fr::N).from_mont();     // canonical integer; the input is left untouched
         uint32_t next_w = 0;
@@ -94,12 +88,12 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
             // bucket-class shard: only the buckets congruent to class_index survive, renumbered 0 .. nb-1 (bucket = local * 2^class_log2 + class_index)
             if (((mag - 1) & class_mask) != class_index) return;
             const uint32_t local = (mag - 1) >> class_log2;
-            for (; next_w < w; next_w++) codes[(size_t)next_w * n + i] = SKIP;
-            codes[(size_t)w * n + i] = (Code)(local | (neg << SIGN_BIT));
+            for (; next_w < w; next_w++) codes[(size_t)next_w * n + i] = CODE_SKIP32;
+            codes[(size_t)w * n + i] = local | (neg << 31);
             next_w = w + 1;
-            atomicAdd(&counts[(FOLDED ? (size_t)0 : (size_t)w * nb) + local], 1u);
+            atomicAdd(&counts[(size_t)w * nb + local], 1u);
         });
-        for (; next_w < W; next_w++) codes[(size_t)next_w * n + i] = SKIP;
+        for (; next_w < W; next_w++) codes[(size_t)next_w * n + i] = CODE_SKIP32;
     }
 }
 
@@ -190,17 +184,17 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32
 
 // K3 (windowed): scatter point indices (digit sign in bit 31) into their bucket's range.  blockIdx.y = window, so one window's
 // 4n-byte output range is being filled at a time and stays in L2 while it is written.
-static __global__ void __launch_bounds__(256) k_scatter(const uint16_t *__restrict__ digits, uint32_t n, uint32_t nb, uint32_t w0,
+static __global__ void __launch_bounds__(256) k_scatter(const uint32_t *__restrict__ codes, uint32_t n, uint32_t nb, uint32_t w0,
                                                         uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
     const uint32_t w = w0 + blockIdx.y;             // the pipelined driver launches one window at a time (gridDim.y = 1)
-    const uint16_t *dw = digits + (size_t)w * n;
+    const uint32_t *dw = codes + (size_t)w * n;
     uint32_t *kw = cursor + (size_t)w * nb;
     uint32_t *sw = sorted + (size_t)w * n;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t code = dw[i];
-        if (code == DIGIT_SKIP) continue;
-        const uint32_t pos = atomicAdd(&kw[code & 0x7FFFu], 1u);
-        sw[pos] = i | ((code >> 15) << 31);
+        if (code == CODE_SKIP32) continue;
+        const uint32_t pos = atomicAdd(&kw[code & 0x7FFFFFFFu], 1u);
+        sw[pos] = i | (code & 0x80000000u);
     }
 }
 
@@ -970,7 +964,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                     const uint32_t tblocks = std::min<uint32_t>((t1 - t0 + TILE_PTS - 1) / TILE_PTS, digit_cap);
                     k_digits_tiled<C><<<tblocks, TILE_PTS, sh_bytes, sq>>>(sc + (size_t)t0 * 8, t1 - t0, p.c, p.windows, p.wide, log2_span, p.phases, p.class_log2, p.class_index,
                                                                           (uint32_t *)codes_q + (size_t)tile0 * TILE_PTS * p.windows, heads_q + (size_t)tile0 * (p.phases + 1), counts_q);
-                } else k_digits<C, false><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, codes_q, counts_q);
+                } else k_digits<C><<<sblocks, 256, 0, sq>>>(sc, nq, p.c, p.windows, p.wide, p.nb, p.class_log2, p.class_index, (uint32_t *)codes_q, counts_q);
             }
             if (err != cudaSuccess) break;
             tm.mark();
@@ -1017,7 +1011,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                 // windowed plan: window w+1 is scattered while window w is accumulated
                 const uint32_t blocks = (p.segs_ps + acc_threads - 1) / acc_threads;
                 for (uint32_t w = 0; w < p.windows && err == cudaSuccess; w++) {
-                    k_scatter<<<dim3(w ? std::min(sblocks, side_ctas / 2) : sblocks, 1), 256, 0, ss>>>((const uint16_t *)codes_q, nq, p.nb, w, cursor_q, sorted_q);
+                    k_scatter<<<dim3(w ? std::min(sblocks, side_ctas / 2) : sblocks, 1), 256, 0, ss>>>((const uint32_t *)codes_q, nq, p.nb, w, cursor_q, sorted_q);
                     cudaStream_t sa = acc_streams[acc_launch++ & 3];
                     if ((err = hand_over(sa)) != cudaSuccess) break;
                     if (w == 0) tm.mark();
@@ -1026,7 +1020,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                 }
             } else {
                 if (p.folded) k_scatter_tiled<<<dim3(beside ? std::max<uint32_t>(1, scat_blocks / p.phases) : scat_blocks, p.phases), 256, 0, ss>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, 0, cursor_q, sorted_q);
-                else k_scatter<<<dim3(sblocks, p.windows), 256, 0, ss>>>((const uint16_t *)codes_q, nq, p.nb, 0, cursor_q, sorted_q);
+                else k_scatter<<<dim3(sblocks, p.windows), 256, 0, ss>>>((const uint32_t *)codes_q, nq, p.nb, 0, cursor_q, sorted_q);
                 tm.mark();
                 trace.mark("sorted", q, ss);
                 cudaStream_t sa = multi ? acc_streams[acc_launch++ & 3] : stream;

@@ -68,7 +68,7 @@ def test_msm_plan_selection():
         for k in list(range(0, 27)):
             assert ffi.lib.panda_debug_msm_plan(curve, 1 << k, 0, 0, 0, C.byref(p)) == 0
             c, W, nb = p.window_bits, p.windows, p.buckets_per_window
-            assert 8 <= c <= 16 and nb == 1 << (c - 1) and W <= 32
+            assert 8 <= c <= 20 and nb == 1 << (c - 1) and W <= 32
             # signed digits: the windows below the top one cover (W-1)*c bits, the top window (no recoding) must hold the
             # remaining bits plus a carry without exceeding the bucket count
             top_bits = bits - (W - 1) * c
@@ -76,7 +76,7 @@ def test_msm_plan_selection():
             assert p.segment_len >= 8 and p.segments_per_window == -(-(1 << k) // p.segment_len)
             assert nb % p.reduce_chunk == 0
     ffi.lib.panda_debug_msm_plan(0, 1 << 24, 0, 0, 0, C.byref(p))
-    assert (p.window_bits, p.windows, p.folded, p.bucket_sets) == (16, 16, 0, 16)
+    assert (p.window_bits, p.windows, p.folded, p.bucket_sets) == (17, 15, 0, 15)      # 32-bit digit codes: windows wider than 16 bits are allowed
     ffi.lib.panda_debug_msm_plan(0, 1 << 20, 0, 13, 32, C.byref(p))      # overrides are honoured
     assert (p.window_bits, p.segment_len) == (13, 32)
     # folded plans (precomputed 2^(c*j)*P tables): one bucket set, table index + sign fit 32 bits
