@@ -28,6 +28,17 @@ struct Bls381 {
     static constexpr int SCALAR_BITS = 255;
 };
 
+// -DPANDA_BOUNDS_CHECK=1 (the pool's GPUs refuse compute-sanitizer): every index the sort / accumulation kernels compute into the workspace is
+// checked against its array's capacity and a violation traps; the GPU suite is run once per round against a library built this way
+// (profiles/scripts/r2_bounds_check.sh).  Compiled out of the product.
+#ifndef PANDA_BOUNDS_CHECK
+#define PANDA_BOUNDS_CHECK 0
+#endif
+#if PANDA_BOUNDS_CHECK
+#define PB_CHECK(cond, what) do { if (!(cond)) { printf("[panda-b200] bounds check failed: %s (block %u thread %u)\n", what, blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define PB_CHECK(cond, what) do { } while (0)
+#endif
 static constexpr int ACC_THREADS = 128;
 #ifndef PANDA_ACC_MAXNREG
 #define PANDA_ACC_MAXNREG 128     // k_accumulate_range: 4 CTAs per SM (16 warps); 136 (3 CTAs, room for a side-stream CTA beside them) measured 29.15 vs 28.38 ms at 2^24
@@ -89,6 +100,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
             if (((mag - 1) & class_mask) != class_index) return;
             const uint32_t local = (mag - 1) >> class_log2;
             for (; next_w < w; next_w++) codes[(size_t)next_w * n + i] = CODE_SKIP32;
+            PB_CHECK(w < W && local < nb, "k_digits: digit");
             codes[(size_t)w * n + i] = local | (neg << 31);
             next_w = w + 1;
             atomicAdd(&counts[(size_t)w * nb + local], 1u);
@@ -193,7 +205,9 @@ static __global__ void __launch_bounds__(256) k_scatter(const uint32_t *__restri
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t code = dw[i];
         if (code == CODE_SKIP32) continue;
+        PB_CHECK((code & 0x7FFFFFFFu) < nb, "k_scatter: bucket");
         const uint32_t pos = atomicAdd(&kw[code & 0x7FFFFFFFu], 1u);
+        PB_CHECK(pos < n, "k_scatter: position in the sorted list");
         sw[pos] = i | (code & 0x80000000u);
     }
 }
@@ -246,6 +260,7 @@ __global__ void __launch_bounds__(TILE_PTS) k_digits_tiled(const uint32_t *__res
             uint32_t code = CODE_SKIP32;
             if (mag && ((mag - 1) & class_mask) == class_index) {      // bucket-class shard: only the buckets congruent to class_index survive, renumbered
                 const uint32_t b = (mag - 1) >> class_log2;
+                PB_CHECK((b >> log2_span) < ranges, "k_digits_tiled: bucket");
                 atomicAdd(&counts[b], 1u);
                 cnt[(b >> log2_span) * TILE_PTS + tid]++;
                 code = (neg << 31) | b;
@@ -285,6 +300,7 @@ __global__ void __launch_bounds__(TILE_PTS) k_digits_tiled(const uint32_t *__res
             if (code == CODE_SKIP32) continue;
             const uint32_t b = code & 0x7FFFFFFFu, r = b >> log2_span;
             const uint32_t pos = base[r] + cnt[r * TILE_PTS + tid]++;
+            PB_CHECK(pos < TILE_PTS * W && r < ranges, "k_digits_tiled: tile position");
             out[pos] = (code & 0x80000000u) | ((w * TILE_PTS + tid) << TILE_ID_SHIFT) | (b & span_mask);
         }
         __syncthreads();
@@ -299,7 +315,7 @@ __global__ void __launch_bounds__(TILE_PTS) k_digits_tiled(const uint32_t *__res
 // K3 (table plan): bucket range(s) first_range + blockIdx.y; a warp per tile walks the tile's slice for the range -- every code is placed.
 static __global__ void __launch_bounds__(256) k_scatter_tiled(const uint32_t *__restrict__ codes, const uint16_t *__restrict__ heads, uint32_t nq, uint32_t W,
                                                               uint32_t n_total, uint32_t point0, uint32_t log2_span, uint32_t ranges, uint32_t first_range,
-                                                              uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+                                                              uint32_t capacity, uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
     const uint32_t r = first_range + blockIdx.y;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -308,12 +324,15 @@ static __global__ void __launch_bounds__(256) k_scatter_tiled(const uint32_t *__
     for (uint32_t tile = warp_g; tile < tiles; tile += nwarps) {
         const uint16_t *h = heads + (size_t)tile * (ranges + 1) + r;
         const uint32_t h0 = h[0], h1 = h[1];
+        PB_CHECK(h0 <= h1 && h1 <= TILE_PTS * W && r < ranges, "k_scatter_tiled: tile header");
         const uint32_t *src = codes + (size_t)tile * TILE_PTS * W;
         const uint32_t entry0 = point0 + tile * TILE_PTS;
         auto place = [&](uint32_t code) {
             const uint32_t id = (code >> TILE_ID_SHIFT) & 0x1FFFu;
             const uint32_t entry = (id >> 8) * n_total + entry0 + (id & 255u);
+            PB_CHECK((id >> 8) < W && entry0 + (id & 255u) < point0 + nq, "k_scatter_tiled: code");
             const uint32_t pos = atomicAdd(&cursor[bucket0 | (code & span_mask)], 1u);
+            PB_CHECK(pos < capacity, "k_scatter_tiled: position in the sorted list");
             sorted[pos] = entry | (code & 0x80000000u);
         };
         uint32_t k = h0 + lane;
@@ -357,7 +376,7 @@ PB_DEV void accumulate_segment(const uint8_t *__restrict__ bases, const uint32_t
         if (pos >= next_bd) {          // bucket boundary: emit the finished partial, skip empty buckets
             acc.store(slot_s + (size_t)b * Pt::BYTES);
             acc = Pt::identity();
-            do { b++; next_bd = __ldg(ow + b + 1); } while (pos >= next_bd);
+            do { b++; PB_CHECK(b < b_hi, "accumulate: bucket walk"); next_bd = __ldg(ow + b + 1); } while (pos >= next_bd);
         }
         if (p.is_identity()) continue; // affine identity <=> x == 0 (affine.cuh:72-75)
         if (e >> 31) p.y = p.y.neg();
@@ -999,7 +1018,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                     const double share = ((double)p.wide + (r < ranges / 2 || ranges == 1 ? 2.0 * (p.windows - p.wide) : 0.0)) / ((double)p.windows * ranges);
                     const uint32_t blocks = std::min<uint32_t>(all_blocks, (uint32_t)((double)all_blocks * share * 1.03) + 8);
                     const uint32_t grid = (k == 0 && q == 0) ? scat_blocks : std::min(scat_blocks, chunked ? side_ctas : side_ctas / 2);
-                    k_scatter_tiled<<<dim3(grid, 1), 256, 0, ss>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, r, cursor_q, sorted_q);
+                    k_scatter_tiled<<<dim3(grid, 1), 256, 0, ss>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, r, p.stride, cursor_q, sorted_q);
                     cudaStream_t sa = acc_streams[acc_launch++ & 3];
                     if ((err = hand_over(sa)) != cudaSuccess) break;
                     if (k == 0) { tm.mark(); trace.mark("first range", q, sa); }   // "scatter" = the exposed first range
@@ -1019,7 +1038,7 @@ cudaError_t msm_pipeline_t(const MsmPlan &p, const void *points, const void *sca
                     else k_accumulate<C><<<blocks, acc_threads, 0, sa>>>((const uint8_t *)points, sorted_q, offsets_q, p.stride, p.nb, p.seg_len, p.segs_ps, 1, w, slots_q);
                 }
             } else {
-                if (p.folded) k_scatter_tiled<<<dim3(beside ? std::max<uint32_t>(1, scat_blocks / p.phases) : scat_blocks, p.phases), 256, 0, ss>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, 0, cursor_q, sorted_q);
+                if (p.folded) k_scatter_tiled<<<dim3(beside ? std::max<uint32_t>(1, scat_blocks / p.phases) : scat_blocks, p.phases), 256, 0, ss>>>((const uint32_t *)codes_q, heads_q, nq, p.windows, p.table_n, point0, log2_span, p.phases, 0, p.stride, cursor_q, sorted_q);
                 else k_scatter<<<dim3(sblocks, p.windows), 256, 0, ss>>>((const uint32_t *)codes_q, nq, p.nb, 0, cursor_q, sorted_q);
                 tm.mark();
                 trace.mark("sorted", q, ss);
