@@ -546,11 +546,27 @@ def run_own_arm(args):
             yin = sn.forward(xin).clone()
             tms["inverse"] = timed(lambda: sn.inverse(yin), 5, warm=3)
             xbytes = (1 << kk) // world * 32 * (world - 1) // world
+            # where the forward transform's time goes: events between its four steps, mean of 3 calls on this rank, max over ranks per step
+            # ("exchange" = the fused twiddle + transpose + peer-store kernel between its two symmetric-memory barriers, so it also holds
+            # the wait for the slowest peer)
+            phase_ms = {}
+            for _ in range(3):
+                marks = []
+                sn.forward(xin, marks=marks)
+                torch.cuda.synchronize()
+                for (_, e0), (name, e1) in zip(marks, marks[1:]):
+                    phase_ms[name] = phase_ms.get(name, 0.0) + e0.elapsed_time(e1) / 3
+            names = sorted(phase_ms)
+            pt = torch.tensor([phase_ms[k_] for k_ in names], dtype=torch.float64, device=dev)
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+            phase_ms = {k_: round(float(v), 4) for k_, v in zip(names, pt.tolist())}
             sharded_ntt = {"metric": "bn254_fr_ntt_2^26_sharded_latency", "log_n": kk, "gpus": world, "transport": sn.transport,
                            "forward_ms": tms["forward"], "inverse_ms": tms["inverse"], "dft_spot_checks": all_ok(ok_dft),
                            "spot_indices_per_rank": len(spots), "round_trip_ok": all_ok(ok_rt),
                            "exchange_bytes_per_gpu": xbytes,
-                           "exchange_GBps_lower_bound": xbytes / (tms["forward"] * 1e-3) / 1e9,
+                           "phase_ms": phase_ms,
+                           "exchange_GBps": ((1 << kk) // world * 32) / (phase_ms["exchange"] * 1e-3) / 1e9 if phase_ms.get("exchange") else None,
+                           "exchange_GBps_note": "bytes this GPU's exchange kernel reads (= writes, (N-1)/N of them over NVLink) / the exchange step's time",
                            "layout": "column blocks in, row blocks out (panda_b200/sharded_ntt.py)"}
             del sn, xin, y, yin
             torch.cuda.empty_cache()

@@ -89,7 +89,11 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
         // scatter kernels (measured at n = 2^21, t = 7: +0.6 ms, i.e. ~20 modmul-equivalents per scalar), ~2500 / 2^t per scalar.
         const int t = (int)bits - (int)(W - 1) * (int)c;
         const double hot = !folded && t > 0 && t < 20 ? (double)n * 2500.0 / (double)(1u << t) : 0.0;   // the table plan has no short window
-        const double cost = (double)n * W * 10.0 + (folded ? 1.0 : W) * nb * 3.5 * 14.0 * 2.0 + hot;
+        // Table plan, measured on the final kernels (profiles/r2_plan_sweep.md): bucket reduction + stitching cost ~0.55 ms + 1.07 ns per bucket
+        // beyond the first 2^17, i.e. 72 modmul-equivalents per bucket at the accumulation's 14.8 ps per product (2^21 points: c = 20 / W = 13
+        // 5.36 ms against 5.52 for c = 19 / W = 14, which the flat 98 per bucket preferred)
+        const double reduce_cost = folded ? 98.0 * std::min(nb, 131072.0) + 72.0 * std::max(0.0, nb - 131072.0) : W * nb * 3.5 * 14.0 * 2.0;
+        const double cost = (double)n * W * 10.0 + reduce_cost + hot;
         if (cost < best) { best = cost; best_c = c; }
     }
     if (!best_c) { p.c = 0; return p; }                         // no feasible plan (folded table would not fit)
@@ -148,6 +152,10 @@ MsmPlan msm_make_plan(CurveId curve, uint32_t n, bool folded, uint32_t c_overrid
     // small bucket sets: the stitching is a chain of ~60 dependent point additions per level (0.55 ms), so folding up to 8 buckets per
     // thread is worth it when it brings a set down to 32 groups of 1024 chunk sums (one stitch level instead of two; 16 per thread measured worse: 2^22 points, 1.77 vs 1.60 ms)
     if (p.nb / 8 <= 32768) m = std::max<uint32_t>(m, std::max<uint32_t>(1, p.nb / 32768));
+    {   // PANDA_MSM_REDUCE_CHUNK (tuning): buckets folded per thread of the bucket reduction
+        static const uint32_t forced_m = [] { const char *e = getenv("PANDA_MSM_REDUCE_CHUNK"); return e ? (uint32_t)atoi(e) : 0u; }();
+        if (forced_m) m = std::min<uint32_t>(pow2_floor(forced_m), p.nb);
+    }
     p.chunk = m;
     p.chunks_ps = p.nb / m;
     // at most one stitching CTA per SM over all sets (128 for one set): with 256 two of them share an SM and the latency-bound chains slow each other down

@@ -190,20 +190,35 @@ class ShardedNtt:
                 return t
         raise AssertionError("result pointer is none of the work buffers")
 
-    def forward(self, x, stream=None):
+    def forward(self, x, stream=None, marks=None):
         """x: this rank's column block (module docstring); never written.  Returns this rank's row block in a buffer owned by this
-        object (valid until the next forward / inverse call).  Work is queued on torch's current stream."""
+        object (valid until the next forward / inverse call).  Work is queued on torch's current stream.
+        marks: optional list; (phase name, CUDA event recorded on that stream at the END of the phase) pairs are appended to it, the first
+        one ("start") before any work -- how bench.py splits the transform's time into its four steps (CUDA devices only)."""
         l1, l2, lg, ops = self.l1, self.l2, self.lg, self.ops
         stream, ctx = self._stream(stream)
         if x.numel() != self.local_elems * 32:
             raise ValueError("shard size mismatch")
         A, B = self.buf_a, self.buf_b
+
+        def mark(name):
+            if marks is not None and self.device.type == "cuda":
+                ev = self.torch.cuda.Event(enable_timing=True)
+                ev.record(self.torch.cuda.current_stream(self.device))
+                marks.append((name, ev))
+
         with ctx:
+            mark("start")
             ops.exchange(x.data_ptr(), l1, l2 - lg, 0, None, 0, False, [A.data_ptr()], 1 << l1, 0, stream)            # 1. At[i2l][i1]
+            mark("transpose")
             p = self._pick(ops.batch_ntt(A.data_ptr(), B.data_ptr(), l1, 1 << (l2 - lg), self.omega_rows, False, stream))   # 2. Yt[i2l][j1]
+            mark("column_transforms")
             q = B if p is A else A
             z = self._exchange(p, q, l2 - lg, l1, False, stream)                                                       # 3. Z[j1l][i2]
-            return self._pick(ops.batch_ntt(z.data_ptr(), A.data_ptr(), l2, 1 << (l1 - lg), self.omega_cols, False, stream))  # 4. X[j1l][j2]
+            mark("exchange")
+            out = self._pick(ops.batch_ntt(z.data_ptr(), A.data_ptr(), l2, 1 << (l1 - lg), self.omega_cols, False, stream))  # 4. X[j1l][j2]
+            mark("row_transforms")
+            return out
 
     def inverse(self, y, stream=None):
         """y: this rank's row block (the layout forward() returns).  Returns the column block of (1/n) DFT_{omega^-1}."""

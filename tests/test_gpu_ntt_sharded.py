@@ -103,6 +103,13 @@ def test_sharded_ntt_one_rank(oracle, dev, k):
     back = sn.inverse(y)
     torch.cuda.synchronize()
     assert (back.cpu().numpy() == x).all()
+    # the per-step events bench.py reads (ntt_sharded.phase_ms): one mark per step, in order, after a "start" mark
+    marks = []
+    y2 = sn.forward(xin, marks=marks)
+    torch.cuda.synchronize()
+    assert [name for name, _ in marks] == ["start", "transpose", "column_transforms", "exchange", "row_transforms"]
+    assert all(a.elapsed_time(b) >= 0.0 for (_, a), (_, b) in zip(marks, marks[1:]))
+    assert (y2.cpu().numpy().reshape(n, 32) == full[row_block_indices(k, 0, 1)]).all()
 
 
 def _two_rank_worker(rank, world, port, k, transport, q):
