@@ -350,8 +350,10 @@ struct NttExchangeArgs {
 template <class P>
 __global__ void __launch_bounds__(256) k_ntt_exchange(const NttExchangeArgs a) {
     using F = Fe<P>;
-    constexpr uint32_t T = 16, TP = T + 1;
-    __shared__ uint32_t sm[F::N * T * TP];
+    // limb planes of T * TP words, padded so that the two 4-limb halves of an element sit 16 banks apart (the store phase reads them side by side)
+    constexpr uint32_t T = 16, TP = T + 1, LS = T * TP + 4;
+    static_assert(F::N == 8 && (4 * LS) % 32 == 16, "store phase: 16-byte halves of 32-byte elements");
+    __shared__ uint32_t sm[F::N * LS];
     const uint32_t rows = 1u << a.log_rows, cols = 1u << a.log_cols;
     const uint32_t tiles_c = (cols + T - 1) / T;
     const uint32_t r_base = (blockIdx.x / tiles_c) * T, c_base = (blockIdx.x % tiles_c) * T;
@@ -368,17 +370,23 @@ __global__ void __launch_bounds__(256) k_ntt_exchange(const NttExchangeArgs a) {
                     x = (x * tw).canon();
                 }
             }
-            sm_store(sm, T * TP, tc * TP + tr, x);
+            sm_store(sm, LS, tc * TP + tr, x);
         }
     }
     __syncthreads();
-    {
-        const uint32_t oc = threadIdx.x / T, orow = threadIdx.x % T;
+    // Store phase: a lane writes ONE 16-byte half of an element, so a warp's store instruction covers 512 contiguous bytes (16 elements of
+    // one output row).  With a whole 32-byte element per lane every instruction left 16-byte holes in its sectors -- harmless in local HBM
+    // (L2 merges the two instructions), but peer stores leave the GPU as they are issued and NVLink carried twice the packets, half empty.
+#pragma unroll
+    for (uint32_t pass = 0; pass < 2; pass++) {
+        const uint32_t e = (threadIdx.x >> 1) + pass * (T * T / 2), half = threadIdx.x & 1;
+        const uint32_t oc = e / T, orow = e % T;
         const uint32_t r = r_base + orow, c = c_base + oc;
         if (r < rows && c < cols) {
-            F x = sm_load<F>(sm, T * TP, oc * TP + orow);
+            const uint32_t *q = sm + (half * 4) * LS + oc * TP + orow;
+            const uint4 v = make_uint4(q[0], q[LS], q[2 * LS], q[3 * LS]);
             const uint32_t h = c >> a.log_part_cols, cl = c & ((1u << a.log_part_cols) - 1);
-            x.store(a.dst[h] + ((size_t)cl * a.ld + a.col_off + r) * F::N);
+            reinterpret_cast<uint4 *>(a.dst[h] + ((size_t)cl * a.ld + a.col_off + r) * F::N)[half] = v;
         }
     }
 }
