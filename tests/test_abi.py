@@ -85,6 +85,10 @@ def test_msm_plan_selection():
         assert p.folded == 1 and p.bucket_sets == 1 and p.windows * (1 << k) < 2 ** 31
         assert p.table_bytes == p.windows * (1 << k) * 64
         assert 254 - (p.windows - 1) * p.window_bits <= p.window_bits - 1
+    # the measured choices of the table plan at the bench's per-rank sizes (profiles/r2_plan_sweep.md): 2^21 .. 2^23 points c = 20 / W = 13, 2^24 c = 22 / W = 12
+    for k, want in ((20, (17, 15)), (21, (20, 13)), (22, (20, 13)), (23, (20, 13)), (24, (22, 12)), (26, (22, 12))):
+        assert ffi.lib.panda_debug_msm_plan(0, 1 << k, 1, 0, 0, C.byref(p)) == 0
+        assert (p.window_bits, p.windows) == want, (k, p.window_bits, p.windows)
 
 
 def test_host_api_fails_loudly_without_a_device():
