@@ -376,7 +376,8 @@ __global__ void __launch_bounds__(256) k_ntt_exchange(const NttExchangeArgs a) {
     __syncthreads();
     // Store phase: a lane writes ONE 16-byte half of an element, so a warp's store instruction covers 512 contiguous bytes (16 elements of
     // one output row).  With a whole 32-byte element per lane every instruction left 16-byte holes in its sectors -- harmless in local HBM
-    // (L2 merges the two instructions), but peer stores leave the GPU as they are issued and NVLink carried twice the packets, half empty.
+    // (L2 merges the two instructions), but peer stores leave the GPU as they are issued and NVLink carried twice the packets, half empty
+    // (2^26 on two GPUs: exchange step 1.85 -> 1.25 ms = the kernel's local time; plain local transpose 5.1 -> 5.7 TB/s).
 #pragma unroll
     for (uint32_t pass = 0; pass < 2; pass++) {
         const uint32_t e = (threadIdx.x >> 1) + pass * (T * T / 2), half = threadIdx.x & 1;
