@@ -347,47 +347,69 @@ struct NttExchangeArgs {
     unsigned lo_bits, log_n;
 };
 
+// A CTA takes NTT_XCHG_TILES 16 x 16 tiles along a row of tiles: thread (tr, tc) keeps its row and steps 16 columns at a time, so its twiddle
+// omega^(R * c) advances by the constant omega^(16 R) -- one product for the update instead of the two-level table's product and its two gathers:
+// (2 + (K - 1) + K) / K = 2.25 products per element for K = 4 where every element on its own took 3 (ncu on that form: FMA-heavy pipe 82 % of
+// elapsed, 10 stall cycles per issue on the math-pipe throttle -- product-bound).  All K elements of a thread are loaded up front and the tiles
+// leave through shared memory behind ONE barrier.
+static constexpr uint32_t NTT_XCHG_TILES = 4;
+
 template <class P>
 __global__ void __launch_bounds__(256) k_ntt_exchange(const NttExchangeArgs a) {
     using F = Fe<P>;
     // limb planes of T * TP words, padded so that the two 4-limb halves of an element sit 16 banks apart (the store phase reads them side by side)
-    constexpr uint32_t T = 16, TP = T + 1, LS = T * TP + 4;
+    constexpr uint32_t T = 16, TP = T + 1, LS = T * TP + 4, K = NTT_XCHG_TILES, TILE_WORDS = F::N * LS;
     static_assert(F::N == 8 && (4 * LS) % 32 == 16, "store phase: 16-byte halves of 32-byte elements");
-    __shared__ uint32_t sm[F::N * LS];
+    __shared__ uint32_t sm[K * TILE_WORDS];
     const uint32_t rows = 1u << a.log_rows, cols = 1u << a.log_cols;
-    const uint32_t tiles_c = (cols + T - 1) / T;
-    const uint32_t r_base = (blockIdx.x / tiles_c) * T, c_base = (blockIdx.x % tiles_c) * T;
-    {
-        const uint32_t tr = threadIdx.x / T, tc = threadIdx.x % T;
-        const uint32_t r = r_base + tr, c = c_base + tc;
-        if (r < rows && c < cols) {
-            F x = F::load(a.src + ((size_t)r * cols + c) * F::N);
-            if (a.t_lo) {
-                const uint64_t prod = (uint64_t)(a.row0 + r) * c;
-                const uint32_t ex = (uint32_t)(prod & (((uint64_t)1 << a.log_n) - 1));
-                if (ex) {
-                    F tw = F::load(a.t_hi + (size_t)(ex >> a.lo_bits) * F::N) * F::load(a.t_lo + (size_t)(ex & ((1u << a.lo_bits) - 1)) * F::N);
-                    x = (x * tw).canon();
-                }
-            }
-            sm_store(sm, LS, tc * TP + tr, x);
+    const uint32_t tiles_c = (cols + T * K - 1) / (T * K);
+    const uint32_t r_base = (blockIdx.x / tiles_c) * T, c_base0 = (blockIdx.x % tiles_c) * T * K;
+    const uint32_t tr = threadIdx.x / T, tc = threadIdx.x % T;
+    const uint32_t r_in = r_base + tr;
+    if (r_in < rows) {
+        F x[K];
+#pragma unroll
+        for (uint32_t j = 0; j < K; j++) {
+            const uint32_t c = c_base0 + j * T + tc;
+            if (c < cols) x[j] = F::load(a.src + ((size_t)r_in * cols + c) * F::N);
         }
+        if (a.t_lo) {
+            const uint32_t lo_mask = (1u << a.lo_bits) - 1;
+            const uint64_t n_mask = ((uint64_t)1 << a.log_n) - 1, R = (uint64_t)a.row0 + r_in;
+            auto power = [&](uint32_t ex) { return F::load(a.t_hi + (size_t)(ex >> a.lo_bits) * F::N) * F::load(a.t_lo + (size_t)(ex & lo_mask) * F::N); };
+            F tw = power((uint32_t)((R * (c_base0 + tc)) & n_mask));
+            const F step = power((uint32_t)((R * T) & n_mask));
+#pragma unroll
+            for (uint32_t j = 0; j < K; j++) {
+                if (c_base0 + j * T + tc < cols) x[j] = (x[j] * tw).canon();
+                if (j + 1 < K) tw = tw * step;
+            }
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < K; j++)
+            if (c_base0 + j * T + tc < cols) sm_store(sm + j * TILE_WORDS, LS, tc * TP + tr, x[j]);
     }
     __syncthreads();
     // Store phase: a lane writes ONE 16-byte half of an element, so a warp's store instruction covers 512 contiguous bytes (16 elements of
     // one output row).  With a whole 32-byte element per lane every instruction left 16-byte holes in its sectors -- harmless in local HBM
     // (L2 merges the two instructions), but peer stores leave the GPU as they are issued and NVLink carried twice the packets, half empty
     // (2^26 on two GPUs: exchange step 1.85 -> 1.25 ms = the kernel's local time; plain local transpose 5.1 -> 5.7 TB/s).
+#pragma unroll 1
+    for (uint32_t j = 0; j < K; j++) {
+        const uint32_t c_base = c_base0 + j * T;
+        if (c_base >= cols) break;
+        const uint32_t *tile = sm + j * TILE_WORDS;
 #pragma unroll
-    for (uint32_t pass = 0; pass < 2; pass++) {
-        const uint32_t e = (threadIdx.x >> 1) + pass * (T * T / 2), half = threadIdx.x & 1;
-        const uint32_t oc = e / T, orow = e % T;
-        const uint32_t r = r_base + orow, c = c_base + oc;
-        if (r < rows && c < cols) {
-            const uint32_t *q = sm + (half * 4) * LS + oc * TP + orow;
-            const uint4 v = make_uint4(q[0], q[LS], q[2 * LS], q[3 * LS]);
-            const uint32_t h = c >> a.log_part_cols, cl = c & ((1u << a.log_part_cols) - 1);
-            reinterpret_cast<uint4 *>(a.dst[h] + ((size_t)cl * a.ld + a.col_off + r) * F::N)[half] = v;
+        for (uint32_t pass = 0; pass < 2; pass++) {
+            const uint32_t e = (threadIdx.x >> 1) + pass * (T * T / 2), half = threadIdx.x & 1;
+            const uint32_t oc = e / T, orow = e % T;
+            const uint32_t r = r_base + orow, c = c_base + oc;
+            if (r < rows && c < cols) {
+                const uint32_t *q = tile + (half * 4) * LS + oc * TP + orow;
+                const uint4 v = make_uint4(q[0], q[LS], q[2 * LS], q[3 * LS]);
+                const uint32_t h = c >> a.log_part_cols, cl = c & ((1u << a.log_part_cols) - 1);
+                reinterpret_cast<uint4 *>(a.dst[h] + ((size_t)cl * a.ld + a.col_off + r) * F::N)[half] = v;
+            }
         }
     }
 }
@@ -644,7 +666,7 @@ cudaError_t ntt_exchange(NttField field, const void *d_src, unsigned log_rows, u
         a.t_lo = tab->d_tab + tab->layout.off_lo; a.t_hi = tab->d_tab + tab->layout.off_hi;
         a.lo_bits = tab->layout.lo_bits; a.log_n = log_n;
     }
-    const uint32_t tiles_r = ((1u << log_rows) + 15) / 16, tiles_c = ((1u << log_cols) + 15) / 16;
+    const uint32_t tiles_r = ((1u << log_rows) + 15) / 16, tiles_c = ((1u << log_cols) + 16 * NTT_XCHG_TILES - 1) / (16 * NTT_XCHG_TILES);
     k_ntt_exchange<Bn254Fr><<<tiles_r * tiles_c, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
